@@ -1,0 +1,196 @@
+// api.cu — context, error reporting and memory plumbing of libtfbs_cuda.so.
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tfbs_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes)
+{
+    if (s.bytes >= bytes && s.ptr) return TFBS_OK;
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.bytes = 0;
+    cudaError_t e = cudaMalloc(&s.ptr, bytes);
+    if (e != cudaSuccess) {
+        tfbs_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        s.ptr = nullptr;
+        cudaGetLastError();
+        return TFBS_ERR_NOMEM;
+    }
+    s.bytes = bytes;
+    return TFBS_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) flush_kernel(uint4 *p, size_t n16, uint32_t v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(v, v, v, v);
+}
+void free_scratch(tfbs_scratch &s)
+{
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.bytes = 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char *tfbs_last_error(void) { return g_err; }
+
+const char *tfbs_version(void) { return "discover_tfbs_b200 libtfbs_cuda 0.1 (sm_100a)"; }
+
+int tfbs_device_count(int *n)
+{
+    TFBS_REQUIRE(n, "tfbs_device_count: null argument");
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        tfbs_set_error("no CUDA device: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return TFBS_ERR_NO_DEVICE;
+    }
+    return TFBS_OK;
+}
+
+int tfbs_ctx_create(int device, tfbs_ctx **out)
+{
+    TFBS_REQUIRE(out, "tfbs_ctx_create: null argument");
+    int n = 0;
+    int rc = tfbs_device_count(&n);
+    if (rc) return rc;
+    if (n == 0) {
+        tfbs_set_error("no CUDA device visible; libtfbs_cuda has no CPU fallback");
+        return TFBS_ERR_NO_DEVICE;
+    }
+    TFBS_REQUIRE(device >= 0 && device < n, "tfbs_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    TFBS_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TFBS_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        tfbs_set_error("device %d is sm_%d%d; libtfbs_cuda is built for sm_100a (B200) only", device,
+                       prop.major, prop.minor);
+        return TFBS_ERR_NO_DEVICE;
+    }
+    tfbs_ctx *c = new tfbs_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        tfbs_set_error("tfbs_ctx_create: %s", cudaGetErrorString(e));
+        delete c;
+        return TFBS_ERR_CUDA;
+    }
+    *out = c;
+    return TFBS_OK;
+}
+
+int tfbs_ctx_destroy(tfbs_ctx *ctx)
+{
+    if (!ctx) return TFBS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scratch(ctx->dense_fwd);
+    free_scratch(ctx->dense_rev);
+    free_scratch(ctx->hits);
+    free_scratch(ctx->hit_count);
+    free_scratch(ctx->tracks);
+    free_scratch(ctx->sites);
+    free_scratch(ctx->misc);
+    free_scratch(ctx->flush);
+    free_scratch(ctx->thr);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TFBS_OK;
+}
+
+int tfbs_ctx_sync(tfbs_ctx *ctx)
+{
+    TFBS_REQUIRE(ctx, "tfbs_ctx_sync: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TFBS_OK;
+}
+
+int tfbs_last_kernel_ms(tfbs_ctx *ctx, float *ms)
+{
+    TFBS_REQUIRE(ctx && ms, "tfbs_last_kernel_ms: null argument");
+    *ms = ctx->last_ms;
+    return TFBS_OK;
+}
+
+int tfbs_last_kernel_launches(tfbs_ctx *ctx, int64_t *n)
+{
+    TFBS_REQUIRE(ctx && n, "tfbs_last_kernel_launches: null argument");
+    *n = ctx->last_launches;
+    return TFBS_OK;
+}
+
+int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n)
+{
+    TFBS_REQUIRE(ctx && n, "tfbs_total_kernel_launches: null argument");
+    *n = ctx->total_launches;
+    return TFBS_OK;
+}
+
+int tfbs_host_alloc(void **ptr, int64_t bytes)
+{
+    TFBS_REQUIRE(ptr && bytes >= 0, "tfbs_host_alloc: bad argument");
+    TFBS_CHECK_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return TFBS_OK;
+}
+
+int tfbs_host_free(void *ptr)
+{
+    if (ptr) TFBS_CHECK_CUDA(cudaFreeHost(ptr));
+    return TFBS_OK;
+}
+
+int tfbs_flush_l2(tfbs_ctx *ctx)
+{
+    TFBS_REQUIRE(ctx, "tfbs_flush_l2: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    int rc = tfbs_scratch_reserve(ctx->flush, bytes);
+    if (rc) return rc;
+    static uint32_t tick = 0;
+    flush_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint4 *)ctx->flush.ptr, bytes / 16, ++tick);
+    TFBS_CHECK_CUDA(cudaGetLastError());
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TFBS_OK;
+}
+
+int tfbs_device_free(tfbs_ctx *ctx, void *dev_ptr)
+{
+    TFBS_REQUIRE(ctx, "tfbs_device_free: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    if (dev_ptr) TFBS_CHECK_CUDA(cudaFree(dev_ptr));
+    return TFBS_OK;
+}
+
+int tfbs_device_download(tfbs_ctx *ctx, const void *dev_ptr, void *host, int64_t bytes)
+{
+    TFBS_REQUIRE(ctx && (bytes == 0 || (dev_ptr && host)) && bytes >= 0, "tfbs_device_download: bad argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bytes > 0) TFBS_CHECK_CUDA(cudaMemcpy(host, dev_ptr, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return TFBS_OK;
+}
+
+}  // extern "C"

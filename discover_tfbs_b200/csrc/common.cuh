@@ -1,0 +1,134 @@
+// common.cuh — shared declarations for libtfbs_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/tfbs_cuda.h"
+
+#define TFBS_SM_COUNT_FALLBACK 148
+
+void tfbs_set_error(const char *fmt, ...);
+
+#define TFBS_CHECK_CUDA(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            tfbs_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                      \
+            return _e == cudaErrorMemoryAllocation ? TFBS_ERR_NOMEM : TFBS_ERR_CUDA;        \
+        }                                                                                  \
+    } while (0)
+
+#define TFBS_REQUIRE(cond, ...)          \
+    do {                                 \
+        if (!(cond)) {                   \
+            tfbs_set_error(__VA_ARGS__); \
+            return TFBS_ERR_INVALID;     \
+        }                                \
+    } while (0)
+
+// Grow-only device scratch buffer.
+struct tfbs_scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct tfbs_ctx {
+    int device = 0;
+    int sm_count = TFBS_SM_COUNT_FALLBACK;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int64_t last_launches = 0;
+    int64_t total_launches = 0;
+    tfbs_scratch dense_fwd, dense_rev;  // dense scan outputs [M][pitch]
+    tfbs_scratch hits;                  // tfbs_hit[cap]
+    tfbs_scratch hit_count;             // unsigned long long + work counters
+    tfbs_scratch tracks;                // shape tracks [T][pitch]
+    tfbs_scratch sites;                 // shape sites out / args
+    tfbs_scratch misc;                  // small argument staging
+    tfbs_scratch flush;                 // >L2 buffer for tfbs_flush_l2
+    tfbs_scratch thr;                   // per-motif thresholds
+};
+
+struct tfbs_seq {
+    tfbs_ctx *ctx = nullptr;
+    int64_t n = 0;          // bases
+    int64_t n_words = 0;    // packed words allocated (padded, zero-filled past n)
+    int64_t n_mask = 0;     // mask words allocated (padded, all-ones past n)
+    uint32_t *packed = nullptr;
+    uint32_t *mask = nullptr;
+    void *staging = nullptr;   // device ASCII staging for tfbs_encode (host input)
+    size_t staging_bytes = 0;
+};
+
+// Motif library on device.
+struct tfbs_pwms {
+    tfbs_ctx *ctx = nullptr;
+    int32_t M = 0, Lmax = 0;
+    std::vector<int32_t> lens;       // host copy
+    std::vector<double> logodds;     // host copy [M][Lmax][4]
+    // exact matrices for re-scoring: double[M][2][TFBS_MAX_MOTIF_LEN][4] (strand 0 fwd, 1 revcomp)
+    double *exact = nullptr;
+    // fp32 k-mer LUTs (k = 3): per motif G[m] groups of 64 float2 (fwd, rev), concatenated
+    float2 *lut = nullptr;
+    int32_t *lut_off = nullptr;      // [M] offset in float2 units
+    int32_t *glen = nullptr;         // [M] packed (G << 8) | L
+    float *fslack = nullptr;         // [M] fp32 filter slack (upper bound of |fp32 - exact|)
+    std::vector<float> fslack_host;
+    int64_t lut_entries = 0;
+    int32_t Gmax = 0;
+};
+
+struct tfbs_shapes {
+    tfbs_ctx *ctx = nullptr;
+    int32_t T = 0;
+    std::vector<int32_t> kinds;
+    // tables re-indexed by the little-endian pentamer index used by the kernels:
+    // float[T][2][1024] on device
+    float *tables = nullptr;
+    int32_t *kinds_dev = nullptr;
+};
+
+int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
+
+// RAII-free timing helpers: bracket the kernels of one API call.
+static inline void tfbs_begin(tfbs_ctx *ctx)
+{
+    ctx->last_launches = 0;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+}
+static inline void tfbs_launched(tfbs_ctx *ctx, int n = 1)
+{
+    ctx->last_launches += n;
+    ctx->total_launches += n;
+}
+static inline int tfbs_end(tfbs_ctx *ctx)
+{
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev1);
+    if (e != cudaSuccess) {
+        tfbs_set_error("kernel execution failed: %s", cudaGetErrorString(e));
+        return TFBS_ERR_CUDA;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        tfbs_set_error("kernel launch failed: %s", cudaGetErrorString(e));
+        return TFBS_ERR_CUDA;
+    }
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return TFBS_OK;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ld_words_guard(const uint32_t *__restrict__ p, int64_t idx,
+                                                   int64_t n_words, uint32_t fill)
+{
+    return (idx >= 0 && idx < n_words) ? __ldg(p + idx) : fill;
+}
+#endif

@@ -1,0 +1,418 @@
+// scan.cu — (2) PWM log-odds sliding-window scan on both strands.
+//
+// Replaces Biopython PositionSpecificScoringMatrix.calculate/.search (Bio/motifs/matrix.py,
+// Bio/motifs/_pwm.c) — the scoring the north star names — and generalises the
+// reference's exact-match BLASTn candidate stage (utils.py:340-398, process_blast.sh:32).
+//
+// Arithmetic: the motif matrix and its reverse complement are folded on the host into 3-mer
+// look-up tables (64 entries per group of 3 columns, each entry the double sum of its <=3
+// log-odds values rounded once to fp32, fwd and rev packed as float2) so a window of length L
+// costs ceil(L/3) shared-memory loads for both strands.  The 6-bit LUT index is sliced straight
+// out of the 2-bit packed sequence held in registers.
+//   dense mode : fp32 accumulation, scores written for every (motif, start, strand).
+//   hits mode  : the same fp32 score is used only as a filter with a proven error slack; every
+//                candidate is re-scored left to right in double and cast to float, which is the
+//                oracle's arithmetic, so hit sets and scores are bit-exact.
+#include <algorithm>
+#include <cmath>
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kPosPerThread = 8;
+constexpr int kTile = kScanThreads * kPosPerThread;  // 2048 window starts per CTA
+constexpr int kTileWords = kTile / 16 + 4;           // + 48-base halo, rounded to 16 B
+constexpr int kTileMask = kTile / 32 + 4;
+constexpr int kMaxGroups = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
+
+struct ScanParams {
+    const uint32_t *packed;
+    const uint32_t *mask;
+    int64_t pitch;  // row pitch of the dense outputs (multiple of kTile)
+    const float2 *lut;
+    const int32_t *lut_off;
+    const int32_t *glen;
+    int32_t M;
+    float *out_fwd;
+    float *out_rev;
+    const float *thr_lo;  // filter threshold (thr - slack)
+    const float *thr;     // exact threshold
+    const double *exact;  // [M][2][32][4]
+    tfbs_hit *hits;
+    unsigned long long *hit_count;
+    unsigned long long cap;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Oracle arithmetic for one window: left-to-right double sum, cast to float, compare.
+__device__ __noinline__ void rescore_and_emit(const uint32_t *__restrict__ packed,
+                                              const double *__restrict__ exact,
+                                              const float *__restrict__ thr, tfbs_hit *hits,
+                                              unsigned long long *hit_count, unsigned long long cap,
+                                              int64_t gpos, int m, int strand, int L)
+{
+    const double *mat = exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+    double s = 0.0;
+    for (int j = 0; j < L; j++) {
+        const int64_t i = gpos + j;
+        const uint32_t code = (__ldg(packed + (i >> 4)) >> (2 * (i & 15))) & 3u;
+        s += __ldg(mat + j * 4 + code);
+    }
+    const float f = (float)s;
+    const bool hit = f >= __ldg(thr + m);
+    if (hit) {
+        // warp-aggregated compaction: one atomic per group of simultaneously hitting lanes
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(hit_count, (unsigned long long)g.size());
+        base = g.shfl(base, 0);
+        const unsigned long long slot = base + g.thread_rank();
+        if (slot < cap) {
+            tfbs_hit h;
+            h.pos = strand ? ~gpos : gpos;
+            h.motif = m;
+            h.score = f;
+            hits[slot] = h;
+        }
+    }
+}
+
+template <bool HITS>
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const ScanParams P)
+{
+    __shared__ __align__(16) uint32_t s_words[kTileWords];
+    __shared__ __align__(16) uint32_t s_mask[kTileMask];
+    __shared__ __align__(16) float2 s_lut[2][kMaxGroups * 64];
+
+    const int tid = threadIdx.x;
+    const int64_t tile_start = (int64_t)blockIdx.x * kTile;
+
+    // stage the tile (+halo) of packed words and mask words; the encoded buffer is padded by
+    // >= 8192 bases so these reads never leave the allocation
+    if (tid < kTileWords) s_words[tid] = __ldg(P.packed + (tile_start >> 4) + tid);
+    if (tid >= 128 && tid < 128 + kTileMask) s_mask[tid - 128] = __ldg(P.mask + (tile_start >> 5) + (tid - 128));
+
+    // prefetch LUT of motif 0
+    {
+        const int32_t gl = __ldg(P.glen + 0);
+        const int chunks = (gl >> 8) * 32;
+        const char *src = reinterpret_cast<const char *>(P.lut + __ldg(P.lut_off + 0));
+        for (int c = tid; c < chunks; c += kScanThreads)
+            cp_async16(reinterpret_cast<char *>(s_lut[0]) + c * 16, src + c * 16);
+        cp_async_commit();
+    }
+    __syncthreads();
+
+    // per-thread register window: 48 bases starting at the thread's first window start
+    const int p0 = tid * kPosPerThread;
+    uint32_t W0, W1, W2;
+    {
+        const int wi = p0 >> 4, sh = (p0 & 15) * 2;
+        const uint32_t a0 = s_words[wi], a1 = s_words[wi + 1], a2 = s_words[wi + 2], a3 = s_words[wi + 3];
+        W0 = __funnelshift_r(a0, a1, sh);
+        W1 = __funnelshift_r(a1, a2, sh);
+        W2 = __funnelshift_r(a2, a3, sh);
+    }
+    uint32_t inv_lo, inv_hi;  // invalid bits of bases p0 .. p0+63
+    {
+        const int mi = p0 >> 5, sh = p0 & 31;
+        const uint32_t m0 = s_mask[mi], m1 = s_mask[mi + 1], m2 = s_mask[mi + 2];
+        inv_lo = __funnelshift_r(m0, m1, sh);
+        inv_hi = __funnelshift_r(m1, m2, sh);
+    }
+
+    for (int m = 0; m < P.M; m++) {
+        const int buf = m & 1;
+        cp_async_wait_all();
+        __syncthreads();  // LUT m visible; everyone is done with LUT m-1 (buffer buf^1)
+        if (m + 1 < P.M) {
+            const int32_t gl = __ldg(P.glen + m + 1);
+            const int chunks = (gl >> 8) * 32;
+            const char *src = reinterpret_cast<const char *>(P.lut + __ldg(P.lut_off + m + 1));
+            for (int c = tid; c < chunks; c += kScanThreads)
+                cp_async16(reinterpret_cast<char *>(s_lut[buf ^ 1]) + c * 16, src + c * 16);
+        }
+        cp_async_commit();
+
+        const int32_t gl = __ldg(P.glen + m);
+        const int G = gl >> 8, L = gl & 255;
+        float accf[kPosPerThread], accr[kPosPerThread];
+#pragma unroll
+        for (int p = 0; p < kPosPerThread; p++) accf[p] = accr[p] = 0.f;
+        uint32_t w0 = W0, w1 = W1, w2 = W2;
+        const float2 *lg = s_lut[buf];
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+            for (int p = 0; p < kPosPerThread; p++) {
+                const uint32_t x = (w0 >> (2 * p)) & 63u;
+                const float2 v = lg[x];
+                accf[p] += v.x;
+                accr[p] += v.y;
+            }
+            lg += 64;
+            w0 = __funnelshift_r(w0, w1, 6);
+            w1 = __funnelshift_r(w1, w2, 6);
+            w2 >>= 6;
+        }
+        const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+        if (!HITS) {
+            const float qnan = __int_as_float(0x7FC00000);
+#pragma unroll
+            for (int p = 0; p < kPosPerThread; p++) {
+                const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
+                if (bad) accf[p] = accr[p] = qnan;
+            }
+            float4 *of = reinterpret_cast<float4 *>(P.out_fwd + (size_t)m * P.pitch + tile_start + p0);
+            float4 *orv = reinterpret_cast<float4 *>(P.out_rev + (size_t)m * P.pitch + tile_start + p0);
+            __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
+            __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
+            __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
+            __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
+        } else {
+            const float tlo = __ldg(P.thr_lo + m);
+#pragma unroll
+            for (int p = 0; p < kPosPerThread; p++) {
+                const bool cf = accf[p] >= tlo, cr = accr[p] >= tlo;
+                if (cf || cr) {
+                    const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
+                    if (!bad) {
+                        if (cf) rescore_and_emit(P.packed, P.exact, P.thr, P.hits, P.hit_count, P.cap, tile_start + p0 + p, m, 0, L);
+                        if (cr) rescore_and_emit(P.packed, P.exact, P.thr, P.hits, P.hit_count, P.cap, tile_start + p0 + p, m, 1, L);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+struct HitLess {
+    bool operator()(const tfbs_hit &a, const tfbs_hit &b) const
+    {
+        if (a.motif != b.motif) return a.motif < b.motif;
+        const int64_t pa = a.pos < 0 ? ~a.pos : a.pos, pb = b.pos < 0 ? ~b.pos : b.pos;
+        if (pa != pb) return pa < pb;
+        return (a.pos < 0) < (b.pos < 0);
+    }
+};
+
+void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_t pitch)
+{
+    P.packed = seq->packed;
+    P.mask = seq->mask;
+    P.pitch = pitch;
+    P.lut = pw->lut;
+    P.lut_off = pw->lut_off;
+    P.glen = pw->glen;
+    P.M = pw->M;
+    P.out_fwd = P.out_rev = nullptr;
+    P.thr_lo = P.thr = nullptr;
+    P.exact = pw->exact;
+    P.hits = nullptr;
+    P.hit_count = nullptr;
+    P.cap = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, int32_t M,
+                    int32_t Lmax, tfbs_pwms **out)
+{
+    TFBS_REQUIRE(ctx && logodds && lens && out && M > 0 && Lmax > 0, "tfbs_pwm_upload: bad argument");
+    TFBS_REQUIRE(Lmax <= TFBS_MAX_MOTIF_LEN, "tfbs_pwm_upload: Lmax %d > %d", Lmax, TFBS_MAX_MOTIF_LEN);
+    for (int m = 0; m < M; m++) {
+        TFBS_REQUIRE(lens[m] >= 1 && lens[m] <= Lmax, "tfbs_pwm_upload: motif %d has length %d", m, lens[m]);
+        for (int j = 0; j < lens[m]; j++)
+            for (int b = 0; b < 4; b++) {
+                const double v = logodds[((size_t)m * Lmax + j) * 4 + b];
+                TFBS_REQUIRE(!(std::isnan(v) || (std::isinf(v) && v > 0)),
+                             "tfbs_pwm_upload: motif %d column %d has a NaN/+inf entry", m, j);
+            }
+    }
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+
+    tfbs_pwms *p = new tfbs_pwms();
+    p->ctx = ctx;
+    p->M = M;
+    p->Lmax = Lmax;
+    p->lens.assign(lens, lens + M);
+    p->logodds.assign(logodds, logodds + (size_t)M * Lmax * 4);
+
+    std::vector<double> exact((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
+    std::vector<int32_t> lut_off(M), glen(M);
+    std::vector<float2> lut;
+    p->fslack_host.resize(M);
+    int Gmax = 0;
+    for (int m = 0; m < M; m++) {
+        const int L = lens[m], G = (L + 2) / 3;
+        Gmax = std::max(Gmax, G);
+        double *F = &exact[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4];
+        double *R = &exact[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4];
+        for (int j = 0; j < L; j++)
+            for (int b = 0; b < 4; b++) {
+                F[j * 4 + b] = logodds[((size_t)m * Lmax + j) * 4 + b];
+                R[j * 4 + b] = logodds[((size_t)m * Lmax + (L - 1 - j)) * 4 + (3 - b)];
+            }
+        lut_off[m] = (int32_t)lut.size();
+        glen[m] = (G << 8) | L;
+        double sabs = 0.0;
+        for (int g = 0; g < G; g++) {
+            double gmax = 0.0;
+            for (int x = 0; x < 64; x++) {
+                double sf = 0.0, sr = 0.0;
+                for (int j = 0; j < 3 && 3 * g + j < L; j++) {
+                    const int b = (x >> (2 * j)) & 3;
+                    sf += F[(3 * g + j) * 4 + b];
+                    sr += R[(3 * g + j) * 4 + b];
+                }
+                if (std::isfinite(sf)) gmax = std::max(gmax, std::fabs(sf));
+                if (std::isfinite(sr)) gmax = std::max(gmax, std::fabs(sr));
+                lut.push_back(make_float2((float)sf, (float)sr));
+            }
+            sabs += gmax;
+        }
+        // |fp32 running sum - exact| <= G * 2^-24 * sum_g max|entry| (entry rounding + G-1 adds);
+        // doubled for safety, plus an absolute epsilon
+        p->fslack_host[m] = (float)(2.0 * (G + 1) * std::ldexp(1.0, -24) * sabs + 1e-6);
+    }
+    p->Gmax = Gmax;
+    p->lut_entries = (int64_t)lut.size();
+
+    cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->lut, lut.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->lut_off, M * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(p->exact, exact.data(), exact.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->lut_off, lut_off.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->glen, glen.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        tfbs_set_error("tfbs_pwm_upload: CUDA error: %s", cudaGetErrorString(e));
+        tfbs_pwms_destroy(p);
+        return e == cudaErrorMemoryAllocation ? TFBS_ERR_NOMEM : TFBS_ERR_CUDA;
+    }
+    *out = p;
+    return TFBS_OK;
+}
+
+int tfbs_pwms_destroy(tfbs_pwms *p)
+{
+    if (!p) return TFBS_OK;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    if (p->exact) cudaFree(p->exact);
+    if (p->lut) cudaFree(p->lut);
+    if (p->lut_off) cudaFree(p->lut_off);
+    if (p->glen) cudaFree(p->glen);
+    delete p;
+    return TFBS_OK;
+}
+
+int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, float *fwd_host,
+                    float *rev_host)
+{
+    TFBS_REQUIRE(ctx && seq && pwms, "tfbs_scan_dense: null argument");
+    TFBS_REQUIRE(seq->ctx == ctx && pwms->ctx == ctx, "tfbs_scan_dense: handle from another context");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = seq->n;
+    if (n == 0) return TFBS_OK;
+    const int64_t pitch = ((n + kTile - 1) / kTile) * kTile;
+    const size_t bytes = (size_t)pwms->M * pitch * sizeof(float);
+    int rc = tfbs_scratch_reserve(ctx->dense_fwd, bytes);
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->dense_rev, bytes);
+    if (rc) return rc;
+    ScanParams P;
+    fill_params(P, seq, pwms, pitch);
+    P.out_fwd = (float *)ctx->dense_fwd.ptr;
+    P.out_rev = (float *)ctx->dense_rev.ptr;
+    tfbs_begin(ctx);
+    scan_kernel<false><<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
+    tfbs_launched(ctx);
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    if (fwd_host)
+        TFBS_CHECK_CUDA(cudaMemcpy2D(fwd_host, (size_t)n * 4, ctx->dense_fwd.ptr, (size_t)pitch * 4,
+                                     (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost));
+    if (rev_host)
+        TFBS_CHECK_CUDA(cudaMemcpy2D(rev_host, (size_t)n * 4, ctx->dense_rev.ptr, (size_t)pitch * 4,
+                                     (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost));
+    return TFBS_OK;
+}
+
+int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const float *thr,
+                   tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits)
+{
+    TFBS_REQUIRE(ctx && seq && pwms && thr && n_hits && cap >= 0, "tfbs_scan_hits: bad argument");
+    TFBS_REQUIRE(seq->ctx == ctx && pwms->ctx == ctx, "tfbs_scan_hits: handle from another context");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    *n_hits = 0;
+    const int64_t n = seq->n;
+    if (n == 0) return TFBS_OK;
+    const int M = pwms->M;
+    int rc = tfbs_scratch_reserve(ctx->hits, (size_t)std::max<int64_t>(cap, 1) * sizeof(tfbs_hit));
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->hit_count, 64);
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->thr, (size_t)M * 2 * sizeof(float));
+    if (rc) return rc;
+    std::vector<float> th(2 * (size_t)M);
+    for (int m = 0; m < M; m++) {
+        const float t = thr[m];
+        th[m] = t;
+        // filter threshold: exact threshold minus the proven fp32 slack and one ulp of the
+        // threshold itself (the oracle compares the float-rounded double score)
+        float lo = t;
+        if (std::isfinite(t)) {
+            const double d = (double)t - (double)pwms->fslack_host[m] - std::fabs((double)t) * std::ldexp(1.0, -22);
+            lo = std::nextafterf((float)d, -INFINITY);
+        }
+        th[M + m] = lo;
+    }
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->thr.ptr, th.data(), th.size() * sizeof(float),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemsetAsync(ctx->hit_count.ptr, 0, 64, ctx->stream));
+    const int64_t pitch = ((n + kTile - 1) / kTile) * kTile;
+    ScanParams P;
+    fill_params(P, seq, pwms, pitch);
+    P.thr = (const float *)ctx->thr.ptr;
+    P.thr_lo = P.thr + M;
+    P.hits = (tfbs_hit *)ctx->hits.ptr;
+    P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
+    P.cap = (unsigned long long)cap;
+    tfbs_begin(ctx);
+    scan_kernel<true><<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
+    tfbs_launched(ctx);
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    unsigned long long cnt = 0;
+    TFBS_CHECK_CUDA(cudaMemcpy(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost));
+    *n_hits = (int64_t)cnt;
+    const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
+    if (out_host && take > 0) {
+        TFBS_CHECK_CUDA(cudaMemcpy(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
+                                   cudaMemcpyDeviceToHost));
+        if (sorted) std::sort(out_host, out_host + take, HitLess());
+    }
+    if ((int64_t)cnt > cap) {
+        tfbs_set_error("tfbs_scan_hits: %llu hits exceed capacity %lld", cnt, (long long)cap);
+        return TFBS_ERR_OVERFLOW;
+    }
+    return TFBS_OK;
+}
+
+}  // extern "C"

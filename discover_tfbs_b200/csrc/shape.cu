@@ -1,0 +1,440 @@
+// shape.cu — (3) DNA-shape pentamer-table lookup.
+//
+// Replaces DNAshapeR getShape()/getDNAShape() (get_DNA_shapes.R:23-25,
+// create_bkg_seqs.py:365-366), the 71.5 M-string parse of its text output
+// (build_features.py:193-198) and the per-site window slicing of utils.py:1061-1084
+// (_get_DNA_shape) and build_features.py:215-241 (background trims).
+//
+// The pentamer tables (1024 entries per value plane) live in shared memory, indexed by the
+// little-endian pentamer index that falls straight out of the 2-bit packed words
+// (x = sum code[c-2+k] << 2k); the host re-indexes the caller's big-endian tables once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kShapeThreads = 256;
+constexpr int kShapePosPerThread = 8;
+constexpr int kShapeTile = kShapeThreads * kShapePosPerThread;  // 2048 positions per CTA
+constexpr int kMaxTracks = 8;
+
+struct TrackParams {
+    const uint32_t *packed;
+    const uint32_t *mask;
+    int64_t n_words;  // allocation sizes, for the guards at the buffer start
+    int64_t n_mask;
+    int64_t pitch;
+    const float *tables;  // [T][2][1024], little-endian pentamer index
+    int32_t T;
+    uint32_t step_mask;  // bit t set: track t is per-step
+    float *out;  // [T][pitch]
+};
+
+// One thread produces 8 consecutive positions of every track.  It needs bases p0-2 .. p0+10; a
+// 64-bit register window holds bases p0-8 .. p0+23.
+__global__ void __launch_bounds__(kShapeThreads)
+shape_tracks_kernel(const TrackParams P)
+{
+    extern __shared__ float s_tab[];  // [T][2][1024]
+    const int tid = threadIdx.x;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(P.tables);
+        float4 *dst = reinterpret_cast<float4 *>(s_tab);
+        for (int i = tid; i < P.T * 512; i += kShapeThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const int64_t p0 = (int64_t)blockIdx.x * kShapeTile + tid * kShapePosPerThread;
+    const int64_t b0 = p0 - 8;  // first base of the window (multiple of 8, may be -8)
+    uint32_t wlo, whi, inv;
+    {
+        const int64_t wi = b0 >> 4;  // floor division: b0 = -8 -> -1
+        const int sh = (int)(b0 & 15) * 2;
+        const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
+        const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
+        const uint32_t a2 = ld_words_guard(P.packed, wi + 2, P.n_words, 0u);
+        wlo = __funnelshift_r(a0, a1, sh);
+        whi = __funnelshift_r(a1, a2, sh);
+        const int64_t mi = b0 >> 5;
+        const int msh = (int)(b0 & 31);
+        const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
+        const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
+        inv = __funnelshift_r(m0, m1, msh);  // invalid bits of bases b0 .. b0+31
+    }
+    // pentamer centred at p0+d (d = 0..8; d = 8 is needed by the last step value) starts at
+    // window base d+6: index bits [2(d+6), 2(d+6)+10), validity bits [d+6, d+11)
+    uint32_t pent[9];
+    bool ok[9];
+#pragma unroll
+    for (int d = 0; d < 9; d++) {
+        const int s = 2 * (d + 6);
+        pent[d] = (s < 32 ? __funnelshift_r(wlo, whi, s) : (whi >> (s - 32))) & 1023u;
+        ok[d] = ((inv >> (d + 6)) & 31u) == 0u;
+    }
+    const float qnan = __int_as_float(0x7FC00000);
+    for (int t = 0; t < P.T; t++) {
+        const float *y1 = s_tab + t * 2048;
+        const float *y2 = y1 + 1024;
+        float v[kShapePosPerThread];
+        if (((P.step_mask >> t) & 1u) == 0u) {
+#pragma unroll
+            for (int d = 0; d < 8; d++) v[d] = ok[d] ? y1[pent[d]] : qnan;
+        } else {
+            // step k between bases k and k+1: mean of Y2(pentamer@k) and Y1(pentamer@k+1).
+            // (a + b) * 0.5f in fp32 equals the oracle's (float)(((double)a + (double)b) / 2).
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2[pent[d]], y1[pent[d + 1]]), 0.5f) : qnan;
+        }
+        float4 *o = reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0);
+        __stcs(o, make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(o + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+}
+
+// Value of one track at index idx of a record [rs, rs+rl) — the DNAshapeR rule including the
+// single-pentamer step values next to the record ends.  Returns NaN for NA.
+__device__ __forceinline__ int pentamer_at(const uint32_t *__restrict__ packed,
+                                           const uint32_t *__restrict__ mask, int64_t rs, int64_t rl,
+                                           int64_t c, uint32_t *idx)
+{
+    if (c < 2 || c + 2 >= rl) return -2;  // does not exist
+    uint32_t x = 0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int64_t i = rs + c - 2 + k;
+        bad |= ((__ldg(mask + (i >> 5)) >> (i & 31)) & 1u) != 0u;
+        x |= ((__ldg(packed + (i >> 4)) >> (2 * (i & 15))) & 3u) << (2 * k);
+    }
+    *idx = x;
+    return bad ? -1 : 0;
+}
+
+__device__ float shape_value(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                             const float *__restrict__ tab, int kind, int64_t rs, int64_t rl,
+                             int64_t idx)
+{
+    const float qnan = __int_as_float(0x7FC00000);
+    const float *y1 = tab, *y2 = tab + 1024;
+    uint32_t xa = 0, xb = 0;
+    if (kind == TFBS_SHAPE_PER_NUCLEOTIDE) {
+        const int ra = pentamer_at(packed, mask, rs, rl, idx, &xa);
+        return ra == 0 ? __ldg(y1 + xa) : qnan;
+    }
+    const int ra = pentamer_at(packed, mask, rs, rl, idx, &xa);      // contributes Y2
+    const int rb = pentamer_at(packed, mask, rs, rl, idx + 1, &xb);  // contributes Y1
+    if (ra == -1 || rb == -1 || (ra == -2 && rb == -2)) return qnan;
+    if (ra == -2) return __ldg(y1 + xb);
+    if (rb == -2) return __ldg(y2 + xa);
+    return __fmul_rn(__fadd_rn(__ldg(y2 + xa), __ldg(y1 + xb)), 0.5f);
+}
+
+// Patches the two single-pentamer step values of every record (k = 1 and k = len-3) that the
+// streaming kernel, which only sees the invalid mask, had to leave as NA.
+__global__ void __launch_bounds__(256)
+shape_edge_fix_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                      const float *__restrict__ tables, int32_t T, const int32_t *__restrict__ kinds,
+                      const int64_t *__restrict__ rec_start, const int64_t *__restrict__ rec_len,
+                      int64_t S, int64_t pitch, float *__restrict__ out)
+{
+    const int64_t total = S * 2 * T;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const int side = (int)((i / T) & 1);
+        const int64_t rec = i / (2 * T);
+        if (__ldg(kinds + t) != TFBS_SHAPE_PER_STEP) continue;
+        const int64_t rs = __ldg(rec_start + rec), rl = __ldg(rec_len + rec);
+        if (rl < 5) continue;
+        const int64_t k = side == 0 ? 1 : rl - 3;
+        out[(size_t)t * pitch + rs + k] =
+            shape_value(packed, mask, tables + (size_t)t * 2048, TFBS_SHAPE_PER_STEP, rs, rl, k);
+    }
+}
+
+// out[s][t][w]: the reference's per-site slices (see tfbs_cuda.h for the modes).
+__global__ void __launch_bounds__(256)
+shape_sites_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ mask,
+                   const float *__restrict__ tables, int32_t T, const int32_t *__restrict__ kinds,
+                   const int64_t *__restrict__ rec_start, const int64_t *__restrict__ rec_len,
+                   const int64_t *__restrict__ start, const int64_t *__restrict__ end,
+                   const int8_t *__restrict__ strand, int64_t S, int32_t W, int32_t mode,
+                   int32_t trailing_empty, float *__restrict__ out)
+{
+    const float qnan = __int_as_float(0x7FC00000);
+    const int64_t total = S * T * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        const int t = (int)((i / W) % T);
+        const int64_t s = i / ((int64_t)W * T);
+        const int kind = __ldg(kinds + t);
+        const int64_t rs = __ldg(rec_start + s), rl = __ldg(rec_len + s);
+        const int64_t n_tok = kind == TFBS_SHAPE_PER_NUCLEOTIDE ? rl : rl - 1;  // real tokens
+        int64_t idx;
+        bool present;
+        if (mode == 0) {
+            const int64_t a = __ldg(start + s), b = __ldg(end + s);
+            const int64_t list_len = n_tok + (trailing_empty ? 1 : 0);
+            if (__ldg(strand + s) >= 0) {
+                // Python slice [a : b+1]
+                idx = a + w;
+                present = a >= 0 && idx <= b && idx < list_len;
+            } else {
+                // Python slice [b : a-1 : -1]; a == 0 makes the stop -1 == "last element", i.e. an
+                // empty slice; a start beyond the list is clamped to the last element
+                const int64_t first = b < list_len - 1 ? b : list_len - 1;
+                idx = first - w;
+                present = a >= 1 && idx >= a && list_len > 0;
+            }
+        } else {
+            // background trims: per-nucleotide [2:-2] of rl tokens, per-step [1:-1] of rl-1 tokens
+            const int64_t lo = kind == TFBS_SHAPE_PER_NUCLEOTIDE ? 2 : 1;
+            const int64_t hi = kind == TFBS_SHAPE_PER_NUCLEOTIDE ? rl - 2 : rl - 2;  // exclusive
+            idx = lo + w;
+            present = idx < hi;
+        }
+        float v = qnan;
+        if (present) {
+            if (idx >= n_tok) v = 0.0f;  // the trailing '' of the flattened file -> 0.0
+            else {
+                v = shape_value(packed, mask, tables + (size_t)t * 2048, kind, rs, rl, idx);
+                if (v != v) v = 0.0f;    // 'NA' -> ValueError -> 0.0 (utils.py:1076-1077)
+            }
+        }
+        out[i] = v;
+    }
+}
+
+
+// Python-slice gather over precomputed per-record token values (legacy input: the reference's
+// {shape: {chrom: [tokens]}} dict, already parsed to floats with NA/'' -> 0.0 on the host):
+// out[s][w] = values[rec_off[s] + idx] for idx in the reference's slice, NaN where the slice is
+// shorter than W (utils.py:1061-1084).
+__global__ void __launch_bounds__(256)
+track_sites_kernel(const float *__restrict__ values, const int64_t *__restrict__ rec_off,
+                   const int64_t *__restrict__ rec_ntok, const int64_t *__restrict__ start,
+                   const int64_t *__restrict__ end, const int8_t *__restrict__ strand, int64_t S,
+                   int32_t W, float *__restrict__ out)
+{
+    const float qnan = __int_as_float(0x7FC00000);
+    const int64_t total = S * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        const int64_t s = i / W;
+        const int64_t a = __ldg(start + s), b = __ldg(end + s), list_len = __ldg(rec_ntok + s);
+        int64_t idx;
+        bool present;
+        if (__ldg(strand + s) >= 0) {
+            idx = a + w;
+            present = a >= 0 && idx <= b && idx < list_len;
+        } else {
+            const int64_t first = b < list_len - 1 ? b : list_len - 1;
+            idx = first - w;
+            present = a >= 1 && idx >= a && list_len > 0;
+        }
+        out[i] = present ? __ldg(values + __ldg(rec_off + s) + idx) : qnan;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfbs_shapes_upload(tfbs_ctx *ctx, const float *tables, const int32_t *kinds, int32_t T,
+                       tfbs_shapes **out)
+{
+    TFBS_REQUIRE(ctx && tables && kinds && out && T > 0 && T <= kMaxTracks,
+                 "tfbs_shapes_upload: bad argument (T must be 1..%d)", kMaxTracks);
+    for (int t = 0; t < T; t++)
+        TFBS_REQUIRE(kinds[t] == TFBS_SHAPE_PER_NUCLEOTIDE || kinds[t] == TFBS_SHAPE_PER_STEP,
+                     "tfbs_shapes_upload: kinds[%d] = %d", t, kinds[t]);
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    tfbs_shapes *s = new tfbs_shapes();
+    s->ctx = ctx;
+    s->T = T;
+    s->kinds.assign(kinds, kinds + T);
+    // re-index: little-endian index x (first base in the low bits) <- big-endian index
+    std::vector<float> le((size_t)T * 2048);
+    for (int t = 0; t < T; t++)
+        for (int plane = 0; plane < 2; plane++)
+            for (int x = 0; x < 1024; x++) {
+                int be = 0;
+                for (int k = 0; k < 5; k++) be = be * 4 + ((x >> (2 * k)) & 3);
+                le[((size_t)t * 2 + plane) * 1024 + x] = tables[((size_t)t * 2 + plane) * 1024 + be];
+            }
+    cudaError_t e = cudaMalloc(&s->tables, le.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s->kinds_dev, T * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(s->tables, le.data(), le.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->kinds_dev, kinds, T * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        tfbs_set_error("tfbs_shapes_upload: CUDA error: %s", cudaGetErrorString(e));
+        tfbs_shapes_destroy(s);
+        return e == cudaErrorMemoryAllocation ? TFBS_ERR_NOMEM : TFBS_ERR_CUDA;
+    }
+    *out = s;
+    return TFBS_OK;
+}
+
+int tfbs_shapes_destroy(tfbs_shapes *s)
+{
+    if (!s) return TFBS_OK;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    if (s->tables) cudaFree(s->tables);
+    if (s->kinds_dev) cudaFree(s->kinds_dev);
+    delete s;
+    return TFBS_OK;
+}
+
+int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *shapes,
+                      const int64_t *rec_start, const int64_t *rec_len, int64_t S, float *out_host)
+{
+    TFBS_REQUIRE(ctx && seq && shapes && S >= 0, "tfbs_shape_tracks: bad argument");
+    TFBS_REQUIRE(seq->ctx == ctx && shapes->ctx == ctx, "tfbs_shape_tracks: handle from another context");
+    TFBS_REQUIRE(S == 0 || (rec_start && rec_len), "tfbs_shape_tracks: null record arrays");
+    const int64_t n = seq->n;
+    if (n == 0) return TFBS_OK;
+    for (int64_t i = 0; i < S; i++)
+        TFBS_REQUIRE(rec_start[i] >= 0 && rec_len[i] >= 0 && rec_start[i] + rec_len[i] <= n,
+                     "tfbs_shape_tracks: record %lld out of range", (long long)i);
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const int T = shapes->T;
+    const int64_t pitch = ((n + kShapeTile - 1) / kShapeTile) * kShapeTile;
+    int rc = tfbs_scratch_reserve(ctx->tracks, (size_t)T * pitch * sizeof(float));
+    if (rc) return rc;
+    // record table for the edge fix-up (one implicit record [0, n) when none is given)
+    const int64_t one_start = 0, one_len = n;
+    if (S == 0) {
+        rec_start = &one_start;
+        rec_len = &one_len;
+        S = 1;
+    }
+    rc = tfbs_scratch_reserve(ctx->sites, (size_t)S * 16);
+    if (rc) return rc;
+    int64_t *d_rs = (int64_t *)ctx->sites.ptr, *d_rl = d_rs + S;
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_rs, rec_start, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_rl, rec_len, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));  // rec_start may point at our stack
+
+    TrackParams P;
+    P.packed = seq->packed;
+    P.mask = seq->mask;
+    P.n_words = seq->n_words;
+    P.n_mask = seq->n_mask;
+    P.pitch = pitch;
+    P.tables = shapes->tables;
+    P.T = T;
+    P.step_mask = 0;
+    for (int t = 0; t < T; t++)
+        if (shapes->kinds[t] == TFBS_SHAPE_PER_STEP) P.step_mask |= 1u << t;
+    P.out = (float *)ctx->tracks.ptr;
+    const size_t smem = (size_t)T * 2048 * sizeof(float);
+    TFBS_CHECK_CUDA(cudaFuncSetAttribute(shape_tracks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tfbs_begin(ctx);
+    shape_tracks_kernel<<<(unsigned)(pitch / kShapeTile), kShapeThreads, smem, ctx->stream>>>(P);
+    tfbs_launched(ctx);
+    {
+        const int64_t total = S * 2 * T;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+        shape_edge_fix_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+            seq->packed, seq->mask, shapes->tables, T, shapes->kinds_dev, d_rs, d_rl, S, pitch, P.out);
+        tfbs_launched(ctx);
+    }
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    if (out_host)
+        TFBS_CHECK_CUDA(cudaMemcpy2D(out_host, (size_t)n * 4, ctx->tracks.ptr, (size_t)pitch * 4,
+                                     (size_t)n * 4, T, cudaMemcpyDeviceToHost));
+    return TFBS_OK;
+}
+
+int tfbs_shape_sites(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *shapes,
+                     const int64_t *rec_start, const int64_t *rec_len, const int64_t *start,
+                     const int64_t *end, const int8_t *strand, int64_t S, int32_t W, int32_t mode,
+                     int32_t trailing_empty, float *out_host)
+{
+    TFBS_REQUIRE(ctx && seq && shapes && S >= 0 && W > 0, "tfbs_shape_sites: bad argument");
+    TFBS_REQUIRE(seq->ctx == ctx && shapes->ctx == ctx, "tfbs_shape_sites: handle from another context");
+    TFBS_REQUIRE(mode == 0 || mode == 1, "tfbs_shape_sites: mode %d", mode);
+    if (S == 0) return TFBS_OK;
+    TFBS_REQUIRE(rec_start && rec_len && out_host, "tfbs_shape_sites: null argument");
+    TFBS_REQUIRE(mode == 1 || (start && end && strand), "tfbs_shape_sites: mode 0 needs start/end/strand");
+    for (int64_t i = 0; i < S; i++)
+        TFBS_REQUIRE(rec_start[i] >= 0 && rec_len[i] >= 0 && rec_start[i] + rec_len[i] <= seq->n,
+                     "tfbs_shape_sites: record of site %lld out of range", (long long)i);
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const int T = shapes->T;
+    const size_t out_bytes = (size_t)S * T * W * sizeof(float);
+    const size_t arg_bytes = (size_t)S * (8 * 4 + 8);  // 4 int64 arrays + strand (padded)
+    int rc = tfbs_scratch_reserve(ctx->sites, arg_bytes + out_bytes + 256);
+    if (rc) return rc;
+    char *base = (char *)ctx->sites.ptr;
+    int64_t *d_rs = (int64_t *)base, *d_rl = d_rs + S, *d_st = d_rl + S, *d_en = d_st + S;
+    int8_t *d_sd = (int8_t *)(d_en + S);
+    float *d_out = (float *)(base + ((arg_bytes + 255) / 256) * 256);
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_rs, rec_start, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_rl, rec_len, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (mode == 0) {
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(d_st, start, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(d_en, end, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(d_sd, strand, (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    tfbs_begin(ctx);
+    const int64_t total = S * T * W;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+    shape_sites_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+        seq->packed, seq->mask, shapes->tables, T, shapes->kinds_dev, d_rs, d_rl, d_st, d_en, d_sd, S, W,
+        mode, trailing_empty, d_out);
+    tfbs_launched(ctx);
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    TFBS_CHECK_CUDA(cudaMemcpy(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost));
+    return TFBS_OK;
+}
+
+int tfbs_track_sites(tfbs_ctx *ctx, const float *values_host, int64_t n_values,
+                     const int64_t *rec_off, const int64_t *rec_ntok, const int64_t *start,
+                     const int64_t *end, const int8_t *strand, int64_t S, int32_t W, float *out_host)
+{
+    TFBS_REQUIRE(ctx && S >= 0 && W > 0 && n_values >= 0, "tfbs_track_sites: bad argument");
+    if (S == 0) return TFBS_OK;
+    TFBS_REQUIRE(values_host && rec_off && rec_ntok && start && end && strand && out_host,
+                 "tfbs_track_sites: null argument");
+    for (int64_t i = 0; i < S; i++)
+        TFBS_REQUIRE(rec_off[i] >= 0 && rec_ntok[i] >= 0 && rec_off[i] + rec_ntok[i] <= n_values,
+                     "tfbs_track_sites: token list of site %lld out of range", (long long)i);
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    const size_t val_bytes = (((size_t)n_values * 4 + 255) / 256) * 256;
+    const size_t arg_bytes = (((size_t)S * 33 + 255) / 256) * 256;
+    const size_t out_bytes = (size_t)S * W * sizeof(float);
+    int rc = tfbs_scratch_reserve(ctx->tracks, val_bytes + 256);
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->sites, arg_bytes + out_bytes + 256);
+    if (rc) return rc;
+    float *d_val = (float *)ctx->tracks.ptr;
+    char *base = (char *)ctx->sites.ptr;
+    int64_t *d_off = (int64_t *)base, *d_nt = d_off + S, *d_st = d_nt + S, *d_en = d_st + S;
+    int8_t *d_sd = (int8_t *)(d_en + S);
+    float *d_out = (float *)(base + arg_bytes);
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_val, values_host, (size_t)n_values * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_off, rec_off, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_nt, rec_ntok, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_st, start, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_en, end, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(d_sd, strand, (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+    tfbs_begin(ctx);
+    const int64_t total = S * W;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+    track_sites_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_val, d_off, d_nt, d_st, d_en, d_sd, S, W, d_out);
+    tfbs_launched(ctx);
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    TFBS_CHECK_CUDA(cudaMemcpy(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost));
+    return TFBS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""Biopython-shaped PSSM API running on the B200 scan kernels.
+
+The north star names Biopython's `Bio.motifs.matrix.PositionSpecificScoringMatrix` as the
+scoring contract (the reference itself finds candidates with exact-match BLASTn,
+utils.py:340-398).  `PSSM.calculate` / `PSSM.search` keep that call shape; `MotifScanner`
+is the batched form (many motifs, one pass over the sequence) the feature builder uses.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+LETTERS = "ACGT"
+_default_ctx = None
+
+
+def default_context() -> _lib.Context:
+    global _default_ctx
+    if _default_ctx is None or _default_ctx._h is None:
+        _default_ctx = _lib.Context(0)
+    return _default_ctx
+
+
+def normalize(counts, pseudocounts=None) -> np.ndarray:
+    """FrequencyPositionMatrix.normalize: counts[L][4] -> probabilities (host, tiny)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    if pseudocounts is None:
+        pc = np.zeros(4)
+    elif isinstance(pseudocounts, dict):
+        pc = np.array([float(pseudocounts[b]) for b in LETTERS])
+    else:
+        pc = np.full(4, float(pseudocounts))
+    p = counts + pc[None, :]
+    return p / p.sum(axis=1, keepdims=True)
+
+
+def log_odds(pwm, background=None) -> np.ndarray:
+    """PositionWeightMatrix.log_odds: log2(p / bg), p == 0 -> -inf, uniform bg by default."""
+    pwm = np.asarray(pwm, dtype=np.float64)
+    if background is None:
+        bg = np.full(4, 0.25)
+    else:
+        bg = np.array([float(background[b]) for b in LETTERS])
+        bg = bg / bg.sum()
+    out = np.empty_like(pwm)
+    for j in range(pwm.shape[0]):
+        for b in range(4):
+            p, q = pwm[j, b], bg[b]
+            if q > 0:
+                out[j, b] = math.log(p / q, 2) if p > 0 else -math.inf
+            else:
+                out[j, b] = math.inf if p > 0 else math.nan
+    return out
+
+
+class PSSM:
+    """One position-specific scoring matrix (log-odds[L][4], ACGT order)."""
+
+    def __init__(self, logodds, ctx: _lib.Context = None):
+        self.matrix = np.ascontiguousarray(logodds, dtype=np.float64)
+        self.length = self.matrix.shape[0]
+        self._ctx = ctx
+        self._lib = None
+
+    @property
+    def ctx(self):
+        return self._ctx or default_context()
+
+    def _library(self):
+        if self._lib is None or self._lib._h is None:
+            self._lib = self.ctx.upload_pwms(self.matrix[None])
+        return self._lib
+
+    def reverse_complement(self) -> "PSSM":
+        return PSSM(self.matrix[::-1, ::-1], self._ctx)
+
+    @property
+    def max(self) -> float:
+        return float(self.matrix.max(axis=1).sum())
+
+    @property
+    def min(self) -> float:
+        return float(self.matrix.min(axis=1).sum())
+
+    def calculate(self, sequence):
+        """float32[n-L+1] forward-strand scores (a bare float when n == L, as Biopython)."""
+        a = _lib.as_ascii(sequence)
+        if a.size < self.length:
+            raise ValueError("sequence shorter than the motif")
+        enc = self.ctx.encode(a)
+        fwd, _ = self.ctx.scan_dense(enc, self._library())
+        enc.close()
+        out = fwd[0, : a.size - self.length + 1]
+        return out[0] if out.size == 1 else out
+
+    def search(self, sequence, threshold=0.0, both=True):
+        """Yield (position, score) with score >= threshold; reverse-strand hits carry the
+        negative position p - len(sequence) (Biopython convention), ordered by p, fwd first."""
+        a = _lib.as_ascii(sequence)
+        n = a.size
+        enc = self.ctx.encode(a)
+        hits = self.ctx.scan_hits(enc, self._library(), [threshold], sort=True)
+        enc.close()
+        for h in hits:
+            p = int(h["pos"])
+            if p >= 0:
+                yield p, h["score"]
+            elif both:
+                yield (~p) - n, h["score"]
+
+
+class MotifScanner:
+    """A motif library resident on one GPU; scans encoded buffers in dense or hits mode."""
+
+    def __init__(self, logodds, lens=None, ctx: _lib.Context = None):
+        self.ctx = ctx or default_context()
+        self.library = self.ctx.upload_pwms(logodds, lens)
+        self.lens = np.asarray(self.library.lens)
+        self.M = self.library.M
+
+    def dense(self, enc: _lib.EncodedSeq, to_host=True):
+        return self.ctx.scan_dense(enc, self.library, to_host=to_host)
+
+    def hits(self, enc: _lib.EncodedSeq, thresholds, **kw):
+        return self.ctx.scan_hits(enc, self.library, thresholds, **kw)
+
+    def units(self, n: int) -> int:
+        """motif x bp units of one scan of an n-base buffer: sum_m (n - L_m + 1)."""
+        return int(sum(max(n - int(L) + 1, 0) for L in self.lens))

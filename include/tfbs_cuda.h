@@ -1,0 +1,184 @@
+/*
+ * tfbs_cuda.h — C ABI of libtfbs_cuda.so, the B200 (sm_100a) implementation of the
+ * discover_tfbs feature-extraction hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference
+ * (akshayparopkari/discover_tfbs) is pure Python, so the binding a maintainer adds is a ctypes
+ * stub; discover_tfbs_b200/_lib.py is that stub.  Each entry point cites the
+ * reference interface whose arithmetic it replaces (file:line in the reference repository).
+ *
+ * Conventions
+ *   - every function returns 0 (TFBS_OK) or a negative tfbs_status; it never throws and never
+ *     calls exit().  The message for the last failure on the calling thread is
+ *     tfbs_last_error().  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with TFBS_ERR_NO_DEVICE / TFBS_ERR_CUDA.
+ *   - the caller owns every host buffer (pointer + length); the library owns device memory
+ *     behind opaque handles released by the matching *_destroy.
+ *   - one host thread per tfbs_ctx; contexts on different devices may be driven concurrently
+ *     (ctypes releases the GIL).  The only global state is the thread-local error string.
+ *   - base coding: A=0 C=1 G=2 T=3, case-insensitive (acgt == ACGT, as Biopython's _pwm.c);
+ *     every other byte (N, IUPAC ambiguity codes, gaps, separators) is INVALID.
+ *     complement(b) = 3 - b  (reference: utils.py:97-105 reverse_complement).
+ *   - a sequence SET (many FASTA records) is passed as one buffer with at least one invalid
+ *     separator byte (e.g. '\n') between records; windows that touch a separator score NaN /
+ *     never hit / give NA shapes, so no per-record bookkeeping is needed in the kernels.
+ */
+#ifndef TFBS_CUDA_H
+#define TFBS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tfbs_status {
+    TFBS_OK = 0,
+    TFBS_ERR_INVALID = -1,    /* bad argument */
+    TFBS_ERR_NO_DEVICE = -2,  /* no CUDA device / driver */
+    TFBS_ERR_CUDA = -3,       /* CUDA runtime error (message has the CUDA string) */
+    TFBS_ERR_NOMEM = -4,      /* device or host allocation failed */
+    TFBS_ERR_OVERFLOW = -5    /* output capacity too small (n_hits still reports the need) */
+} tfbs_status;
+
+typedef struct tfbs_ctx tfbs_ctx;       /* one device + one stream + scratch */
+typedef struct tfbs_seq tfbs_seq;       /* encoded sequence (2-bit words + invalid mask) in HBM */
+typedef struct tfbs_pwms tfbs_pwms;     /* uploaded motif library (log-odds + derived LUTs) */
+typedef struct tfbs_shapes tfbs_shapes; /* uploaded pentamer tables */
+
+/* One thresholded hit.  pos is the 0-based start of the window on the + strand of the encoded
+ * buffer; a reverse-strand hit stores ~pos (bitwise NOT, always negative) so that strand is
+ * recoverable without a fifth field.  (Biopython's search() reports p - len(seq) for the
+ * reverse strand; the Python wrapper converts.)  16 bytes. */
+typedef struct tfbs_hit {
+    int64_t pos;
+    int32_t motif;
+    float score;
+} tfbs_hit;
+
+#define TFBS_MAX_MOTIF_LEN 32     /* JASPAR-sized library: lengths 6..30 */
+#define TFBS_SHAPE_PER_NUCLEOTIDE 0 /* MGW, ProT, EP : value = table[0][pentamer] */
+#define TFBS_SHAPE_PER_STEP 1       /* Roll, HelT    : mean of Y2(P@k) and Y1(P@k+1) */
+
+/* ---- library / context ---------------------------------------------------------------- */
+const char *tfbs_last_error(void);
+const char *tfbs_version(void);
+int tfbs_device_count(int *n);
+int tfbs_ctx_create(int device, tfbs_ctx **out);
+int tfbs_ctx_destroy(tfbs_ctx *ctx);
+int tfbs_ctx_sync(tfbs_ctx *ctx);
+/* Device time (CUDA events on the context's stream) of the kernels launched by the most recent
+ * compute call on this context, and how many kernels that call launched. */
+int tfbs_last_kernel_ms(tfbs_ctx *ctx, float *ms);
+int tfbs_last_kernel_launches(tfbs_ctx *ctx, int64_t *n);
+/* Total kernels launched through this context since creation (bench.py's gpu_launches). */
+int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n);
+/* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
+int tfbs_host_alloc(void **ptr, int64_t bytes);
+int tfbs_host_free(void *ptr);
+/* Overwrite a >L2-sized scratch buffer so the next timed launch starts with a cold L2. */
+int tfbs_flush_l2(tfbs_ctx *ctx);
+
+/* ---- (1) sequence encoding -------------------------------------------------------------
+ * Replaces the per-character Python string handling of utils.py:97-105 (reverse_complement),
+ * utils.py:224-238 (calculate_gc_content) and the byte switch of Biopython's _pwm.c.
+ * ASCII -> 2-bit words (16 bases / uint32, base i at bits 2*(i%16)) + invalid mask (32 bases /
+ * uint32, bit i%32; padding bits past n are 1).  1.375 B/bp of HBM traffic. */
+int tfbs_encode(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq **out);
+/* Same, input already resident in HBM (device pointer). */
+int tfbs_encode_device(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq **out);
+/* Re-encode into an existing handle of the same length (no allocation; bench inner loop). */
+int tfbs_encode_into(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq);
+int tfbs_encode_device_into(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq *seq);
+int tfbs_seq_destroy(tfbs_seq *seq);
+int tfbs_seq_length(const tfbs_seq *seq, int64_t *n);
+/* Copy the encoding back: packed[ceil(n/16)], mask[ceil(n/32)] (parity tests). */
+int tfbs_seq_download(tfbs_ctx *ctx, const tfbs_seq *seq, uint32_t *packed, uint32_t *mask);
+/* counts[5] = #A #C #G #T #invalid over the whole buffer (popcounts on the packed planes). */
+int tfbs_seq_base_counts(tfbs_ctx *ctx, const tfbs_seq *seq, int64_t counts[5]);
+/* Per-record G+C counts for S records [start, start+len) of the encoded buffer
+ * (utils.py:224-238: gc = (count('G') + count('C')) / len after upper()). */
+int tfbs_gc_counts(tfbs_ctx *ctx, const tfbs_seq *seq, const int64_t *start, const int64_t *len,
+                   int64_t S, int64_t *gc_out);
+/* Device-side synthetic genome (position-addressable hash; identical to
+ * discover_tfbs_b200/synth.py) written as ASCII into a library-owned HBM buffer. */
+int tfbs_synth_ascii(tfbs_ctx *ctx, uint64_t seed, int64_t start, int64_t n, double gc,
+                     int32_t with_n_runs, int32_t with_lowercase, void **ascii_dev_out);
+int tfbs_device_free(tfbs_ctx *ctx, void *dev_ptr);
+int tfbs_device_download(tfbs_ctx *ctx, const void *dev_ptr, void *host, int64_t bytes);
+
+/* ---- (2) PWM log-odds scan, both strands -----------------------------------------------
+ * Replaces Biopython PositionSpecificScoringMatrix.calculate / .search / .reverse_complement
+ * (Bio/motifs/matrix.py, Bio/motifs/_pwm.c — the north-star oracle; the reference's own
+ * candidate stage is exact-match BLASTn, utils.py:340-398, process_blast.sh:32).
+ * logodds: double[M][Lmax][4], ACGT order, rows >= lens[m] ignored; -inf entries allowed.
+ * 6 <= ... any 1 <= lens[m] <= TFBS_MAX_MOTIF_LEN. */
+int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, int32_t M,
+                    int32_t Lmax, tfbs_pwms **out);
+int tfbs_pwms_destroy(tfbs_pwms *p);
+/* Dense mode: fwd[m][i], rev[m][i] = float32 score of motif m at start i on the + strand and of
+ * its reverse-complement matrix at the same window (so rev[m][i] == fwd score of
+ * revcomp(seq) at n-L-i); NaN where the window touches an invalid byte or runs past n.
+ * Output layout [M][n] row-major, fp32 accumulation of double-precomputed k-mer partial sums
+ * (|error| <= 1e-4 vs the double-accumulating oracle is asserted in tests).
+ * Host pointers may be NULL: results then stay in the context's device scratch (bench `value`). */
+int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, float *fwd_host,
+                    float *rev_host);
+/* Hits mode: every (motif, start, strand) with (float)score >= thr[motif].  A packed
+ * fixed-point filter with a rigorous upper bound selects candidates; each candidate is then
+ * re-scored left to right in double and cast to float, so hit sets and scores are bit-exact
+ * with the oracle.  Order of `out` is unspecified unless `sorted` is non-zero (then ascending
+ * (motif, pos, strand)).  out_host may be NULL (hits stay on device).  If more than `cap` hits
+ * exist the call returns TFBS_ERR_OVERFLOW with *n_hits = the number found. */
+int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const float *thr,
+                   tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits);
+
+/* ---- (3) DNA-shape pentamer lookup -----------------------------------------------------
+ * Replaces DNAshapeR getShape()/getDNAShape() (get_DNA_shapes.R:23-25,
+ * create_bkg_seqs.py:365-366) and the text parsing + window slicing the reference does on its
+ * output (build_features.py:193-198,215-241; utils.py:1061-1084 _get_DNA_shape).
+ * tables: float[T][2][1024]; pentamer index = sum code[k]*4^(4-k); kinds[t] is
+ * TFBS_SHAPE_PER_NUCLEOTIDE (uses tables[t][0]) or TFBS_SHAPE_PER_STEP (Y1 = tables[t][0],
+ * Y2 = tables[t][1]). */
+int tfbs_shapes_upload(tfbs_ctx *ctx, const float *tables, const int32_t *kinds, int32_t T,
+                       tfbs_shapes **out);
+int tfbs_shapes_destroy(tfbs_shapes *s);
+/* Whole-buffer tracks: out[t][i], NaN = NA.  Records are delimited by invalid separator bytes;
+ * rec_start/rec_len (S records, may be NULL/0 = the buffer is one record) give the record
+ * boundaries needed for the single-pentamer step values next to record ends.
+ * out_host may be NULL (tracks stay in device scratch). */
+int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *shapes,
+                      const int64_t *rec_start, const int64_t *rec_len, int64_t S,
+                      float *out_host);
+/* Per-site feature matrix out[s][t][w], w < W, written exactly as the reference slices it:
+ *   mode 0 (utils.py:1061-1084): site = (record, start, end, strand);
+ *           '+': indices start..end, '-': indices end..start (descending), i.e. L+1 values with
+ *           L = end-start; an index whose token would be 'NA' or the trailing '' of the
+ *           flattened file (index == n_tokens when trailing_empty) yields 0.0; an index past the
+ *           tokens yields NaN (missing column); '-' with start == 0 yields an all-NaN row.
+ *   mode 1 (build_features.py:215-241): background records of length len: per-nucleotide
+ *           tracks give indices 2..len-3, per-step tracks 1..len-3; NA -> 0.0.
+ * rec_start/rec_len locate the record (chromosome) of every site inside the encoded buffer. */
+int tfbs_shape_sites(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *shapes,
+                     const int64_t *rec_start, const int64_t *rec_len, const int64_t *start,
+                     const int64_t *end, const int8_t *strand, int64_t S, int32_t W, int32_t mode,
+                     int32_t trailing_empty, float *out_host);
+
+/* Legacy input path: the caller already holds DNAshapeR output as per-record token lists (the
+ * reference's {shape: {chrom: [str, ...]}} dict, build_features.py:193-198) parsed to floats
+ * ('NA' and '' -> 0.0, as utils.py:1076-1077 does).  Gathers the reference's Python slices
+ * ('+': [start : end+1], '-': [end : start-1 : -1]) of list rec_off[s] .. +rec_ntok[s] into
+ * out[s][w]; NaN where the slice is shorter than W. */
+int tfbs_track_sites(tfbs_ctx *ctx, const float *values_host, int64_t n_values,
+                     const int64_t *rec_off, const int64_t *rec_ntok, const int64_t *start,
+                     const int64_t *end, const int8_t *strand, int64_t S, int32_t W, float *out_host);
+
+/* ---- test hooks (host-only, no device needed) -------------------------------------------
+ * The encode kernel converts 4 ASCII bytes per 32-bit word with integer bit tricks; this runs
+ * the same inline function on the host so the CPU test-suite can check it exhaustively. */
+int tfbs_debug_swar4(uint32_t four_ascii_bytes, uint32_t *codes8, uint32_t *valid4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFBS_CUDA_H */
