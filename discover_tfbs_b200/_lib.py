@@ -31,6 +31,8 @@ _PROTOTYPES = {
     "tfbs_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_last_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_total_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "tfbs_timer_start": (C.c_int, [_vp]),
+    "tfbs_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_host_alloc": (C.c_int, [_pp, _i64]),
     "tfbs_host_free": (C.c_int, [_vp]),
     "tfbs_flush_l2": (C.c_int, [_vp]),
@@ -180,6 +182,14 @@ class Context:
         n = _i64(0)
         _check(self._lib.tfbs_total_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+    def timer_start(self):
+        _check(self._lib.tfbs_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        _check(self._lib.tfbs_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def flush_l2(self):
         _check(self._lib.tfbs_flush_l2(self._h))

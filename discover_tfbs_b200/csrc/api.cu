@@ -90,6 +90,8 @@ int tfbs_ctx_create(int device, tfbs_ctx **out)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_ctx_create: %s", cudaGetErrorString(e));
         delete c;
@@ -115,6 +117,8 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     free_scratch(ctx->thr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evt0) cudaEventDestroy(ctx->evt0);
+    if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TFBS_OK;
@@ -146,6 +150,24 @@ int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n)
 {
     TFBS_REQUIRE(ctx && n, "tfbs_total_kernel_launches: null argument");
     *n = ctx->total_launches;
+    return TFBS_OK;
+}
+
+int tfbs_timer_start(tfbs_ctx *ctx)
+{
+    TFBS_REQUIRE(ctx, "tfbs_timer_start: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TFBS_CHECK_CUDA(cudaEventRecord(ctx->evt0, ctx->stream));
+    return TFBS_OK;
+}
+
+int tfbs_timer_stop(tfbs_ctx *ctx, float *ms)
+{
+    TFBS_REQUIRE(ctx && ms, "tfbs_timer_stop: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TFBS_CHECK_CUDA(cudaEventRecord(ctx->evt1, ctx->stream));
+    TFBS_CHECK_CUDA(cudaEventSynchronize(ctx->evt1));
+    TFBS_CHECK_CUDA(cudaEventElapsedTime(ms, ctx->evt0, ctx->evt1));
     return TFBS_OK;
 }
 

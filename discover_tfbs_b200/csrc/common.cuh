@@ -41,7 +41,8 @@ struct tfbs_ctx {
     int device = 0;
     int sm_count = TFBS_SM_COUNT_FALLBACK;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // per-call kernel bracket
+    cudaEvent_t evt0 = nullptr, evt1 = nullptr;  // user region timer
     float last_ms = 0.f;
     int64_t last_launches = 0;
     int64_t total_launches = 0;

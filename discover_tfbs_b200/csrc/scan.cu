@@ -346,11 +346,12 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
     rc = tfbs_end(ctx);
     if (rc) return rc;
     if (fwd_host)
-        TFBS_CHECK_CUDA(cudaMemcpy2D(fwd_host, (size_t)n * 4, ctx->dense_fwd.ptr, (size_t)pitch * 4,
-                                     (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost));
+        TFBS_CHECK_CUDA(cudaMemcpy2DAsync(fwd_host, (size_t)n * 4, ctx->dense_fwd.ptr, (size_t)pitch * 4,
+                                          (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost, ctx->stream));
     if (rev_host)
-        TFBS_CHECK_CUDA(cudaMemcpy2D(rev_host, (size_t)n * 4, ctx->dense_rev.ptr, (size_t)pitch * 4,
-                                     (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost));
+        TFBS_CHECK_CUDA(cudaMemcpy2DAsync(rev_host, (size_t)n * 4, ctx->dense_rev.ptr, (size_t)pitch * 4,
+                                          (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost, ctx->stream));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return TFBS_OK;
 }
 
@@ -400,12 +401,14 @@ int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, co
     rc = tfbs_end(ctx);
     if (rc) return rc;
     unsigned long long cnt = 0;
-    TFBS_CHECK_CUDA(cudaMemcpy(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost));
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     *n_hits = (int64_t)cnt;
     const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
     if (out_host && take > 0) {
-        TFBS_CHECK_CUDA(cudaMemcpy(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
-                                   cudaMemcpyDeviceToHost));
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
         if (sorted) std::sort(out_host, out_host + take, HitLess());
     }
     if ((int64_t)cnt > cap) {

@@ -73,6 +73,10 @@ int tfbs_last_kernel_ms(tfbs_ctx *ctx, float *ms);
 int tfbs_last_kernel_launches(tfbs_ctx *ctx, int64_t *n);
 /* Total kernels launched through this context since creation (bench.py's gpu_launches). */
 int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n);
+/* Region timer: CUDA events recorded on the context's stream; stop synchronises and returns the
+ * elapsed device time of everything enqueued in between (kernels and async copies). */
+int tfbs_timer_start(tfbs_ctx *ctx);
+int tfbs_timer_stop(tfbs_ctx *ctx, float *ms);
 /* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
 int tfbs_host_alloc(void **ptr, int64_t bytes);
 int tfbs_host_free(void *ptr);

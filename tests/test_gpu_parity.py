@@ -1,0 +1,362 @@
+"""GPU parity tests: every kernel, through the C ABI, against the CPU oracle and the
+reference's golden vectors.  Bit-exact for encodings, hit sets/scores and shape lookups;
+|error| <= 1e-4 absolute for dense fp32 log-odds scores (north-star tolerance)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from discover_tfbs_b200 import _lib, dnashape, pssm, synth
+from discover_tfbs_b200 import utils as U
+from oracle import pssm_oracle as po
+from oracle import shape_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+SCORE_ATOL = 1e-4  # BASELINE.json north_star: "within 1e-4 absolute (fp32 accumulation)"
+
+
+def _noisy_seq(rng, n):
+    alphabet = np.frombuffer(b"ACGTacgtNRYn-\n", dtype=np.uint8)
+    p = np.array([0.21, 0.21, 0.21, 0.21, 0.03, 0.03, 0.03, 0.03] + [0.04 / 6] * 6)
+    return alphabet[rng.choice(alphabet.size, size=n, p=p / p.sum())]
+
+
+# ---- (1) encode -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 32, 33, 2047, 2048, 2049, 8191, 8192, 100_003])
+def test_encode_bit_exact(ctx, n):
+    rng = np.random.default_rng(n)
+    seq = _noisy_seq(rng, n)
+    enc = ctx.encode(seq)
+    packed, mask = enc.download()
+    o_packed, o_mask = po.encode(seq)
+    assert np.array_equal(packed, o_packed)
+    assert np.array_equal(mask, o_mask)
+    counts = enc.base_counts()
+    oc = po.base_counts(seq)
+    assert counts[:4].tolist() == oc[:4].tolist() and counts[4] == oc[4] + oc[5]
+    enc.close()
+
+
+def test_encode_empty_and_all_bytes(ctx):
+    enc = ctx.encode(b"")
+    assert enc.n == 0
+    enc.close()
+    allb = np.arange(256, dtype=np.uint8).repeat(3)
+    enc = ctx.encode(allb)
+    packed, mask = enc.download()
+    o_packed, o_mask = po.encode(allb)
+    assert np.array_equal(packed, o_packed) and np.array_equal(mask, o_mask)
+    enc.close()
+
+
+def test_encode_device_unaligned_and_reencode(ctx):
+    dev = ctx.synth_ascii(39, 0, 70_001, gc=0.41)
+    host = dev.download()
+    assert np.array_equal(host, synth.genome(39, 0, 70_001, gc=0.41))
+    for off in (0, 1, 7, 16):
+        enc = ctx.encode_device(dev.ptr + off, 70_001 - off)
+        packed, mask = enc.download()
+        o_packed, o_mask = po.encode(host[off:])
+        assert np.array_equal(packed, o_packed) and np.array_equal(mask, o_mask), off
+        enc.close()
+    enc = ctx.encode(host[:5000])
+    other = synth.genome(40, 0, 5000)
+    enc.reencode(other)
+    assert np.array_equal(enc.download()[0], po.encode(other)[0])
+    enc.close()
+    dev.close()
+
+
+def test_synth_device_matches_numpy_at_offset(ctx):
+    for start, n, gc in ((0, 33, 0.335), (123_456_789, 50_000, 0.41), (3_000_000_000, 4097, 0.5)):
+        dev = ctx.synth_ascii(39, start, n, gc=gc)
+        assert np.array_equal(dev.download(), synth.genome(39, start, n, gc=gc)), (start, n)
+        dev.close()
+
+
+def test_gc_counts_vs_reference_golden(ctx, golden):
+    seqs = [s for s, _ in golden["primitives"]["calculate_gc_content"]]
+    buf, starts, lens = synth.join_records(seqs)
+    enc = ctx.encode(buf)
+    gc = enc.gc_counts(starts, lens)
+    for (s, want), g, ln in zip(golden["primitives"]["calculate_gc_content"], gc, lens):
+        assert int(g) / int(ln) == want
+    enc.close()
+    for s, want in golden["primitives"]["calculate_gc_content"][:3]:
+        assert U.calculate_gc_content(s) == want
+
+
+# ---- (2) PWM scan ---------------------------------------------------------------------------------
+def _check_dense(ctx, seq, logodds, lens):
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    fwd, rev = ctx.scan_dense(enc, lib)
+    worst = 0.0
+    for m in range(lib.M):
+        L = int(lens[m])
+        nw = seq.size - L + 1
+        if nw > 0:
+            rf = po.calculate(seq, logodds[m, :L])
+            rr = po.calculate(seq, po.reverse_complement(logodds[m, :L]))
+            for got, ref in ((fwd[m, :nw], rf), (rev[m, :nw], rr)):
+                assert np.array_equal(np.isnan(got), np.isnan(ref)), m
+                assert np.array_equal(np.isneginf(got), np.isneginf(ref)), m
+                ok = np.isfinite(ref)
+                if ok.any():
+                    err = float(np.max(np.abs(got[ok].astype(np.float64) - ref[ok])))
+                    worst = max(worst, err)
+                    assert err <= SCORE_ATOL, (m, err)
+        assert np.isnan(fwd[m, max(nw, 0):]).all() and np.isnan(rev[m, max(nw, 0):]).all()
+    enc.close()
+    lib.close()
+    return worst
+
+
+@pytest.mark.parametrize("n", [64, 2048, 2049, 4100, 50_000])
+def test_dense_scores_within_tolerance(ctx, n):
+    rng = np.random.default_rng(n)
+    logodds, lens = synth.pwm_library(n, 12)
+    _check_dense(ctx, _noisy_seq(rng, n), logodds, lens)
+
+
+def test_dense_every_motif_length_and_minus_inf(ctx):
+    rng = np.random.default_rng(3)
+    mats = []
+    for L in range(1, 33):
+        counts = rng.integers(0, 30, size=(L, 4)).astype(float)
+        counts[rng.random((L, 4)) < 0.1] = 0.0
+        counts[counts.sum(axis=1) == 0, 0] = 1.0
+        mats.append(po.log_odds(po.normalize(counts, None if L % 2 else 0.25)))
+    lens = np.array([m.shape[0] for m in mats], dtype=np.int32)
+    lo = np.zeros((len(mats), 32, 4))
+    for i, m in enumerate(mats):
+        lo[i, : m.shape[0]] = m
+    assert np.isneginf(lo).any()
+    _check_dense(ctx, _noisy_seq(rng, 6000), lo, lens)
+
+
+def test_dense_sequence_shorter_than_motif_and_record_set(ctx):
+    logodds, lens = synth.pwm_library(5, 6, lmin=8, lmax=20)
+    # a ragged record set: windows crossing the '\n' separators must be NaN
+    rng = np.random.default_rng(11)
+    recs = ["".join(rng.choice(list("ACGT"), size=k)) for k in (3, 8, 19, 20, 21, 200, 1, 57)]
+    buf, starts, rl = synth.join_records(recs)
+    enc = ctx.encode(buf)
+    lib = ctx.upload_pwms(logodds, lens)
+    fwd, rev = ctx.scan_dense(enc, lib)
+    for m in range(lib.M):
+        L = int(lens[m])
+        covered = np.zeros(buf.size, dtype=bool)
+        for rec, s, ln in zip(recs, starts, rl):
+            if ln >= L:
+                ref = po.calculate(rec, logodds[m, :L])
+                assert np.allclose(fwd[m, s: s + ref.size], ref, atol=SCORE_ATOL, rtol=0)
+                covered[s: s + ref.size] = True
+        assert np.isnan(fwd[m, ~covered]).all() and np.isnan(rev[m, ~covered]).all()
+    enc.close()
+    lib.close()
+
+
+def test_reverse_strand_symmetry_property(ctx):
+    """rev(seq)[i] == fwd(revcomp(seq))[n-L-i] (size-independent property, 3 Mb)."""
+    n = 3_000_000
+    seq = synth.genome(39, 0, n, gc=0.335, lowercase=False)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    rc = np.ascontiguousarray(comp[seq][::-1])
+    logodds, lens = synth.pwm_library(1, 3, lmin=8, lmax=20)
+    lib = ctx.upload_pwms(logodds, lens)
+    e1, e2 = ctx.encode(seq), ctx.encode(rc)
+    _, rev = ctx.scan_dense(e1, lib)
+    fwd2, _ = ctx.scan_dense(e2, lib)
+    for m in range(lib.M):
+        nw = n - int(lens[m]) + 1
+        a, b = rev[m, :nw], fwd2[m, :nw][::-1]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.nanmax(np.abs(a - b)) <= SCORE_ATOL
+    for h in (e1, e2, lib):
+        h.close()
+
+
+def _check_hits(ctx, seq, logodds, lens, thr):
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    hits = ctx.scan_hits(enc, lib, thr, cap=4096, sort=True)
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+    assert hits.size == cnt
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    assert np.array_equal(gpos, pos)
+    assert np.array_equal(hits["motif"], mot)
+    assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
+    assert np.array_equal(hits["score"], score)  # bit-exact: double re-score cast to float
+    n_dev = ctx.scan_hits(enc, lib, thr, cap=max(cnt, 1), to_host=False)
+    assert n_dev == cnt
+    enc.close()
+    lib.close()
+    return cnt
+
+
+@pytest.mark.parametrize("n,rate", [(100, 0.05), (5000, 1e-2), (200_000, 1e-3), (200_000, 1e-4)])
+def test_hits_bit_exact(ctx, n, rate):
+    rng = np.random.default_rng(n)
+    logodds, lens = synth.pwm_library(n + 1, 24)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=rate, sample=50_000)
+    seq = _noisy_seq(rng, n) if n < 100_000 else synth.genome(n, 0, n)
+    cnt = _check_hits(ctx, seq, logodds, lens, thr)
+    assert cnt > 0
+
+
+def test_hits_thresholds_exactly_on_scores_and_overflow(ctx):
+    """Thresholds equal to attained float32 scores exercise the >= boundary; a too-small capacity
+    must report TFBS_ERR_OVERFLOW together with the true count."""
+    rng = np.random.default_rng(8)
+    logodds, lens = synth.pwm_library(8, 6)
+    seq = _noisy_seq(rng, 20_000)
+    thr = np.empty(6, dtype=np.float32)
+    for m in range(6):
+        sc = po.calculate(seq, logodds[m, : lens[m]])
+        thr[m] = np.sort(sc[np.isfinite(sc)])[-40]
+    cnt = _check_hits(ctx, seq, logodds, lens, thr)
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    with pytest.raises(RuntimeError, match="exceed capacity"):
+        ctx.scan_hits(enc, lib, thr, cap=3, grow=False)
+    grown = ctx.scan_hits(enc, lib, thr, cap=3, grow=True)
+    assert grown.size == cnt
+    enc.close()
+    lib.close()
+
+
+def test_biopython_shaped_api(ctx):
+    rng = np.random.default_rng(21)
+    counts = rng.integers(0, 50, size=(12, 4))
+    lo = pssm.log_odds(pssm.normalize(counts, 0.5))
+    assert np.array_equal(lo, po.log_odds(po.normalize(counts, 0.5)))
+    seq = bytes(_noisy_seq(rng, 3000)).decode("latin1")
+    p = pssm.PSSM(lo, ctx)
+    got = p.calculate(seq)
+    ref = po.calculate(seq.encode("latin1"), lo)
+    assert np.allclose(got, ref, atol=SCORE_ATOL, rtol=0, equal_nan=True)
+    hits = list(p.search(seq, threshold=3.0))
+    want = po.search(seq.encode("latin1"), lo, threshold=3.0)
+    assert [h[0] for h in hits] == [h[0] for h in want]
+    assert [float(h[1]) for h in hits] == [float(h[1]) for h in want]
+    assert isinstance(p.calculate(seq[:12].replace("N", "A")), (float, np.floating))
+
+
+# ---- (3) DNA shape --------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 5, 6, 9, 40, 2047, 2048, 2056, 30_000])
+def test_shape_tracks_bit_exact_single_record(ctx, n):
+    rng = np.random.default_rng(n)
+    seq = _noisy_seq(rng, n) if n > 100 else np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+    tables, kinds = dnashape.synthetic_tables()
+    tab = ctx.upload_shapes(tables, kinds)
+    enc = ctx.encode(seq)
+    got = ctx.shape_tracks(enc, tab)
+    ref = so.tracks(seq, tables, kinds)
+    assert np.array_equal(got, ref, equal_nan=True)
+    enc.close()
+    tab.close()
+
+
+def test_shape_tracks_record_set(ctx):
+    rng = np.random.default_rng(2)
+    recs = ["".join(rng.choice(list("ACGTN"), p=[.24, .24, .24, .24, .04], size=k))
+            for k in (16, 5, 4, 1, 204, 204, 7, 2300, 12)]
+    buf, starts, lens = synth.join_records(recs)
+    tables, kinds = dnashape.synthetic_tables()
+    tab = ctx.upload_shapes(tables, kinds)
+    enc = ctx.encode(buf)
+    got = ctx.shape_tracks(enc, tab, starts, lens)
+    for rec, s, ln in zip(recs, starts, lens):
+        ref = so.tracks(rec, tables, kinds)
+        assert np.array_equal(got[:, s: s + ln], ref, equal_nan=True), ln
+    enc.close()
+    tab.close()
+
+
+def test_get_dna_shape_vs_reference_golden_both_input_forms(ctx, golden):
+    """utils._get_DNA_shape on (a) the reference's token-list dict and (b) a GenomeShapeSource
+    that computes shapes from sequence on the GPU — both must equal the reference's output."""
+    shapes = tuple(golden["meta"]["shapes"])
+    tables, kinds = dnashape.synthetic_tables(shapes, seed=golden["meta"]["table_seed"])
+    src = U.GenomeShapeSource(records=golden["genome"], tables=tables, kinds=kinds, shapes=shapes, ctx=ctx)
+    for case in golden["get_dna_shape"]:
+        legacy = U._get_DNA_shape(case["loc"], golden["shape_tokens"][case["shape"]], case["shape"])
+        assert legacy == case["out"], ("dict", case["loc"], case["shape"])
+        fresh = U._get_DNA_shape(case["loc"], src[case["shape"]], case["shape"])
+        assert fresh == case["out"], ("gpu", case["loc"], case["shape"])
+
+
+def _assert_table_equal(df, gold_table, float_tol=0.0, sim_tol=1e-12):
+    assert list(df.columns) == gold_table["columns"]
+    assert [str(t) for t in df.dtypes] == gold_table["dtypes"]
+    want = pd.DataFrame(gold_table["rows"], columns=gold_table["columns"])
+    for col in df.columns:
+        if col in ("location", "sequence", "seq_type"):
+            assert list(df[col]) == list(want[col]), col
+        else:
+            a = df[col].to_numpy(dtype=np.float64)
+            b = want[col].astype(float).to_numpy()
+            tol = sim_tol if col in ("MinHash", "PAS", "PPS") else float_tol
+            assert np.array_equal(np.isnan(a), np.isnan(b)), col
+            assert np.nanmax(np.abs(a - b), initial=0.0) <= tol, col
+
+
+def test_build_feature_table_vs_reference_golden(ctx, golden, tmp_path):
+    ft = golden["feature_table"]
+    fg, cand = tmp_path / "fg.fasta", tmp_path / "cand.fasta"
+    fg.write_text("".join(f">{n}\n{s}\n" for n, s in ft["fg"]))
+    cand.write_text("".join(f">{n}\n{s}\n" for n, s in ft["cand"]))
+    shapes = tuple(golden["meta"]["shapes"])
+    tables, kinds = dnashape.synthetic_tables(shapes, seed=golden["meta"]["table_seed"])
+    src = U.GenomeShapeSource(records=golden["genome"], tables=tables, kinds=kinds, shapes=shapes, ctx=ctx)
+    # reference call shapes: (fg, fg, shape_data), (cand, fg, shape_data), (cand, fg, minhash=False)
+    _assert_table_equal(U.build_feature_table(str(fg), str(fg), golden["shape_tokens"], minhash=True), ft["fg_table"])
+    _assert_table_equal(U.build_feature_table(str(fg), str(fg), src, minhash=True), ft["fg_table"])
+    _assert_table_equal(U.build_feature_table(str(cand), str(fg), src, minhash=True), ft["cand_table"])
+    _assert_table_equal(U.build_feature_table(str(cand), str(fg), minhash=False), ft["cand_noshape_table"])
+
+
+def test_background_shape_table_vs_reference_golden(ctx, golden, tmp_path):
+    bg = golden["background"]
+    path = tmp_path / "bkg.fasta"
+    path.write_text("".join(f">{n}\n{s}\n" for n, s in bg["records"]))
+    shapes = tuple(golden["meta"]["shapes"])
+    tables, kinds = dnashape.synthetic_tables(shapes, seed=golden["meta"]["table_seed"])
+    df = U.background_shape_table(str(path), tables, kinds, shapes, ctx=ctx)
+    _assert_table_equal(df, bg["shapes_data_df"])
+    # DNAshapeR-format writer round-trips through the reference's own parser rules
+    out = dnashape.getDNAShape(str(path), "Roll", ctx=ctx, tables=tables, kinds=kinds, shapes=shapes)
+    assert open(out).read() == bg["shape_file_text"]["Roll"]
+
+
+def test_shape_sites_mode0_property_large(ctx):
+    """Sites sliced from a 2 Mb chromosome equal slices of the full tracks (both strands)."""
+    n = 2_000_000
+    seq = synth.genome(39, 0, n, gc=0.335)
+    tables, kinds = dnashape.synthetic_tables()
+    tab = ctx.upload_shapes(tables, kinds)
+    enc = ctx.encode(seq)
+    tracks = ctx.shape_tracks(enc, tab)
+    rng = np.random.default_rng(4)
+    S = 5000
+    start = rng.integers(1, n - 40, size=S)
+    L = rng.integers(6, 21, size=S)
+    end = start + L
+    strand = np.where(rng.random(S) < 0.5, 1, -1).astype(np.int8)
+    W = 21
+    out = ctx.shape_sites(enc, tab, np.zeros(S, np.int64), np.full(S, n, np.int64), start, end, strand,
+                          width=W, mode=0)
+    for i in rng.integers(0, S, size=300):
+        for t in range(len(kinds)):
+            if strand[i] > 0:
+                ref = tracks[t, start[i]: end[i] + 1]
+            else:
+                ref = tracks[t, end[i]: start[i] - 1: -1]
+            ref = np.where(np.isnan(ref), 0.0, ref)
+            assert np.array_equal(out[i, t, : ref.size], ref)
+            assert np.isnan(out[i, t, ref.size:]).all()
+    enc.close()
+    tab.close()

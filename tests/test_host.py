@@ -1,0 +1,170 @@
+"""CPU tests of the host side: C-ABI surface, bit tricks, generators, host-only feature code."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from discover_tfbs_b200 import _lib, dnashape, similarity, synth
+from discover_tfbs_b200 import utils as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "tfbs_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tfbs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/tfbs_cuda.h but not exported"
+    # and the ctypes binding covers exactly the declared surface
+    assert sorted(_lib.exported_symbols()) == names
+
+
+def test_hit_struct_is_16_bytes():
+    assert _lib.HIT_DTYPE.itemsize == 16
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU every compute entry point must fail loudly."""
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="libtfbs_cuda error"):
+        _lib.Context(0)
+    with pytest.raises(RuntimeError):
+        U.calculate_gc_content("ACGT")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "discover_tfbs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "oracle/" not in text.replace("the oracle/", ""), f
+
+
+def test_swar_encode_bit_tricks_exhaustive():
+    lib = _lib.load()
+    codes, valid = C.c_uint32(0), C.c_uint32(0)
+    expect = {ord(c): i for i, c in enumerate("ACGT")}
+    expect.update({ord(c): i for i, c in enumerate("acgt")})
+    rng = np.random.default_rng(0)
+    for pos in range(4):
+        for b in range(256):
+            others = rng.integers(0, 256, size=4)
+            others[pos] = b
+            w = int(others[0]) | int(others[1]) << 8 | int(others[2]) << 16 | int(others[3]) << 24
+            assert lib.tfbs_debug_swar4(w, C.byref(codes), C.byref(valid)) == 0
+            for k in range(4):
+                byte = int(others[k])
+                ok = byte in expect
+                assert ((valid.value >> k) & 1) == int(ok), (hex(w), k)
+                assert ((codes.value >> (2 * k)) & 3) == (expect[byte] if ok else 0), (hex(w), k)
+    assert valid.value < 16 and codes.value < 256
+
+
+def test_synth_genome_is_position_addressable():
+    a = synth.genome(39, 0, 100_000)
+    b = synth.genome(39, 40_000, 20_000)
+    assert np.array_equal(a[40_000:60_000], b)
+    assert set(np.unique(a)) <= set(b"ACGTacgtN")
+    frac_n = (a == ord("N")).mean()
+    up = np.char.upper(a.view("S1"))
+    gc = np.isin(up, [b"G", b"C"]).sum() / np.isin(up, [b"A", b"C", b"G", b"T"]).sum()
+    assert 0.38 < gc < 0.44 and frac_n < 0.05
+    big = synth.genome(7, 0, 2_000_000)
+    assert 0.03 < np.isin(big, list(b"acgt")).mean() < 0.07
+    # N-runs: ~0.3 % of the 16 384-base blocks carry one run of 100..10 000 Ns
+    blocks = np.arange(200_000, dtype=np.uint64)
+    has = (synth._mix(7, 2, blocks) & np.uint64(0xFFFF)) < np.uint64(213)
+    assert 0.002 < has.mean() < 0.005
+    b = int(np.flatnonzero(has)[0])
+    blk = synth.genome(7, b * 16384, 16384)
+    n_count = int((blk == ord("N")).sum())
+    assert 1 <= n_count <= 10_000
+    runs = np.flatnonzero(np.diff(np.concatenate([[0], (blk == ord("N")).astype(int), [0]])))
+    assert runs.size == 2  # one contiguous run
+
+
+def test_join_records_layout():
+    buf, starts, lens = synth.join_records(["ACGT", "GG", "TTTAA"])
+    assert bytes(buf) == b"ACGT\nGG\nTTTAA" and starts.tolist() == [0, 5, 8] and lens.tolist() == [4, 2, 5]
+    arr = np.frombuffer(b"ACGTTGCA", dtype=np.uint8).reshape(2, 4)
+    buf2, s2, l2 = synth.join_records(arr)
+    assert bytes(buf2) == b"ACGT\nTGCA" and s2.tolist() == [0, 5] and l2.tolist() == [4, 4]
+
+
+def test_pwm_library_and_thresholds():
+    lo, lens = synth.pwm_library(39, 20)
+    assert lo.shape[0] == 20 and lens.min() >= 6 and lens.max() <= 30
+    assert np.isfinite(lo[0, : lens[0]]).all()
+    thr = synth.thresholds_for_rate(lo, lens, rate=1e-3, sample=20_000)
+    assert thr.dtype == np.float32 and np.isfinite(thr).all()
+
+
+def test_synthetic_shape_tables_symmetry():
+    tables, kinds = dnashape.synthetic_tables()
+    idx = np.arange(1024)
+    rc = dnashape._revcomp_index(idx)
+    assert np.array_equal(dnashape._revcomp_index(rc), idx)
+    for t, k in enumerate(kinds):
+        if k == 0:
+            assert np.array_equal(tables[t, 0], tables[t, 0][rc])
+        else:
+            assert np.array_equal(tables[t, 1], tables[t, 0][rc])
+    assert np.array_equal(np.round(tables.astype(np.float64), 2).astype(np.float32), tables)
+
+
+def test_to_reference_float64_equals_printf_roundtrip():
+    rng = np.random.default_rng(1)
+    a = np.round(rng.uniform(-20, 40, size=5000), 2).astype(np.float32)
+    b = np.round(rng.uniform(-20, 40, size=5000), 2).astype(np.float32)
+    v = np.concatenate([a, (a + b) * np.float32(0.5)])
+    got = dnashape.to_reference_float64(v)
+    want = np.array([float("%.2f" % float(x)) for x in v])
+    assert np.array_equal(got, want)
+
+
+def test_primitives_vs_reference_golden(golden):
+    for s, out in golden["primitives"]["reverse_complement"]:
+        assert U.reverse_complement(s) == out
+    with pytest.raises(KeyError):
+        U.reverse_complement("acgt")  # the reference's table has upper-case keys only
+    for s, k, out in golden["primitives"]["get_kmers"]:
+        assert U.get_kmers(s, k) == out
+
+
+def test_similarity_vs_reference_golden(golden):
+    for kmer, h in golden["similarity"]["minhash_kmer"]:
+        assert similarity._canonical_hash(kmer) == h
+    assert similarity.murmurhash3_32(b"foo", 0) == (-156908512) & 0xFFFFFFFF
+    for a, b, v in golden["similarity"]["jaccard"]:
+        assert similarity.jaccard_similarity(a, b) == v
+    for a, b, (pas, pps) in golden["similarity"]["pac"]:
+        got = similarity.pac(a, b)
+        assert abs(got[0] - pas) < 1e-12 and abs(got[1] - pps) < 1e-12
+
+
+def test_parse_fasta_and_locations(tmp_path):
+    p = tmp_path / "x.fasta"
+    p.write_text(">chr1:5-17(-) extra\nACGT\nTT GG\n>b\n\nAC\n")
+    assert list(U.parse_fasta(str(p))) == [("chr1:5-17(-) extra", "ACGTTTGG"), ("b", "AC")]
+    chrom, s, e, sd = U.parse_locations(["Ca22chr1A:293970-293981(-)", "c:0-12(+)"])
+    assert chrom == ["Ca22chr1A", "c"] and s.tolist() == [293970, 0] and e.tolist() == [293981, 12]
+    assert sd.tolist() == [-1, 1]
+    with pytest.raises(SystemExit):
+        next(U.parse_fasta(str(tmp_path / "missing.fasta")))
+
+
+def test_tokens_to_values_rule():
+    v = U._tokens_to_values(["NA", "5.12", "", "-3.40", "x"])
+    assert v.tolist() == [0.0, 5.12, 0.0, -3.4, 0.0]
