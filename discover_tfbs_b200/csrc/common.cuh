@@ -83,6 +83,15 @@ struct tfbs_pwms {
     std::vector<float> fslack_host;
     int64_t lut_entries = 0;
     int32_t Gmax = 0;
+    // ---- hits mode (scan_hits.cu): motifs sorted by length, 32 per block, one lane each ----
+    int32_t n_blocks = 0;
+    std::vector<int32_t> blk_G, blk_lut_off, blk_motif;  // [n_blocks], [n_blocks], [n_blocks][32]
+    std::vector<double> kmer_f64;    // [M][2][11][64] double 3-mer partial sums (fwd, revcomp)
+    int64_t hq_lut_words = 0;        // total uint32 entries of the packed deficit tables
+    uint32_t *hq_lut_dev = nullptr, *hq_kinit_dev = nullptr;
+    int32_t *blk_G_dev = nullptr, *blk_lut_off_dev = nullptr, *blk_motif_dev = nullptr, *lens_dev = nullptr;
+    std::vector<float> hq_thr;       // thresholds the cached tables were built for
+    bool hq_valid = false;
 };
 
 struct tfbs_shapes {

@@ -9,17 +9,12 @@
 // log-odds values rounded once to fp32, fwd and rev packed as float2) so a window of length L
 // costs ceil(L/3) shared-memory loads for both strands.  The 6-bit LUT index is sliced straight
 // out of the 2-bit packed sequence held in registers.
-//   dense mode : fp32 accumulation, scores written for every (motif, start, strand).
-//   hits mode  : the same fp32 score is used only as a filter with a proven error slack; every
-//                candidate is re-scored left to right in double and cast to float, which is the
-//                oracle's arithmetic, so hit sets and scores are bit-exact.
+//   dense mode (this file): fp32 accumulation, scores written for every (motif, start, strand).
+//   hits mode (scan_hits.cu): packed fixed-point filter + exact double re-scoring of candidates.
 #include <algorithm>
 #include <cmath>
-#include <cooperative_groups.h>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -40,12 +35,6 @@ struct ScanParams {
     int32_t M;
     float *out_fwd;
     float *out_rev;
-    const float *thr_lo;  // filter threshold (thr - slack)
-    const float *thr;     // exact threshold
-    const double *exact;  // [M][2][32][4]
-    tfbs_hit *hits;
-    unsigned long long *hit_count;
-    unsigned long long cap;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
@@ -56,42 +45,8 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Oracle arithmetic for one window: left-to-right double sum, cast to float, compare.
-__device__ __noinline__ void rescore_and_emit(const uint32_t *__restrict__ packed,
-                                              const double *__restrict__ exact,
-                                              const float *__restrict__ thr, tfbs_hit *hits,
-                                              unsigned long long *hit_count, unsigned long long cap,
-                                              int64_t gpos, int m, int strand, int L)
-{
-    const double *mat = exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
-    double s = 0.0;
-    for (int j = 0; j < L; j++) {
-        const int64_t i = gpos + j;
-        const uint32_t code = (__ldg(packed + (i >> 4)) >> (2 * (i & 15))) & 3u;
-        s += __ldg(mat + j * 4 + code);
-    }
-    const float f = (float)s;
-    const bool hit = f >= __ldg(thr + m);
-    if (hit) {
-        // warp-aggregated compaction: one atomic per group of simultaneously hitting lanes
-        cg::coalesced_group g = cg::coalesced_threads();
-        unsigned long long base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(hit_count, (unsigned long long)g.size());
-        base = g.shfl(base, 0);
-        const unsigned long long slot = base + g.thread_rank();
-        if (slot < cap) {
-            tfbs_hit h;
-            h.pos = strand ? ~gpos : gpos;
-            h.motif = m;
-            h.score = f;
-            hits[slot] = h;
-        }
-    }
-}
-
-template <bool HITS>
 __global__ void __launch_bounds__(kScanThreads)
-scan_kernel(const ScanParams P)
+scan_dense_kernel(const ScanParams P)
 {
     __shared__ __align__(16) uint32_t s_words[kTileWords];
     __shared__ __align__(16) uint32_t s_mask[kTileMask];
@@ -168,46 +123,21 @@ scan_kernel(const ScanParams P)
             w2 >>= 6;
         }
         const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-        if (!HITS) {
-            const float qnan = __int_as_float(0x7FC00000);
+        const float qnan = __int_as_float(0x7FC00000);
 #pragma unroll
-            for (int p = 0; p < kPosPerThread; p++) {
-                const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
-                if (bad) accf[p] = accr[p] = qnan;
-            }
-            float4 *of = reinterpret_cast<float4 *>(P.out_fwd + (size_t)m * P.pitch + tile_start + p0);
-            float4 *orv = reinterpret_cast<float4 *>(P.out_rev + (size_t)m * P.pitch + tile_start + p0);
-            __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
-            __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
-            __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
-            __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
-        } else {
-            const float tlo = __ldg(P.thr_lo + m);
-#pragma unroll
-            for (int p = 0; p < kPosPerThread; p++) {
-                const bool cf = accf[p] >= tlo, cr = accr[p] >= tlo;
-                if (cf || cr) {
-                    const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
-                    if (!bad) {
-                        if (cf) rescore_and_emit(P.packed, P.exact, P.thr, P.hits, P.hit_count, P.cap, tile_start + p0 + p, m, 0, L);
-                        if (cr) rescore_and_emit(P.packed, P.exact, P.thr, P.hits, P.hit_count, P.cap, tile_start + p0 + p, m, 1, L);
-                    }
-                }
-            }
+        for (int p = 0; p < kPosPerThread; p++) {
+            const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
+            if (bad) accf[p] = accr[p] = qnan;
         }
+        float4 *of = reinterpret_cast<float4 *>(P.out_fwd + (size_t)m * P.pitch + tile_start + p0);
+        float4 *orv = reinterpret_cast<float4 *>(P.out_rev + (size_t)m * P.pitch + tile_start + p0);
+        __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
+        __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
+        __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
+        __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
     }
     cp_async_wait_all();
 }
-
-struct HitLess {
-    bool operator()(const tfbs_hit &a, const tfbs_hit &b) const
-    {
-        if (a.motif != b.motif) return a.motif < b.motif;
-        const int64_t pa = a.pos < 0 ? ~a.pos : a.pos, pb = b.pos < 0 ? ~b.pos : b.pos;
-        if (pa != pb) return pa < pb;
-        return (a.pos < 0) < (b.pos < 0);
-    }
-};
 
 void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_t pitch)
 {
@@ -219,11 +149,6 @@ void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_
     P.glen = pw->glen;
     P.M = pw->M;
     P.out_fwd = P.out_rev = nullptr;
-    P.thr_lo = P.thr = nullptr;
-    P.exact = pw->exact;
-    P.hits = nullptr;
-    P.hit_count = nullptr;
-    P.cap = 0;
 }
 
 }  // namespace
@@ -254,6 +179,7 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->logodds.assign(logodds, logodds + (size_t)M * Lmax * 4);
 
     std::vector<double> exact((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
+    p->kmer_f64.assign((size_t)M * 2 * kMaxGroups * 64, 0.0);
     std::vector<int32_t> lut_off(M), glen(M);
     std::vector<float2> lut;
     p->fslack_host.resize(M);
@@ -280,6 +206,8 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
                     sf += F[(3 * g + j) * 4 + b];
                     sr += R[(3 * g + j) * 4 + b];
                 }
+                p->kmer_f64[((size_t)(m * 2 + 0) * kMaxGroups + g) * 64 + x] = sf;
+                p->kmer_f64[((size_t)(m * 2 + 1) * kMaxGroups + g) * 64 + x] = sr;
                 if (std::isfinite(sf)) gmax = std::max(gmax, std::fabs(sf));
                 if (std::isfinite(sr)) gmax = std::max(gmax, std::fabs(sr));
                 lut.push_back(make_float2((float)sf, (float)sr));
@@ -293,10 +221,42 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->Gmax = Gmax;
     p->lut_entries = (int64_t)lut.size();
 
+    // hits mode: motifs sorted by descending length, 32 per block (one warp lane each)
+    std::vector<int32_t> order(M);
+    for (int m = 0; m < M; m++) order[m] = m;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    p->n_blocks = (M + 31) / 32;
+    p->blk_G.assign(p->n_blocks, 1);
+    p->blk_lut_off.assign(p->n_blocks, 0);
+    p->blk_motif.assign((size_t)p->n_blocks * 32, -1);
+    int64_t words = 0;
+    for (int b = 0; b < p->n_blocks; b++) {
+        int g = 1;
+        for (int l = 0; l < 32 && b * 32 + l < M; l++) {
+            const int m = order[b * 32 + l];
+            p->blk_motif[(size_t)b * 32 + l] = m;
+            g = std::max(g, (lens[m] + 2) / 3);
+        }
+        p->blk_G[b] = g;
+        p->blk_lut_off[b] = (int32_t)words;
+        words += (int64_t)g * 64 * 32;
+    }
+    p->hq_lut_words = words;
+
     cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&p->lut, lut.size() * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc(&p->lut_off, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->hq_lut_dev, (size_t)p->hq_lut_words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->hq_kinit_dev, (size_t)p->n_blocks * 32 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_G_dev, (size_t)p->n_blocks * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_lut_off_dev, (size_t)p->n_blocks * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_motif_dev, (size_t)p->n_blocks * 32 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->lens_dev, (size_t)M * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(p->blk_G_dev, p->blk_G.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->blk_lut_off_dev, p->blk_lut_off.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->blk_motif_dev, p->blk_motif.data(), (size_t)p->n_blocks * 32 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->lens_dev, lens, (size_t)M * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->exact, exact.data(), exact.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lut_off, lut_off.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -318,6 +278,12 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (p->lut) cudaFree(p->lut);
     if (p->lut_off) cudaFree(p->lut_off);
     if (p->glen) cudaFree(p->glen);
+    if (p->hq_lut_dev) cudaFree(p->hq_lut_dev);
+    if (p->hq_kinit_dev) cudaFree(p->hq_kinit_dev);
+    if (p->blk_G_dev) cudaFree(p->blk_G_dev);
+    if (p->blk_lut_off_dev) cudaFree(p->blk_lut_off_dev);
+    if (p->blk_motif_dev) cudaFree(p->blk_motif_dev);
+    if (p->lens_dev) cudaFree(p->lens_dev);
     delete p;
     return TFBS_OK;
 }
@@ -341,7 +307,7 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
     P.out_fwd = (float *)ctx->dense_fwd.ptr;
     P.out_rev = (float *)ctx->dense_rev.ptr;
     tfbs_begin(ctx);
-    scan_kernel<false><<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
+    scan_dense_kernel<<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
     tfbs_launched(ctx);
     rc = tfbs_end(ctx);
     if (rc) return rc;
@@ -352,69 +318,6 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
         TFBS_CHECK_CUDA(cudaMemcpy2DAsync(rev_host, (size_t)n * 4, ctx->dense_rev.ptr, (size_t)pitch * 4,
                                           (size_t)n * 4, pwms->M, cudaMemcpyDeviceToHost, ctx->stream));
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    return TFBS_OK;
-}
-
-int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const float *thr,
-                   tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits)
-{
-    TFBS_REQUIRE(ctx && seq && pwms && thr && n_hits && cap >= 0, "tfbs_scan_hits: bad argument");
-    TFBS_REQUIRE(seq->ctx == ctx && pwms->ctx == ctx, "tfbs_scan_hits: handle from another context");
-    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
-    *n_hits = 0;
-    const int64_t n = seq->n;
-    if (n == 0) return TFBS_OK;
-    const int M = pwms->M;
-    int rc = tfbs_scratch_reserve(ctx->hits, (size_t)std::max<int64_t>(cap, 1) * sizeof(tfbs_hit));
-    if (rc) return rc;
-    rc = tfbs_scratch_reserve(ctx->hit_count, 64);
-    if (rc) return rc;
-    rc = tfbs_scratch_reserve(ctx->thr, (size_t)M * 2 * sizeof(float));
-    if (rc) return rc;
-    std::vector<float> th(2 * (size_t)M);
-    for (int m = 0; m < M; m++) {
-        const float t = thr[m];
-        th[m] = t;
-        // filter threshold: exact threshold minus the proven fp32 slack and one ulp of the
-        // threshold itself (the oracle compares the float-rounded double score)
-        float lo = t;
-        if (std::isfinite(t)) {
-            const double d = (double)t - (double)pwms->fslack_host[m] - std::fabs((double)t) * std::ldexp(1.0, -22);
-            lo = std::nextafterf((float)d, -INFINITY);
-        }
-        th[M + m] = lo;
-    }
-    TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->thr.ptr, th.data(), th.size() * sizeof(float),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    TFBS_CHECK_CUDA(cudaMemsetAsync(ctx->hit_count.ptr, 0, 64, ctx->stream));
-    const int64_t pitch = ((n + kTile - 1) / kTile) * kTile;
-    ScanParams P;
-    fill_params(P, seq, pwms, pitch);
-    P.thr = (const float *)ctx->thr.ptr;
-    P.thr_lo = P.thr + M;
-    P.hits = (tfbs_hit *)ctx->hits.ptr;
-    P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
-    P.cap = (unsigned long long)cap;
-    tfbs_begin(ctx);
-    scan_kernel<true><<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
-    tfbs_launched(ctx);
-    rc = tfbs_end(ctx);
-    if (rc) return rc;
-    unsigned long long cnt = 0;
-    TFBS_CHECK_CUDA(cudaMemcpyAsync(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
-    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-    *n_hits = (int64_t)cnt;
-    const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
-    if (out_host && take > 0) {
-        TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
-                                        cudaMemcpyDeviceToHost, ctx->stream));
-        TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (sorted) std::sort(out_host, out_host + take, HitLess());
-    }
-    if ((int64_t)cnt > cap) {
-        tfbs_set_error("tfbs_scan_hits: %llu hits exceed capacity %lld", cnt, (long long)cap);
-        return TFBS_ERR_OVERFLOW;
-    }
     return TFBS_OK;
 }
 

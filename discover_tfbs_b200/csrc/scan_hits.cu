@@ -1,0 +1,545 @@
+// scan_hits.cu — (2b) thresholded both-strand PWM scan ("hits mode"), the headline kernel.
+//
+// Replaces Biopython PositionSpecificScoringMatrix.search (Bio/motifs/matrix.py, _pwm.c;
+// SURVEY.md A.1) for a whole motif library in one pass, and generalises the reference's
+// exact-match BLASTn candidate stage (utils.py:340-398, process_blast.sh:32).
+//
+// Design (one warp lane = one motif, so shared-memory LUT reads are bank-conflict free):
+//   * motifs are sorted by length and grouped 32 to a block; a block's table lives in shared
+//     memory as T[g][x][lane] (g = group of 3 motif columns, x = 6-bit 3-mer code, 4 B per
+//     entry): the 32 lanes of a warp read 32 consecutive words for the same (g, x).
+//   * an entry packs two 16-bit fixed-point DEFICITS (how far the 3-mer is below the best 3-mer
+//     of that column group, in units chosen from the threshold), forward strand in the high
+//     half, reverse-complement strand in the low half, so one LDS.32 + one IADD scores both
+//     strands.  Deficits are rounded DOWN and capped, fields are sized so sums never carry, and
+//     a window is a candidate iff bit 15 of its field is still clear — a proven superset of
+//     {score >= threshold}.
+//   * the warp walks its segment base by base (the 3-mer code is warp-uniform, sliced from the
+//     2-bit packed words staged in shared memory by TMA); G loads feed G of the 48 ring
+//     accumulators held in registers; the accumulator that just received its last group is tested.
+//   * candidates (rare) go to a per-warp shared-memory queue and are verified 32 at a time:
+//     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
+//     float, compared with >= — so hit sets and scores are bit-exact.  Hits are compacted with
+//     ballot/popc and one global atomic per warp batch.
+//   * persistent CTAs (2 per SM) pull (motif block, tile) items from an atomic counter in
+//     block-major order, so a CTA re-loads its 8 KB x G table only when the block changes.
+#include <algorithm>
+#include <cmath>
+#include <cooperative_groups.h>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRing = 48;                 // ring accumulators (multiple of 16 and of 3)
+constexpr int kSeg = 2016;                // window starts per warp per tile (42 ring turns)
+constexpr int kTilePos = kWarps * kSeg;   // 16128 starts per tile (multiple of 128)
+constexpr int kTileBases = kTilePos + 128;
+constexpr int kTileWords = kTileBases / 16;  // 1016 words  = 4064 B (multiple of 16)
+constexpr int kTileMask = kTileBases / 32;   // 508 words   = 2032 B (multiple of 16)
+constexpr int kQueueCap = 256;            // candidate queue entries per warp
+constexpr int kMaxG = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
+constexpr uint32_t kPoison = 0x80008000u;
+
+struct HitsParams {
+    const uint32_t *packed;
+    const uint32_t *mask;
+    int64_t n_tiles;
+    int32_t n_blocks;
+    const uint32_t *qlut;        // per block [G_b][64][32] packed deficits
+    const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
+    const int32_t *blk_G;        // [n_blocks]
+    const uint32_t *kinit;       // [n_blocks][32] initial field values (0x7FFF - Dq per strand)
+    const int32_t *blk_motif;    // [n_blocks][32] original motif index or -1
+    const int32_t *lens;         // [M]
+    const float *thr;            // [M]
+    const double *exact;         // [M][2][32][4]
+    tfbs_hit *hits;
+    unsigned long long *hit_count;
+    unsigned long long cap;
+    unsigned int *work_counter;
+};
+
+struct Smem {
+    // LUT region first (8 KB aligned at run time), the rest follows
+    uint32_t *lut;       // [G][64][32]
+    uint32_t *words;     // [kTileWords]
+    uint32_t *mask;      // [kTileMask]
+    uint32_t *queue;     // [kWarps][kQueueCap]
+    uint32_t *qcount;    // [kWarps]
+    int32_t *motif;      // [32]
+    int32_t *len;        // [32]
+    uint64_t *bar;       // mbarrier
+    uint32_t *item;      // broadcast slot
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+struct VerifyCtx {
+    const uint32_t *s_words;
+    const uint32_t *s_mask;
+    const int32_t *s_motif;
+    const int32_t *s_len;
+    const float *thr;
+    const double *exact;
+    int64_t tile_start;
+};
+
+// Oracle arithmetic for one candidate (tile-local start p, motif slot ml, strand).
+__device__ __forceinline__ bool verify(const VerifyCtx &V, int p, int ml, int strand, int *motif_out, float *score_out)
+{
+    const int m = V.s_motif[ml];
+    if (m < 0) return false;
+    const int L = V.s_len[ml];
+    const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    const uint32_t inv = __funnelshift_r(V.s_mask[p >> 5], V.s_mask[(p >> 5) + 1], p & 31) & lmask;
+    if (inv) return false;  // window touches an invalid base: NaN in the oracle, never a hit
+    const double *mat = V.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+    double s = 0.0;
+    for (int j = 0; j < L; j++) {
+        const int i = p + j;
+        const uint32_t code = (V.s_words[i >> 4] >> (2 * (i & 15))) & 3u;
+        s += __ldg(mat + j * 4 + code);
+    }
+    const float f = (float)s;
+    *motif_out = m;
+    *score_out = f;
+    return f >= __ldg(V.thr + m);
+}
+
+__device__ __forceinline__ void store_hit(tfbs_hit *hits, unsigned long long slot, unsigned long long cap,
+                                          int64_t gpos, int strand, int m, float f)
+{
+    if (slot < cap) {
+        tfbs_hit h;
+        h.pos = strand ? ~gpos : gpos;
+        h.motif = m;
+        h.score = f;
+        hits[slot] = h;
+    }
+}
+
+struct PushCtx {
+    uint32_t *queue;   // this warp's queue
+    uint32_t *qcount;  // this warp's counter
+    int seg_begin, seg_end;
+    int lane;
+    const VerifyCtx *V;
+    tfbs_hit *hits;
+    unsigned long long *hit_count;
+    unsigned long long cap;
+};
+
+// Cold path: a lane found a candidate field (bit 31 = forward, bit 15 = reverse).
+__device__ __noinline__ void push_candidate(const PushCtx &C, uint32_t cand, int p)
+{
+    if (p < C.seg_begin || p >= C.seg_end) return;  // ring lead-in / overshoot of the last turn
+#pragma unroll
+    for (int strand = 0; strand < 2; strand++) {
+        if (!(cand & (strand ? 0x00008000u : 0x80000000u))) continue;
+        const uint32_t slot = atomicAdd(C.qcount, 1u);
+        if (slot < (uint32_t)kQueueCap) {
+            C.queue[slot] = (uint32_t)p | ((uint32_t)C.lane << 16) | ((uint32_t)strand << 31);
+        } else {
+            // queue full (pathological thresholds): verify right here, divergently
+            int m;
+            float f;
+            if (verify(*C.V, p, C.lane, strand, &m, &f)) {
+                cg::coalesced_group g = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(C.hit_count, (unsigned long long)g.size());
+                base = g.shfl(base, 0);
+                store_hit(C.hits, base + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, f);
+            }
+        }
+    }
+}
+
+// Warp-synchronous verification of the queued candidates, 32 at a time; hits are compacted with
+// ballot/popc and one atomic per batch.
+__device__ __forceinline__ void drain_queue(const PushCtx &C)
+{
+    __syncwarp();
+    const uint32_t cnt = min(*C.qcount, (uint32_t)kQueueCap);
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + C.lane;
+        bool hit = false;
+        int m = 0, p = 0, strand = 0;
+        float f = 0.f;
+        if (i < cnt) {
+            const uint32_t e = C.queue[i];
+            p = (int)(e & 0xFFFFu);
+            strand = (int)(e >> 31);
+            hit = verify(*C.V, p, (int)((e >> 16) & 31u), strand, &m, &f);
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+        if (ballot) {
+            unsigned long long slot0 = 0;
+            if (C.lane == 0) slot0 = atomicAdd(C.hit_count, (unsigned long long)__popc(ballot));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            if (hit)
+                store_hit(C.hits, slot0 + __popc(ballot & ((1u << C.lane) - 1u)), C.cap, C.V->tile_start + p, strand, m, f);
+        }
+    }
+    __syncwarp();
+    if (C.lane == 0) *C.qcount = 0;
+    __syncwarp();
+}
+
+// One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 motifs of the
+// resident block.  G = column groups of the block (compile time, so the 48-entry accumulator ring
+// and all LUT offsets are static).
+template <int G>
+__device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s_words, uint32_t lut_lane_addr,
+                                             uint32_t kinit)
+{
+    uint32_t acc[kRing];
+#pragma unroll
+    for (int i = 0; i < kRing; i++) acc[i] = kPoison;
+    const uint32_t *wptr = s_words + (C.seg_begin >> 4);
+    uint32_t wlo = wptr[0], whi = wptr[1];
+    int wk = 2;
+    constexpr int kTail = 3 * (G - 1);
+    constexpr int kChunks = (kSeg + kTail + kRing - 1) / kRing;
+    for (int c = 0; c < kChunks; c++) {
+        const int q0 = C.seg_begin + c * kRing;
+#pragma unroll
+        for (int j = 0; j < kRing; j++) {
+            const int jj = j & 15;
+            // bits [7,13) of t7 = 3-mer code at base q0 + j
+            const uint32_t t7 = (2 * jj >= 7) ? __funnelshift_r(wlo, whi, 2 * jj - 7) : (wlo << (7 - 2 * jj));
+            const uint32_t addr = (t7 & 0x1F80u) | lut_lane_addr;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const uint32_t v = lds32(addr + g * 8192);
+                const int slot = (j - 3 * g + 2 * kRing) % kRing;
+                if (g == 0) acc[slot] = kinit + v;
+                else acc[slot] += v;
+            }
+            const int fs = (j - kTail + 2 * kRing) % kRing;
+            const uint32_t cand = ~acc[fs] & kPoison;
+            if (cand) push_candidate(C, cand, q0 + j - kTail);
+            if (jj == 15) {
+                wlo = whi;
+                whi = wptr[wk++];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+scan_hits_kernel(const HitsParams P, const int lut_groups)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // carve shared memory; the LUT must start on an 8 KB boundary of the shared window so that
+    // (g << 13) | (x << 7) | (lane << 2) can be OR-ed into the address
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t lut_off = ((raw + 8191u) & ~8191u) - raw;
+    Smem S;
+    uint8_t *p = smem_raw + lut_off;
+    S.lut = reinterpret_cast<uint32_t *>(p);
+    p += (size_t)lut_groups * 8192;
+    S.words = reinterpret_cast<uint32_t *>(p);
+    p += kTileWords * 4;
+    S.mask = reinterpret_cast<uint32_t *>(p);
+    p += kTileMask * 4;
+    S.queue = reinterpret_cast<uint32_t *>(p);
+    p += kWarps * kQueueCap * 4;
+    S.qcount = reinterpret_cast<uint32_t *>(p);
+    p += kWarps * 4;
+    S.motif = reinterpret_cast<int32_t *>(p);
+    p += 32 * 4;
+    S.len = reinterpret_cast<int32_t *>(p);
+    p += 32 * 4;
+    S.bar = reinterpret_cast<uint64_t *>(p);
+    p += 16;
+    S.item = reinterpret_cast<uint32_t *>(p);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(S.bar, 1);
+    if (tid < kWarps) S.qcount[tid] = 0;
+    __syncthreads();
+
+    const uint32_t total_items = (uint32_t)(P.n_tiles * P.n_blocks);
+    int cur_block = -1;
+    uint32_t phase = 0;
+    uint32_t kinit = kPoison;
+    int G = 1;
+    for (;;) {
+        if (tid == 0) *S.item = atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = *S.item;
+        if (item >= total_items) break;
+        const int b = (int)(item / (uint32_t)P.n_tiles);
+        const int64_t tile = (int64_t)(item % (uint32_t)P.n_tiles);
+        const int64_t tile_start = tile * kTilePos;
+        const bool new_block = b != cur_block;
+        if (new_block) G = __ldg(P.blk_G + b);
+        if (tid == 0) {
+            // order the previous item's generic-proxy reads before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = kTileWords * 4 + kTileMask * 4 + (new_block ? (uint32_t)G * 8192u : 0u);
+            mbar_expect_tx(S.bar, bytes);
+            tma_load_1d(S.words, P.packed + (tile_start >> 4), kTileWords * 4, S.bar);
+            tma_load_1d(S.mask, P.mask + (tile_start >> 5), kTileMask * 4, S.bar);
+            if (new_block) {
+                const uint32_t *src = P.qlut + __ldg(P.blk_lut_off + b);
+                for (int g = 0; g < G; g++) tma_load_1d(S.lut + g * 2048, src + g * 2048, 8192, S.bar);
+            }
+        }
+        if (new_block) {
+            if (tid < 32) {
+                const int m = __ldg(P.blk_motif + b * 32 + tid);
+                S.motif[tid] = m;
+                S.len[tid] = m >= 0 ? __ldg(P.lens + m) : 0;
+            }
+            kinit = __ldg(P.kinit + b * 32 + lane);
+            cur_block = b;
+        }
+        mbar_wait(S.bar, phase);
+        phase ^= 1u;
+        __syncthreads();  // S.motif / S.len visible
+
+        VerifyCtx V;
+        V.s_words = S.words;
+        V.s_mask = S.mask;
+        V.s_motif = S.motif;
+        V.s_len = S.len;
+        V.thr = P.thr;
+        V.exact = P.exact;
+        V.tile_start = tile_start;
+        PushCtx C;
+        C.queue = S.queue + warp * kQueueCap;
+        C.qcount = S.qcount + warp;
+        C.seg_begin = warp * kSeg;
+        C.seg_end = C.seg_begin + kSeg;
+        C.lane = lane;
+        C.V = &V;
+        C.hits = P.hits;
+        C.hit_count = P.hit_count;
+        C.cap = P.cap;
+        const uint32_t lut_lane_addr = smem_u32(S.lut) + (uint32_t)lane * 4u;
+        switch (G) {
+#define TFBS_CASE(g) \
+    case g: scan_segment<g>(C, S.words, lut_lane_addr, kinit); break;
+            TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6)
+            TFBS_CASE(7) TFBS_CASE(8) TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11)
+#undef TFBS_CASE
+            default: break;
+        }
+        drain_queue(C);
+        __syncthreads();  // tile buffers and S.item are reused by the next item
+    }
+}
+
+struct HitLess {
+    bool operator()(const tfbs_hit &a, const tfbs_hit &b) const
+    {
+        if (a.motif != b.motif) return a.motif < b.motif;
+        const int64_t pa = a.pos < 0 ? ~a.pos : a.pos, pb = b.pos < 0 ? ~b.pos : b.pos;
+        if (pa != pb) return pa < pb;
+        return (a.pos < 0) < (b.pos < 0);
+    }
+};
+
+size_t hits_smem_bytes(int lut_groups)
+{
+    return 8192 /* alignment slack */ + (size_t)lut_groups * 8192 + kTileWords * 4 + kTileMask * 4 +
+           kWarps * kQueueCap * 4 + kWarps * 4 + 64 * 4 + 16 + 16;
+}
+
+}  // namespace
+
+// Quantise the block tables for a threshold vector (host).  See the header comment for the
+// construction; everything rounds in the direction that keeps {candidates} a superset of {hits}.
+int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
+{
+    const int M = pw->M;
+    if (pw->hq_valid && pw->hq_thr.size() == (size_t)M && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * M) == 0)
+        return TFBS_OK;
+    const int nb = pw->n_blocks;
+    std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
+    std::vector<uint32_t> kinit((size_t)nb * 32, kPoison);
+    for (int b = 0; b < nb; b++) {
+        const int G = pw->blk_G[b];
+        uint32_t *lut = qlut.data() + pw->blk_lut_off[b];
+        const int dq_max = 0x7FFF / G - 3;
+        const int capq = dq_max + 2;
+        for (int l = 0; l < 32; l++) {
+            const int m = pw->blk_motif[(size_t)b * 32 + l];
+            if (m < 0) continue;
+            const int Gm = (pw->lens[m] + 2) / 3;
+            const float t = thr[m];
+            uint32_t kfield[2] = {0x8000u, 0x8000u};
+            for (int s = 0; s < 2; s++) {
+                const double *e = pw->kmer_f64.data() + ((size_t)(m * 2 + s) * kMaxG) * 64;
+                double gmax[kMaxG];
+                double best = 0.0;
+                bool reachable = true;
+                for (int g = 0; g < Gm; g++) {
+                    double mx = -INFINITY;
+                    for (int x = 0; x < 64; x++) mx = std::max(mx, e[g * 64 + x]);
+                    gmax[g] = mx;
+                    best += mx;
+                    if (!std::isfinite(mx)) reachable = false;  // a column group of -inf only
+                }
+                if (std::isnan(t)) reachable = false;
+                // D: how much a hit may lose against the best possible score (plus slack for the
+                // float rounding of the oracle's comparison and double summation order)
+                double D = reachable ? (best - (double)t) : -1.0;
+                if (reachable && std::isfinite(D)) D += std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(best) * 1e-12 + 1e-9;
+                if (!reachable || D < 0.0) continue;  // field stays poisoned: never a candidate
+                double scale;
+                int Dq;
+                if (std::isinf(D)) {
+                    scale = 0.0;  // threshold -inf: everything is a candidate
+                    Dq = 1;
+                } else {
+                    scale = (double)dq_max / std::max(D, 1e-300);
+                    if (!std::isfinite(scale)) scale = 1e300;
+                    const double dqv = std::floor(D * scale) + 1.0;
+                    Dq = (int)std::min(dqv, (double)(dq_max + 1));
+                }
+                kfield[s] = (uint32_t)(0x7FFF - Dq);
+                for (int g = 0; g < Gm; g++)
+                    for (int x = 0; x < 64; x++) {
+                        const double d = gmax[g] - e[g * 64 + x];  // >= 0, +inf for -inf entries
+                        int q;
+                        if (scale == 0.0) q = 0;
+                        else {
+                            const double v = std::floor(d * scale);
+                            q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
+                        }
+                        uint32_t &w = lut[((size_t)g * 64 + x) * 32 + l];
+                        w |= s == 0 ? ((uint32_t)q << 16) : (uint32_t)q;
+                    }
+            }
+            kinit[(size_t)b * 32 + l] = (kfield[0] << 16) | kfield[1];
+        }
+    }
+    cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), qlut.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), kinit.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
+        return TFBS_ERR_CUDA;
+    }
+    pw->hq_thr.assign(thr, thr + M);
+    pw->hq_valid = true;
+    return TFBS_OK;
+}
+
+extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms_c, const float *thr,
+                              tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits)
+{
+    TFBS_REQUIRE(ctx && seq && pwms_c && thr && n_hits && cap >= 0, "tfbs_scan_hits: bad argument");
+    TFBS_REQUIRE(seq->ctx == ctx && pwms_c->ctx == ctx, "tfbs_scan_hits: handle from another context");
+    tfbs_pwms *pwms = const_cast<tfbs_pwms *>(pwms_c);  // the threshold-specific tables are a cache
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    *n_hits = 0;
+    const int64_t n = seq->n;
+    if (n == 0) return TFBS_OK;
+    const int M = pwms->M;
+    int rc = tfbs_scratch_reserve(ctx->hits, (size_t)std::max<int64_t>(cap, 1) * sizeof(tfbs_hit));
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->hit_count, 64);
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->thr, (size_t)M * sizeof(float));
+    if (rc) return rc;
+    rc = tfbs_build_hits_tables(pwms, thr);
+    if (rc) return rc;
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->thr.ptr, thr, (size_t)M * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemsetAsync(ctx->hit_count.ptr, 0, 64, ctx->stream));
+
+    HitsParams P;
+    P.packed = seq->packed;
+    P.mask = seq->mask;
+    P.n_tiles = (n + kTilePos - 1) / kTilePos;
+    P.n_blocks = pwms->n_blocks;
+    P.qlut = pwms->hq_lut_dev;
+    P.blk_lut_off = pwms->blk_lut_off_dev;
+    P.blk_G = pwms->blk_G_dev;
+    P.kinit = pwms->hq_kinit_dev;
+    P.blk_motif = pwms->blk_motif_dev;
+    P.lens = pwms->lens_dev;
+    P.thr = (const float *)ctx->thr.ptr;
+    P.exact = pwms->exact;
+    P.hits = (tfbs_hit *)ctx->hits.ptr;
+    P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
+    P.cap = (unsigned long long)cap;
+    P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 16);
+    TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFFFFF0ll, "tfbs_scan_hits: too many work items");
+    TFBS_REQUIRE((P.n_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits: sequence padding too small");
+
+    const int lut_groups = pwms->Gmax;
+    const size_t smem = hits_smem_bytes(lut_groups);
+    TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)ctx->sm_count * 2;
+    grid = std::min<int64_t>(grid, P.n_tiles * P.n_blocks);
+    tfbs_begin(ctx);
+    scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, lut_groups);
+    tfbs_launched(ctx);
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    unsigned long long cnt = 0;
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_hits = (int64_t)cnt;
+    const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
+    if (out_host && take > 0) {
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (sorted) std::sort(out_host, out_host + take, HitLess());
+    }
+    if ((int64_t)cnt > cap) {
+        tfbs_set_error("tfbs_scan_hits: %llu hits exceed capacity %lld", cnt, (long long)cap);
+        return TFBS_ERR_OVERFLOW;
+    }
+    return TFBS_OK;
+}

@@ -183,7 +183,8 @@ def _check_hits(ctx, seq, logodds, lens, thr):
     enc = ctx.encode(seq)
     lib = ctx.upload_pwms(logodds, lens)
     hits = ctx.scan_hits(enc, lib, thr, cap=4096, sort=True)
-    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
     assert hits.size == cnt
     gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
     assert np.array_equal(gpos, pos)
@@ -205,6 +206,37 @@ def test_hits_bit_exact(ctx, n, rate):
     seq = _noisy_seq(rng, n) if n < 100_000 else synth.genome(n, 0, n)
     cnt = _check_hits(ctx, seq, logodds, lens, thr)
     assert cnt > 0
+
+
+def test_hits_many_blocks_tiles_and_mixed_lengths(ctx):
+    """70 motifs (3 lane-blocks with different column-group counts) over 3 tiles of 16 128 starts,
+    with N-runs, lower case and -inf matrix entries."""
+    rng = np.random.default_rng(77)
+    logodds, lens = synth.pwm_library(77, 70, lmin=1, lmax=32)
+    kill = rng.random(logodds.shape) < 0.02
+    logodds = np.where(kill, -np.inf, logodds)
+    thr = synth.thresholds_for_rate(np.where(np.isinf(logodds), -30.0, logodds), lens, rate=2e-3, sample=20_000)
+    seq = synth.genome(77, 5_000_000, 40_000)
+    seq[1000:1400] = ord("N")
+    seq[16120:16140] = np.frombuffer(b"ACGTACGTACGTACGTACGT", dtype=np.uint8)  # across a tile edge
+    cnt = _check_hits(ctx, seq, logodds, lens, thr)
+    assert cnt > 100
+
+
+@pytest.mark.parametrize("kind", ["everything", "nothing", "nan"])
+def test_hits_degenerate_thresholds(ctx, kind):
+    """thr far below every score floods the candidate queues (inline verification path);
+    unreachable and NaN thresholds must yield no hit at all."""
+    rng = np.random.default_rng(6)
+    logodds, lens = synth.pwm_library(6, 5, lmin=6, lmax=14)
+    seq = _noisy_seq(rng, 3000)
+    thr = {"everything": np.full(5, -1e30, np.float32), "nothing": np.full(5, 1e30, np.float32),
+           "nan": np.full(5, np.nan, np.float32)}[kind]
+    cnt = _check_hits(ctx, seq, logodds, lens, thr)
+    if kind == "everything":
+        assert cnt > 2 * 5 * 1500
+    else:
+        assert cnt == 0
 
 
 def test_hits_thresholds_exactly_on_scores_and_overflow(ctx):
