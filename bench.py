@@ -230,7 +230,7 @@ def extras(ctx, args, peak):
         ms.append(ctx.last_kernel_ms())
     t = float(np.mean(ms[3:]))
     nbytes = 8.0 * units + 0.375 * big.size
-    out.append({"kernel": "scan_kernel<dense>", "workload": f"C2 x{reps}: 6 PWMs x {big.size} bp, fwd+rev fp32 scores",
+    out.append({"kernel": "scan_dense_kernel", "workload": f"C2 x{reps}: 6 PWMs x {big.size} bp, fwd+rev fp32 scores",
                 "bytes_per_unit": 8.0, "ms": t, "units_per_s": units / t * 1e3,
                 "achieved_gbs": nbytes / t / 1e6, "frac": nbytes / t / 1e6 / peak})
     enc.close()
@@ -342,7 +342,11 @@ def run_ours(args):
         k_ms = float(np.mean(scan_ms))
         mat_bytes = float(sum(2 * 4 * int(L) * 4 for L in lens))
         algo_bytes = 0.375 * n_scan + mat_bytes + 16.0 * n_hits
-        lookups = float(sum((n_scan - int(L) + 1) * ((int(L) + 2) // 3) for L in lens))  # LDS.64 per unit
+        # hits kernel: one LDS.32 per (motif, base, column group); motifs are sorted by descending
+        # length and grouped 32 per block, every lane of a block runs the block's group count
+        order = np.sort(np.asarray(lens))[::-1]
+        blk_groups = [(int(order[i]) + 2) // 3 for i in range(0, len(order), 32)]
+        lookups = float(n_scan) * 32.0 * float(sum(blk_groups))
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         smem_peak = 148 * 128 * sm_mhz * 1e6  # bytes/s of shared-memory bandwidth at the sampled clock
         line = {
@@ -357,13 +361,13 @@ def run_ours(args):
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {
-                "kernel": "scan_kernel<hits>", "bound": "hbm", "achieved": algo_bytes / k_ms / 1e6, "peak": peak,
+                "kernel": "scan_hits_kernel", "bound": "hbm", "achieved": algo_bytes / k_ms / 1e6, "peak": peak,
                 "unit": "GB/s", "frac": algo_bytes / k_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
                 "note": "hits mode at 800 motifs is bounded by shared-memory LUT bandwidth, not HBM "
                         "(SURVEY.md §7/§8d): the HBM fraction on the algorithmic bytes is reported as is",
-                "smem": {"lut_bytes_per_launch": lookups * 8.0, "achieved_gbs": lookups * 8.0 / k_ms / 1e6,
-                         "peak_gbs": smem_peak / 1e9, "frac": lookups * 8.0 / k_ms / 1e6 / (smem_peak / 1e9),
+                "smem": {"lut_bytes_per_launch": lookups * 4.0, "achieved_gbs": lookups * 4.0 / k_ms / 1e6,
+                         "peak_gbs": smem_peak / 1e9, "frac": lookups * 4.0 / k_ms / 1e6 / (smem_peak / 1e9),
                          "peak_def": "148 SM x 128 B/clk x sampled SM clock"},
             },
             "kernel_ms": {"encode": float(np.mean(enc_ms)), "scan_hits": k_ms},

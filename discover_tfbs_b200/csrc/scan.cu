@@ -18,11 +18,9 @@
 
 namespace {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;                   // one persistent CTA per SM
 constexpr int kPosPerThread = 8;
-constexpr int kTile = kScanThreads * kPosPerThread;  // 2048 window starts per CTA
-constexpr int kTileWords = kTile / 16 + 4;           // + 48-base halo, rounded to 16 B
-constexpr int kTileMask = kTile / 32 + 4;
+constexpr int kTile = kScanThreads * kPosPerThread;  // 8192 window starts per sub-tile
 constexpr int kMaxGroups = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 
 struct ScanParams {
@@ -37,106 +35,81 @@ struct ScanParams {
     float *out_rev;
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-__global__ void __launch_bounds__(kScanThreads)
+// Dense mode.  Persistent CTAs; for each motif the 3-mer table is expanded into shared memory as
+// T[g][x][lane] (float2 = fwd, rev) — one private copy per lane, so the 32 data-dependent
+// LDS.64 of a warp hit 32 different bank pairs: no bank conflicts (the v1 layout T[g][x] lost
+// 60 % of its shared-memory wavefronts to conflicts, profiles/r01/ncu_full_v1_raw.csv).  The CTA
+// then streams over its sub-tiles of 8192 window starts: every thread scores 8 consecutive starts
+// from a 48-base register window and writes 32 B per strand with streaming stores.
+__global__ void __launch_bounds__(kScanThreads, 1)
 scan_dense_kernel(const ScanParams P)
 {
-    __shared__ __align__(16) uint32_t s_words[kTileWords];
-    __shared__ __align__(16) uint32_t s_mask[kTileMask];
-    __shared__ __align__(16) float2 s_lut[2][kMaxGroups * 64];
-
-    const int tid = threadIdx.x;
-    const int64_t tile_start = (int64_t)blockIdx.x * kTile;
-
-    // stage the tile (+halo) of packed words and mask words; the encoded buffer is padded by
-    // >= 8192 bases so these reads never leave the allocation
-    if (tid < kTileWords) s_words[tid] = __ldg(P.packed + (tile_start >> 4) + tid);
-    if (tid >= 128 && tid < 128 + kTileMask) s_mask[tid - 128] = __ldg(P.mask + (tile_start >> 5) + (tid - 128));
-
-    // prefetch LUT of motif 0
-    {
-        const int32_t gl = __ldg(P.glen + 0);
-        const int chunks = (gl >> 8) * 32;
-        const char *src = reinterpret_cast<const char *>(P.lut + __ldg(P.lut_off + 0));
-        for (int c = tid; c < chunks; c += kScanThreads)
-            cp_async16(reinterpret_cast<char *>(s_lut[0]) + c * 16, src + c * 16);
-        cp_async_commit();
-    }
-    __syncthreads();
-
-    // per-thread register window: 48 bases starting at the thread's first window start
-    const int p0 = tid * kPosPerThread;
-    uint32_t W0, W1, W2;
-    {
-        const int wi = p0 >> 4, sh = (p0 & 15) * 2;
-        const uint32_t a0 = s_words[wi], a1 = s_words[wi + 1], a2 = s_words[wi + 2], a3 = s_words[wi + 3];
-        W0 = __funnelshift_r(a0, a1, sh);
-        W1 = __funnelshift_r(a1, a2, sh);
-        W2 = __funnelshift_r(a2, a3, sh);
-    }
-    uint32_t inv_lo, inv_hi;  // invalid bits of bases p0 .. p0+63
-    {
-        const int mi = p0 >> 5, sh = p0 & 31;
-        const uint32_t m0 = s_mask[mi], m1 = s_mask[mi + 1], m2 = s_mask[mi + 2];
-        inv_lo = __funnelshift_r(m0, m1, sh);
-        inv_hi = __funnelshift_r(m1, m2, sh);
-    }
+    extern __shared__ __align__(16) float2 s_lut[];  // [G][64][32]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t n_tiles = P.pitch / kTile;
+    const float qnan = __int_as_float(0x7FC00000);
 
     for (int m = 0; m < P.M; m++) {
-        const int buf = m & 1;
-        cp_async_wait_all();
-        __syncthreads();  // LUT m visible; everyone is done with LUT m-1 (buffer buf^1)
-        if (m + 1 < P.M) {
-            const int32_t gl = __ldg(P.glen + m + 1);
-            const int chunks = (gl >> 8) * 32;
-            const char *src = reinterpret_cast<const char *>(P.lut + __ldg(P.lut_off + m + 1));
-            for (int c = tid; c < chunks; c += kScanThreads)
-                cp_async16(reinterpret_cast<char *>(s_lut[buf ^ 1]) + c * 16, src + c * 16);
-        }
-        cp_async_commit();
-
         const int32_t gl = __ldg(P.glen + m);
         const int G = gl >> 8, L = gl & 255;
-        float accf[kPosPerThread], accr[kPosPerThread];
+        __syncthreads();  // everyone is done with the previous motif's table
+        {
+            const float2 *src = P.lut + __ldg(P.lut_off + m);
+            for (int i = tid; i < G * 64 * 32; i += kScanThreads) s_lut[i] = __ldg(src + (i >> 5));
+        }
+        __syncthreads();
+        const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+        float *row_f = P.out_fwd + (size_t)m * P.pitch;
+        float *row_r = P.out_rev + (size_t)m * P.pitch;
+        const float2 *lut_lane = s_lut + lane;
+
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
+            // 48-base register window starting at p0 (p0 is a multiple of 8)
+            uint32_t w0, w1, w2, inv_lo, inv_hi;
+            {
+                const uint32_t *wp = P.packed + (p0 >> 4);
+                const int sh = (int)(p0 & 15) * 2;
+                const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
+                w0 = __funnelshift_r(a0, a1, sh);
+                w1 = __funnelshift_r(a1, a2, sh);
+                w2 = __funnelshift_r(a2, a3, sh);
+                const uint32_t *mp = P.mask + (p0 >> 5);
+                const int msh = (int)(p0 & 31);
+                const uint32_t m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
+                inv_lo = __funnelshift_r(m0, m1, msh);
+                inv_hi = __funnelshift_r(m1, m2, msh);
+            }
+            float accf[kPosPerThread], accr[kPosPerThread];
 #pragma unroll
-        for (int p = 0; p < kPosPerThread; p++) accf[p] = accr[p] = 0.f;
-        uint32_t w0 = W0, w1 = W1, w2 = W2;
-        const float2 *lg = s_lut[buf];
-        for (int g = 0; g < G; g++) {
+            for (int p = 0; p < kPosPerThread; p++) accf[p] = accr[p] = 0.f;
+            const float2 *lg = lut_lane;
+            for (int g = 0; g < G; g++) {
+#pragma unroll
+                for (int p = 0; p < kPosPerThread; p++) {
+                    const uint32_t x = (w0 >> (2 * p)) & 63u;
+                    const float2 v = lg[x * 32];
+                    accf[p] += v.x;
+                    accr[p] += v.y;
+                }
+                lg += 64 * 32;
+                w0 = __funnelshift_r(w0, w1, 6);
+                w1 = __funnelshift_r(w1, w2, 6);
+                w2 >>= 6;
+            }
 #pragma unroll
             for (int p = 0; p < kPosPerThread; p++) {
-                const uint32_t x = (w0 >> (2 * p)) & 63u;
-                const float2 v = lg[x];
-                accf[p] += v.x;
-                accr[p] += v.y;
+                const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
+                if (bad) accf[p] = accr[p] = qnan;
             }
-            lg += 64;
-            w0 = __funnelshift_r(w0, w1, 6);
-            w1 = __funnelshift_r(w1, w2, 6);
-            w2 >>= 6;
+            float4 *of = reinterpret_cast<float4 *>(row_f + p0);
+            float4 *orv = reinterpret_cast<float4 *>(row_r + p0);
+            __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
+            __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
+            __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
+            __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
         }
-        const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-        const float qnan = __int_as_float(0x7FC00000);
-#pragma unroll
-        for (int p = 0; p < kPosPerThread; p++) {
-            const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
-            if (bad) accf[p] = accr[p] = qnan;
-        }
-        float4 *of = reinterpret_cast<float4 *>(P.out_fwd + (size_t)m * P.pitch + tile_start + p0);
-        float4 *orv = reinterpret_cast<float4 *>(P.out_rev + (size_t)m * P.pitch + tile_start + p0);
-        __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
-        __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
-        __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
-        __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
     }
-    cp_async_wait_all();
 }
 
 void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_t pitch)
@@ -306,8 +279,11 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
     fill_params(P, seq, pwms, pitch);
     P.out_fwd = (float *)ctx->dense_fwd.ptr;
     P.out_rev = (float *)ctx->dense_rev.ptr;
+    const size_t smem = (size_t)pwms->Gmax * 64 * 32 * sizeof(float2);
+    TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = std::min<int64_t>(ctx->sm_count, pitch / kTile);
     tfbs_begin(ctx);
-    scan_dense_kernel<<<(unsigned)(pitch / kTile), kScanThreads, 0, ctx->stream>>>(P);
+    scan_dense_kernel<<<(unsigned)grid, kScanThreads, smem, ctx->stream>>>(P);
     tfbs_launched(ctx);
     rc = tfbs_end(ctx);
     if (rc) return rc;

@@ -8,6 +8,8 @@
 // The pentamer tables (1024 entries per value plane) live in shared memory, indexed by the
 // little-endian pentamer index that falls straight out of the 2-bit packed words
 // (x = sum code[c-2+k] << 2k); the host re-indexes the caller's big-endian tables once.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -43,7 +45,9 @@ shape_tracks_kernel(const TrackParams P)
     }
     __syncthreads();
 
-    const int64_t p0 = (int64_t)blockIdx.x * kShapeTile + tid * kShapePosPerThread;
+    const int64_t n_tiles = P.pitch / kShapeTile;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * kShapeTile + tid * kShapePosPerThread;
     const int64_t b0 = p0 - 8;  // first base of the window (multiple of 8, may be -8)
     uint32_t wlo, whi, inv;
     {
@@ -88,6 +92,7 @@ shape_tracks_kernel(const TrackParams P)
         float4 *o = reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0);
         __stcs(o, make_float4(v[0], v[1], v[2], v[3]));
         __stcs(o + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
     }
 }
 
@@ -332,7 +337,9 @@ int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *sha
     const size_t smem = (size_t)T * 2048 * sizeof(float);
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(shape_tracks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tfbs_begin(ctx);
-    shape_tracks_kernel<<<(unsigned)(pitch / kShapeTile), kShapeThreads, smem, ctx->stream>>>(P);
+    // persistent CTAs: the tables are staged into shared memory once per CTA, not once per tile
+    const int64_t grid = std::min<int64_t>(pitch / kShapeTile, (int64_t)ctx->sm_count * 6);
+    shape_tracks_kernel<<<(unsigned)grid, kShapeThreads, smem, ctx->stream>>>(P);
     tfbs_launched(ctx);
     {
         const int64_t total = S * 2 * T;

@@ -3,7 +3,7 @@
 
     python profiles/profile_kernels.py [--genome-mb 10] [--motifs 800]
 
-Used as:  <cmd> && ncu --set full ... -k regex:'scan_kernel|encode_kernel|shape_tracks' <cmd>
+Used as:  <cmd> && ncu --set full ... -k regex:'scan_hits_kernel|scan_dense_kernel|encode_kernel|shape_tracks' <cmd>
 """
 import argparse
 import os
