@@ -186,7 +186,8 @@ def extras(ctx, args, peak):
     from discover_tfbs_b200 import dnashape, synth
 
     out = []
-    n = int(min(args.genome_mb, 100.0) * 1e6)
+    # streaming kernels are timed on the per-GPU shard of config C5 (3.1 Gb / 8 GPUs = 387.5 Mb)
+    n = int(387.5e6 if args.genome_mb >= 100.0 else args.genome_mb * 1e6)
     dev = ctx.synth_ascii(SEED, 0, n, gc=0.41)
     enc = ctx.encode_device(dev.ptr, n)
     ms = []

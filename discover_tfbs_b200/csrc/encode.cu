@@ -57,19 +57,43 @@ encode_kernel(const uint8_t *__restrict__ ascii, int64_t n, int64_t n_pad,
             else if (idx < n) v[j] = ld_bytes_guarded(ascii, idx, n);
             else v[j] = make_uint4(0, 0, 0, 0);
         }
+        // fast path: assume every byte is ACGTacgt (true for almost every chunk of a genome);
+        // the per-byte validity flags are only OR-reduced here
+        uint32_t word[4], bad = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int64_t idx = base + j * 512;
-            uint32_t v0, v1, v2, v3;
-            uint32_t word = tfbs_swar4(v[j].x, &v0);
-            word |= tfbs_swar4(v[j].y, &v1) << 8;
-            word |= tfbs_swar4(v[j].z, &v2) << 16;
-            word |= tfbs_swar4(v[j].w, &v3) << 24;
-            const uint32_t valid16 = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
-            const uint32_t inv16 = ~valid16 & 0xFFFFu;
-            packed[idx >> 4] = word;
-            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, inv16, 1);
-            if ((lane & 1) == 0) mask[idx >> 5] = inv16 | (other << 16);
+            uint32_t d0, d1, d2, d3;
+            const uint32_t g0 = tfbs_gather_top(tfbs_swar_codes(v[j].x, &d0));
+            const uint32_t g1 = tfbs_gather_top(tfbs_swar_codes(v[j].y, &d1));
+            const uint32_t g2 = tfbs_gather_top(tfbs_swar_codes(v[j].z, &d2));
+            const uint32_t g3 = tfbs_gather_top(tfbs_swar_codes(v[j].w, &d3));
+            // top bytes of g0..g3 -> bytes 0..3 of the packed word
+            word[j] = __byte_perm(__byte_perm(g0, g1, 0x0073), __byte_perm(g2, g3, 0x0073), 0x5410);
+            bad |= d0 | d1 | d2 | d3;
+        }
+        if (!__any_sync(0xFFFFFFFFu, bad != 0u)) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t idx = base + j * 512;
+                packed[idx >> 4] = word[j];
+                if ((lane & 1) == 0) mask[idx >> 5] = 0u;
+            }
+        } else {
+            // some byte of this 2048-base chunk is not ACGT (N-run, IUPAC code, separator, padding)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t idx = base + j * 512;
+                uint32_t v0, v1, v2, v3;
+                uint32_t wd = tfbs_swar4(v[j].x, &v0);
+                wd |= tfbs_swar4(v[j].y, &v1) << 8;
+                wd |= tfbs_swar4(v[j].z, &v2) << 16;
+                wd |= tfbs_swar4(v[j].w, &v3) << 24;
+                const uint32_t valid16 = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+                const uint32_t inv16 = ~valid16 & 0xFFFFu;
+                packed[idx >> 4] = wd;
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, inv16, 1);
+                if ((lane & 1) == 0) mask[idx >> 5] = inv16 | (other << 16);
+            }
         }
     }
 }
