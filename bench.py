@@ -67,7 +67,7 @@ def config_dict(args, n_gpus, per_gpu):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -363,7 +363,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "kernel": "scan_hits_kernel", "bound": "hbm", "achieved": algo_bytes / k_ms / 1e6, "peak": peak,
-                "unit": "GB/s", "frac": algo_bytes / k_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": algo_bytes / k_ms / 1e6 / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, from the
+                # committed ncu --set full capture profiles/r01/ncu_full_hits_v2_100Mb_raw.csv
+                "traffic": 120.47e6 + 294.45e6 if (args.motifs == 800 and per_gpu == 100_000_000) else None,
+                "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
                 "note": "hits mode at 800 motifs is bounded by shared-memory LUT bandwidth, not HBM "
                         "(SURVEY.md §7/§8d): the HBM fraction on the algorithmic bytes is reported as is",

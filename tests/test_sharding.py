@@ -1,0 +1,108 @@
+"""Multi-GPU sharding logic: CPU tests (incl. a world_size-2 gloo run) with the oracle standing in
+for the per-rank scan, and a GPU test that runs the shards one after another on one device."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from discover_tfbs_b200 import _lib, sharding, synth
+from oracle import pssm_oracle as po
+
+
+def _oracle_hits(seq, logodds, lens, thr):
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+    h = np.zeros(cnt, dtype=_lib.HIT_DTYPE)
+    h["pos"] = np.where(strand == 1, ~pos, pos)
+    h["motif"] = mot
+    h["score"] = score
+    return h
+
+
+def _workload(n=60_000, M=9):
+    logodds, lens = synth.pwm_library(3, M, lmin=6, lmax=30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-3, sample=20_000)
+    genome = synth.genome(3, 0, n)
+    return genome, logodds, lens, thr
+
+
+@pytest.mark.parametrize("total,n,halo", [(1000, 1, 29), (1000, 3, 29), (100_000_000, 8, 29), (130, 4, 5), (5, 8, 2)])
+def test_plan_shards_partition(total, n, halo):
+    shards = sharding.plan_shards(total, n, halo)
+    assert len(shards) == n
+    assert shards[0].start == 0 and shards[-1].owned_end == total
+    for a, b in zip(shards, shards[1:]):
+        assert a.owned_end == b.start
+    for s in shards:
+        assert s.start % 128 == 0 or s.start == total
+        assert s.scan_end == min(s.owned_end + halo, total)
+    lens = [6, 12, 30]
+    assert sum(sharding.units_of_shard(s, lens, total) for s in shards) == sum(max(total - L + 1, 0) for L in lens)
+
+
+@pytest.mark.parametrize("n_shards", [1, 2, 3, 8])
+def test_sharded_oracle_equals_unsharded(n_shards):
+    genome, logodds, lens, thr = _workload()
+    want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
+    parts = []
+    for sh in sharding.plan_shards(genome.size, n_shards, int(lens.max()) - 1):
+        local = _oracle_hits(genome[sh.start: sh.scan_end], logodds, lens, thr)
+        parts.append(sharding.filter_owned(local, sh))
+    got = sharding.merge_shard_hits(parts)
+    assert got.size == want.size and np.array_equal(got, want)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_rank(rank, world, port, out_path):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    genome, logodds, lens, thr = _workload()
+    # every rank regenerates its own chunk from the position-addressable generator
+    sh = sharding.plan_shards(genome.size, world, int(lens.max()) - 1)[rank]
+    chunk = synth.genome(3, sh.start, sh.scanned)
+    assert np.array_equal(chunk, genome[sh.start: sh.scan_end])
+    mine = sharding.filter_owned(_oracle_hits(chunk, logodds, lens, thr), sh)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)  # host-side gather only; no data-path collective
+    if rank == 0:
+        np.save(out_path, sharding.merge_shard_hits(gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "hits.npy")
+    mp.spawn(_gloo_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+    genome, logodds, lens, thr = _workload()
+    want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
+    got = np.load(out)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_shards_run_sequentially_on_one_gpu_match_single_scan(ctx):
+    genome, logodds, lens, thr = _workload(n=300_000, M=40)
+    lib = ctx.upload_pwms(logodds, lens)
+    enc = ctx.encode(genome)
+    want = sharding.merge_shard_hits([ctx.scan_hits(enc, lib, thr, sort=False)])
+    enc.close()
+    parts = []
+    for sh in sharding.plan_shards(genome.size, 4, int(lens.max()) - 1):
+        e = ctx.encode(genome[sh.start: sh.scan_end])
+        parts.append(sharding.filter_owned(ctx.scan_hits(e, lib, thr, sort=False), sh))
+        e.close()
+    got = sharding.merge_shard_hits(parts)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)]))
+    lib.close()
+    multi = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=[0])
+    assert np.array_equal(multi, want)
