@@ -36,18 +36,96 @@ struct ScanParams {
 };
 
 // Dense mode.  Persistent CTAs; for each motif the 3-mer table is expanded into shared memory as
-// T[g][x][lane] (float2 = fwd, rev) — one private copy per lane, so the 32 data-dependent
-// LDS.64 of a warp hit 32 different bank pairs: no bank conflicts (the v1 layout T[g][x] lost
-// 60 % of its shared-memory wavefronts to conflicts, profiles/r01/ncu_full_v1_raw.csv).  The CTA
-// then streams over its sub-tiles of 8192 window starts: every thread scores 8 consecutive starts
-// from a 48-base register window and writes 32 B per strand with streaming stores.
+// T[g][x][lane] (8 B = fwd, rev) — one private copy per lane, so the 32 data-dependent LDS.64 of a
+// warp hit 32 different bank pairs: no bank conflicts (the v1 layout T[g][x] lost 60 % of its
+// shared-memory wavefronts to conflicts, profiles/r01/ncu_full_v1_raw.csv).  The table is 16 KB
+// aligned so a lookup address is  base | (x << 8)  (one funnel shift + one LOP3), the group offset
+// is an immediate (G is a template parameter) and both strands are accumulated with one packed
+// add.rn.f32x2.  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 8
+// consecutive starts from a 48-base register window and writes 32 B per strand (streaming stores).
+__device__ __forceinline__ uint64_t lds64(uint32_t addr)
+{
+    uint64_t v;
+    asm("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+template <int G>
+__device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, uint32_t lut_lane_addr)
+{
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = P.pitch / kTile;
+    const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    float *row_f = P.out_fwd + (size_t)m * P.pitch;
+    float *row_r = P.out_rev + (size_t)m * P.pitch;
+    const uint64_t qnan2 = 0x7FC000007FC00000ull;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
+        // 48-base register window starting at p0 (p0 is a multiple of 8)
+        uint32_t w0, w1, w2, inv_lo, inv_hi;
+        {
+            const uint32_t *wp = P.packed + (p0 >> 4);
+            const int sh = (int)(p0 & 15) * 2;
+            const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
+            w0 = __funnelshift_r(a0, a1, sh);
+            w1 = __funnelshift_r(a1, a2, sh);
+            w2 = __funnelshift_r(a2, a3, sh);
+            const uint32_t *mp = P.mask + (p0 >> 5);
+            const int msh = (int)(p0 & 31);
+            const uint32_t m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
+            inv_lo = __funnelshift_r(m0, m1, msh);
+            inv_hi = __funnelshift_r(m1, m2, msh);
+        }
+        uint64_t acc[kPosPerThread];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+            for (int p = 0; p < kPosPerThread; p++) {
+                // bits [8,14) of t = 3-mer code at base p0 + p + 3g
+                const uint32_t t = (2 * p >= 8) ? (w0 >> (2 * p - 8)) : (w0 << (8 - 2 * p));
+                const uint64_t v = lds64(((t & 0x3F00u) | lut_lane_addr) + g * 16384);
+                acc[p] = g == 0 ? v : add_f32x2(acc[p], v);
+            }
+            if (g + 1 < G) {
+                w0 = __funnelshift_r(w0, w1, 6);
+                w1 = __funnelshift_r(w1, w2, 6);
+                w2 >>= 6;
+            }
+        }
+        float af[kPosPerThread], ar[kPosPerThread];
+#pragma unroll
+        for (int p = 0; p < kPosPerThread; p++) {
+            const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
+            const uint64_t a = bad ? qnan2 : acc[p];
+            af[p] = __uint_as_float((uint32_t)a);
+            ar[p] = __uint_as_float((uint32_t)(a >> 32));
+        }
+        float4 *of = reinterpret_cast<float4 *>(row_f + p0);
+        float4 *orv = reinterpret_cast<float4 *>(row_r + p0);
+        __stcs(of, make_float4(af[0], af[1], af[2], af[3]));
+        __stcs(of + 1, make_float4(af[4], af[5], af[6], af[7]));
+        __stcs(orv, make_float4(ar[0], ar[1], ar[2], ar[3]));
+        __stcs(orv + 1, make_float4(ar[4], ar[5], ar[6], ar[7]));
+    }
+}
+
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_dense_kernel(const ScanParams P)
 {
-    extern __shared__ __align__(16) float2 s_lut[];  // [G][64][32]
+    extern __shared__ uint8_t dense_smem_raw[];
+    // 16 KB-align the table inside the dynamic shared window
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(dense_smem_raw);
+    const uint32_t pad = ((raw + 16383u) & ~16383u) - raw;
+    float2 *s_lut = reinterpret_cast<float2 *>(dense_smem_raw + pad);  // [G][64][32]
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t n_tiles = P.pitch / kTile;
-    const float qnan = __int_as_float(0x7FC00000);
+    const uint32_t lut_lane_addr = raw + pad + (uint32_t)lane * 8u;
 
     for (int m = 0; m < P.M; m++) {
         const int32_t gl = __ldg(P.glen + m);
@@ -58,56 +136,13 @@ scan_dense_kernel(const ScanParams P)
             for (int i = tid; i < G * 64 * 32; i += kScanThreads) s_lut[i] = __ldg(src + (i >> 5));
         }
         __syncthreads();
-        const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-        float *row_f = P.out_fwd + (size_t)m * P.pitch;
-        float *row_r = P.out_rev + (size_t)m * P.pitch;
-        const float2 *lut_lane = s_lut + lane;
-
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
-            // 48-base register window starting at p0 (p0 is a multiple of 8)
-            uint32_t w0, w1, w2, inv_lo, inv_hi;
-            {
-                const uint32_t *wp = P.packed + (p0 >> 4);
-                const int sh = (int)(p0 & 15) * 2;
-                const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
-                w0 = __funnelshift_r(a0, a1, sh);
-                w1 = __funnelshift_r(a1, a2, sh);
-                w2 = __funnelshift_r(a2, a3, sh);
-                const uint32_t *mp = P.mask + (p0 >> 5);
-                const int msh = (int)(p0 & 31);
-                const uint32_t m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
-                inv_lo = __funnelshift_r(m0, m1, msh);
-                inv_hi = __funnelshift_r(m1, m2, msh);
-            }
-            float accf[kPosPerThread], accr[kPosPerThread];
-#pragma unroll
-            for (int p = 0; p < kPosPerThread; p++) accf[p] = accr[p] = 0.f;
-            const float2 *lg = lut_lane;
-            for (int g = 0; g < G; g++) {
-#pragma unroll
-                for (int p = 0; p < kPosPerThread; p++) {
-                    const uint32_t x = (w0 >> (2 * p)) & 63u;
-                    const float2 v = lg[x * 32];
-                    accf[p] += v.x;
-                    accr[p] += v.y;
-                }
-                lg += 64 * 32;
-                w0 = __funnelshift_r(w0, w1, 6);
-                w1 = __funnelshift_r(w1, w2, 6);
-                w2 >>= 6;
-            }
-#pragma unroll
-            for (int p = 0; p < kPosPerThread; p++) {
-                const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
-                if (bad) accf[p] = accr[p] = qnan;
-            }
-            float4 *of = reinterpret_cast<float4 *>(row_f + p0);
-            float4 *orv = reinterpret_cast<float4 *>(row_r + p0);
-            __stcs(of, make_float4(accf[0], accf[1], accf[2], accf[3]));
-            __stcs(of + 1, make_float4(accf[4], accf[5], accf[6], accf[7]));
-            __stcs(orv, make_float4(accr[0], accr[1], accr[2], accr[3]));
-            __stcs(orv + 1, make_float4(accr[4], accr[5], accr[6], accr[7]));
+        switch (G) {
+#define TFBS_DCASE(g) \
+    case g: dense_tiles<g>(P, m, L, lut_lane_addr); break;
+            TFBS_DCASE(1) TFBS_DCASE(2) TFBS_DCASE(3) TFBS_DCASE(4) TFBS_DCASE(5) TFBS_DCASE(6)
+            TFBS_DCASE(7) TFBS_DCASE(8) TFBS_DCASE(9) TFBS_DCASE(10) TFBS_DCASE(11)
+#undef TFBS_DCASE
+            default: break;
         }
     }
 }
@@ -279,7 +314,7 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
     fill_params(P, seq, pwms, pitch);
     P.out_fwd = (float *)ctx->dense_fwd.ptr;
     P.out_rev = (float *)ctx->dense_rev.ptr;
-    const size_t smem = (size_t)pwms->Gmax * 64 * 32 * sizeof(float2);
+    const size_t smem = (size_t)pwms->Gmax * 64 * 32 * sizeof(float2) + 16384;  // + alignment slack
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = std::min<int64_t>(ctx->sm_count, pitch / kTile);
     tfbs_begin(ctx);

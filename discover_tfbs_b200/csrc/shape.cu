@@ -15,8 +15,8 @@
 namespace {
 
 constexpr int kShapeThreads = 256;
-constexpr int kShapePosPerThread = 8;
-constexpr int kShapeTile = kShapeThreads * kShapePosPerThread;  // 2048 positions per CTA
+constexpr int kShapePosPerThread = 4;
+constexpr int kShapeTile = 8192;  // positions per CTA iteration (8 sub-tiles of 1024)
 constexpr int kMaxTracks = 8;
 
 struct TrackParams {
@@ -31,68 +31,71 @@ struct TrackParams {
     float *out;  // [T][pitch]
 };
 
-// One thread produces 8 consecutive positions of every track.  It needs bases p0-2 .. p0+10; a
-// 64-bit register window holds bases p0-8 .. p0+23.
+// Streaming kernel.  Persistent CTAs keep the tables in shared memory; a lane produces 4
+// consecutive positions of every track, so each track costs one fully contiguous STG.128 per warp
+// (a stride-32 B pattern doubled the store wavefronts in the l1tex data pipe, which is the unit
+// this kernel saturates: profiles/r01/ncu_full_dense_shape_encode_v2_100Mb_raw.csv).  The
+// pentamer just past a lane's 4 positions (needed by the last step value) comes from the next
+// lane by shuffle; only lane 31 looks it up itself.
 __global__ void __launch_bounds__(kShapeThreads)
 shape_tracks_kernel(const TrackParams P)
 {
     extern __shared__ float s_tab[];  // [T][2][1024]
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.tables);
         float4 *dst = reinterpret_cast<float4 *>(s_tab);
         for (int i = tid; i < P.T * 512; i += kShapeThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-
-    const int64_t n_tiles = P.pitch / kShapeTile;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t p0 = tile * kShapeTile + tid * kShapePosPerThread;
-    const int64_t b0 = p0 - 8;  // first base of the window (multiple of 8, may be -8)
-    uint32_t wlo, whi, inv;
-    {
-        const int64_t wi = b0 >> 4;  // floor division: b0 = -8 -> -1
-        const int sh = (int)(b0 & 15) * 2;
-        const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
-        const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
-        const uint32_t a2 = ld_words_guard(P.packed, wi + 2, P.n_words, 0u);
-        wlo = __funnelshift_r(a0, a1, sh);
-        whi = __funnelshift_r(a1, a2, sh);
-        const int64_t mi = b0 >> 5;
-        const int msh = (int)(b0 & 31);
-        const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
-        const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
-        inv = __funnelshift_r(m0, m1, msh);  // invalid bits of bases b0 .. b0+31
-    }
-    // pentamer centred at p0+d (d = 0..8; d = 8 is needed by the last step value) starts at
-    // window base d+6: index bits [2(d+6), 2(d+6)+10), validity bits [d+6, d+11)
-    uint32_t pent[9];
-    bool ok[9];
-#pragma unroll
-    for (int d = 0; d < 9; d++) {
-        const int s = 2 * (d + 6);
-        pent[d] = (s < 32 ? __funnelshift_r(wlo, whi, s) : (whi >> (s - 32))) & 1023u;
-        ok[d] = ((inv >> (d + 6)) & 31u) == 0u;
-    }
     const float qnan = __int_as_float(0x7FC00000);
-    for (int t = 0; t < P.T; t++) {
-        const float *y1 = s_tab + t * 2048;
-        const float *y2 = y1 + 1024;
-        float v[kShapePosPerThread];
-        if (((P.step_mask >> t) & 1u) == 0u) {
-#pragma unroll
-            for (int d = 0; d < 8; d++) v[d] = ok[d] ? y1[pent[d]] : qnan;
-        } else {
-            // step k between bases k and k+1: mean of Y2(pentamer@k) and Y1(pentamer@k+1).
-            // (a + b) * 0.5f in fp32 equals the oracle's (float)(((double)a + (double)b) / 2).
-#pragma unroll
-            for (int d = 0; d < 8; d++)
-                v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2[pent[d]], y1[pent[d + 1]]), 0.5f) : qnan;
+    const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
+    for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
+        const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
+        // 32-base register window starting at base b0 = p0 - 4 (a multiple of 4, may be -4):
+        // pentamer centred at p0 + d starts at window base d + 2
+        const int64_t b0 = p0 - 4;
+        uint32_t wlo, whi, inv;
+        {
+            const int64_t wi = b0 >> 4;
+            const int sh = (int)(b0 & 15) * 2;
+            const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
+            const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
+            wlo = __funnelshift_r(a0, a1, sh);
+            whi = a1 >> sh;  // only bits below 2*12 + 10 of the window are used (sh <= 24)
+            const int64_t mi = b0 >> 5;
+            const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
+            const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
+            inv = __funnelshift_r(m0, m1, (int)(b0 & 31));
         }
-        float4 *o = reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0);
-        __stcs(o, make_float4(v[0], v[1], v[2], v[3]));
-        __stcs(o + 1, make_float4(v[4], v[5], v[6], v[7]));
-    }
+        uint32_t pent[kShapePosPerThread + 1];
+        bool ok[kShapePosPerThread + 1];
+#pragma unroll
+        for (int d = 0; d <= kShapePosPerThread; d++) {
+            pent[d] = __funnelshift_r(wlo, whi, 2 * (d + 2)) & 1023u;
+            ok[d] = ((inv >> (d + 2)) & 31u) == 0u;
+        }
+        for (int t = 0; t < P.T; t++) {
+            const float *y1 = s_tab + t * 2048;
+            const float *y2 = y1 + 1024;
+            float v[kShapePosPerThread];
+            if (((P.step_mask >> t) & 1u) == 0u) {
+#pragma unroll
+                for (int d = 0; d < kShapePosPerThread; d++) v[d] = ok[d] ? y1[pent[d]] : qnan;
+            } else {
+                // step k between bases k and k+1: mean of Y2(pentamer@k) and Y1(pentamer@k+1).
+                // (a + b) * 0.5f in fp32 equals the oracle's (float)(((double)a + (double)b) / 2).
+                float a1[kShapePosPerThread + 1];
+#pragma unroll
+                for (int d = 0; d < kShapePosPerThread; d++) a1[d] = y1[pent[d]];
+                a1[kShapePosPerThread] = __shfl_down_sync(0xFFFFFFFFu, a1[0], 1);
+                if (lane == 31) a1[kShapePosPerThread] = y1[pent[kShapePosPerThread]];
+#pragma unroll
+                for (int d = 0; d < kShapePosPerThread; d++)
+                    v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2[pent[d]], a1[d + 1]), 0.5f) : qnan;
+            }
+            __stcs(reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
+        }
     }
 }
 
@@ -334,12 +337,13 @@ int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *sha
     for (int t = 0; t < T; t++)
         if (shapes->kinds[t] == TFBS_SHAPE_PER_STEP) P.step_mask |= 1u << t;
     P.out = (float *)ctx->tracks.ptr;
-    const size_t smem = (size_t)T * 2048 * sizeof(float);
-    TFBS_CHECK_CUDA(cudaFuncSetAttribute(shape_tracks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = std::min<int64_t>(pitch / (kShapeThreads * kShapePosPerThread), (int64_t)ctx->sm_count * 8);
     tfbs_begin(ctx);
-    // persistent CTAs: the tables are staged into shared memory once per CTA, not once per tile
-    const int64_t grid = std::min<int64_t>(pitch / kShapeTile, (int64_t)ctx->sm_count * 6);
-    shape_tracks_kernel<<<(unsigned)grid, kShapeThreads, smem, ctx->stream>>>(P);
+    {
+        const size_t smem = (size_t)T * 2048 * sizeof(float);
+        TFBS_CHECK_CUDA(cudaFuncSetAttribute(shape_tracks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shape_tracks_kernel<<<(unsigned)grid, kShapeThreads, smem, ctx->stream>>>(P);
+    }
     tfbs_launched(ctx);
     {
         const int64_t total = S * 2 * T;

@@ -292,6 +292,23 @@ def test_shape_tracks_bit_exact_single_record(ctx, n):
     tab.close()
 
 
+@pytest.mark.parametrize("shapes", [("MGW",), ("Roll",), ("MGW", "ProT", "Roll", "HelT"), ("Roll", "MGW", "HelT"),
+                                    ("HelT", "EP", "Roll", "MGW", "ProT"),
+                                    ("MGW", "ProT", "EP", "MGW", "Roll", "HelT", "Roll")])
+def test_shape_tracks_every_track_mix(ctx, shapes):
+    """Packed-table kernel specialisations and the generic fall-through (7 tracks, 10 planes)."""
+    rng = np.random.default_rng(len(shapes))
+    seq = _noisy_seq(rng, 70_001)
+    tables, kinds = dnashape.synthetic_tables(shapes)
+    tab = ctx.upload_shapes(tables, kinds)
+    enc = ctx.encode(seq)
+    got = ctx.shape_tracks(enc, tab)
+    ref = so.tracks(seq, tables, kinds)
+    assert np.array_equal(got, ref, equal_nan=True)
+    enc.close()
+    tab.close()
+
+
 def test_shape_tracks_record_set(ctx):
     rng = np.random.default_rng(2)
     recs = ["".join(rng.choice(list("ACGTN"), p=[.24, .24, .24, .24, .04], size=k))
