@@ -31,6 +31,7 @@ _PROTOTYPES = {
     "tfbs_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_last_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_total_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "tfbs_last_scan_candidates": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_timer_start": (C.c_int, [_vp]),
     "tfbs_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_host_alloc": (C.c_int, [_pp, _i64]),
@@ -57,6 +58,7 @@ _PROTOTYPES = {
     "tfbs_shape_tracks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "tfbs_shape_sites": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "tfbs_track_sites": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "tfbs_similarity_sums": (C.c_int, [_vp] + [_vp] * 6 + [_i64] + [_vp] * 6 + [_i64, _vp]),
     "tfbs_debug_swar4": (C.c_int, [_u32, C.POINTER(_u32), C.POINTER(_u32)]),
 }
 
@@ -181,6 +183,11 @@ class Context:
     def total_kernel_launches(self) -> int:
         n = _i64(0)
         _check(self._lib.tfbs_total_kernel_launches(self._h, C.byref(n)))
+        return int(n.value)
+
+    def last_scan_candidates(self) -> int:
+        n = _i64(0)
+        _check(self._lib.tfbs_last_scan_candidates(self._h, C.byref(n)))
         return int(n.value)
 
     def timer_start(self):
@@ -310,6 +317,20 @@ class Context:
         out = np.empty((ro.size, int(width)), dtype=np.float32)
         _check(self._lib.tfbs_track_sites(self._h, _ptr(val), val.size, _ptr(ro), _ptr(rn), _ptr(st),
                                           _ptr(en), _ptr(sd), ro.size, int(width), _ptr(out)))
+        return out
+
+    def similarity_sums(self, cand: dict, true: dict) -> np.ndarray:
+        """cand / true: dicts with words(u4) counts(u2) woff(i4) nk(i4) hash(u4) hoff(i4).
+        -> float64[S][3] sums of (Jaccard, PAS, PPS) over the true set."""
+        def arr(d, k, dt):
+            return np.ascontiguousarray(d[k], dtype=dt)
+        c = [arr(cand, "words", np.uint32), arr(cand, "counts", np.uint16), arr(cand, "woff", np.int32),
+             arr(cand, "nk", np.int32), arr(cand, "hash", np.uint32), arr(cand, "hoff", np.int32)]
+        t = [arr(true, "words", np.uint32), arr(true, "counts", np.uint16), arr(true, "woff", np.int32),
+             arr(true, "nk", np.int32), arr(true, "hash", np.uint32), arr(true, "hoff", np.int32)]
+        S, U = c[3].size, t[3].size
+        out = np.zeros((S, 3), dtype=np.float64)
+        _check(self._lib.tfbs_similarity_sums(self._h, *[_ptr(a) for a in c], S, *[_ptr(a) for a in t], U, _ptr(out)))
         return out
 
 

@@ -153,6 +153,13 @@ int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n)
     return TFBS_OK;
 }
 
+int tfbs_last_scan_candidates(tfbs_ctx *ctx, int64_t *n)
+{
+    TFBS_REQUIRE(ctx && n, "tfbs_last_scan_candidates: null argument");
+    *n = ctx->last_candidates;
+    return TFBS_OK;
+}
+
 int tfbs_timer_start(tfbs_ctx *ctx)
 {
     TFBS_REQUIRE(ctx, "tfbs_timer_start: null argument");

@@ -46,6 +46,7 @@ struct tfbs_ctx {
     float last_ms = 0.f;
     int64_t last_launches = 0;
     int64_t total_launches = 0;
+    int64_t last_candidates = 0;  // candidates the last hits scan verified exactly
     tfbs_scratch dense_fwd, dense_rev;  // dense scan outputs [M][pitch]
     tfbs_scratch hits;                  // tfbs_hit[cap]
     tfbs_scratch hit_count;             // unsigned long long + work counters
@@ -89,6 +90,7 @@ struct tfbs_pwms {
     std::vector<double> kmer_f64;    // [M][2][11][64] double 3-mer partial sums (fwd, revcomp)
     int64_t hq_lut_words = 0;        // total uint32 entries of the packed deficit tables
     uint32_t *hq_lut_dev = nullptr, *hq_kinit_dev = nullptr;
+    int32_t *hq_G_dev = nullptr;     // [n_blocks] groups the filter evaluates for the cached thresholds
     int32_t *blk_G_dev = nullptr, *blk_lut_off_dev = nullptr, *blk_motif_dev = nullptr, *lens_dev = nullptr;
     std::vector<float> hq_thr;       // thresholds the cached tables were built for
     bool hq_valid = false;

@@ -257,6 +257,7 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_lut_dev, (size_t)p->hq_lut_words * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_kinit_dev, (size_t)p->n_blocks * 32 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->hq_G_dev, (size_t)p->n_blocks * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->blk_G_dev, (size_t)p->n_blocks * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->blk_lut_off_dev, (size_t)p->n_blocks * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->blk_motif_dev, (size_t)p->n_blocks * 32 * 4);
@@ -288,6 +289,7 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (p->glen) cudaFree(p->glen);
     if (p->hq_lut_dev) cudaFree(p->hq_lut_dev);
     if (p->hq_kinit_dev) cudaFree(p->hq_kinit_dev);
+    if (p->hq_G_dev) cudaFree(p->hq_G_dev);
     if (p->blk_G_dev) cudaFree(p->blk_G_dev);
     if (p->blk_lut_off_dev) cudaFree(p->blk_lut_off_dev);
     if (p->blk_motif_dev) cudaFree(p->blk_motif_dev);

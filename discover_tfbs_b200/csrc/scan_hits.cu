@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -53,7 +54,7 @@ struct HitsParams {
     int32_t n_blocks;
     const uint32_t *qlut;        // per block [G_b][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
-    const int32_t *blk_G;        // [n_blocks]
+    const int32_t *blk_G;        // [n_blocks] column groups the filter evaluates (<= groups of the block)
     const uint32_t *kinit;       // [n_blocks][32] initial field values (0x7FFF - Dq per strand)
     const int32_t *blk_motif;    // [n_blocks][32] original motif index or -1
     const int32_t *lens;         // [M]
@@ -141,11 +142,20 @@ __device__ __forceinline__ bool verify(const VerifyCtx &V, int p, int ml, int st
     const uint32_t inv = __funnelshift_r(V.s_mask[p >> 5], V.s_mask[(p >> 5) + 1], p & 31) & lmask;
     if (inv) return false;  // window touches an invalid base: NaN in the oracle, never a hit
     const double *mat = V.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+    // left-to-right double sum (the oracle's order); the table loads of 8 columns are issued
+    // together so their L2 latency overlaps — the adds stay sequential
     double s = 0.0;
-    for (int j = 0; j < L; j++) {
-        const int i = p + j;
-        const uint32_t code = (V.s_words[i >> 4] >> (2 * (i & 15))) & 3u;
-        s += __ldg(mat + j * 4 + code);
+    for (int j0 = 0; j0 < L; j0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int j = j0 + k, i = p + j;
+            const uint32_t code = (V.s_words[i >> 4] >> (2 * (i & 15))) & 3u;
+            v[k] = j < L ? __ldg(mat + j * 4 + code) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (j0 + k < L) s += v[k];
     }
     const float f = (float)s;
     *motif_out = m;
@@ -228,7 +238,10 @@ __device__ __forceinline__ void drain_queue(const PushCtx &C)
         }
     }
     __syncwarp();
-    if (C.lane == 0) *C.qcount = 0;
+    if (C.lane == 0) {
+        if (cnt) atomicAdd(C.hit_count + 1, (unsigned long long)cnt);  // statistics: candidates verified
+        *C.qcount = 0;
+    }
     __syncwarp();
 }
 
@@ -404,10 +417,19 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     if (pw->hq_valid && pw->hq_thr.size() == (size_t)M && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * M) == 0)
         return TFBS_OK;
     const int nb = pw->n_blocks;
+    // The filter may ignore the last column group of a block: a partial deficit is a lower bound of
+    // the full one, so the candidate set stays a superset; every dropped group saves 1/G of the
+    // shared-memory traffic and multiplies the (rare) candidates.  TFBS_HITS_DROP_MIN_G = smallest
+    // block group count for which the last group is dropped (0 = never).
+    int drop_min_g = 0;  // measured on B200 (profiles/r01/drop_group_experiment.txt): never pays off
+    if (const char *e = getenv("TFBS_HITS_DROP_MIN_G")) drop_min_g = atoi(e);
+    std::vector<int32_t> filt_G(nb);
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)nb * 32, kPoison);
     for (int b = 0; b < nb; b++) {
-        const int G = pw->blk_G[b];
+        const int Gfull = pw->blk_G[b];
+        const int G = (drop_min_g > 0 && Gfull >= drop_min_g) ? Gfull - 1 : Gfull;
+        filt_G[b] = G;
         uint32_t *lut = qlut.data() + pw->blk_lut_off[b];
         const int dq_max = 0x7FFF / G - 3;
         const int capq = dq_max + 2;
@@ -447,7 +469,7 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
                     Dq = (int)std::min(dqv, (double)(dq_max + 1));
                 }
                 kfield[s] = (uint32_t)(0x7FFF - Dq);
-                for (int g = 0; g < Gm; g++)
+                for (int g = 0; g < std::min(Gm, G); g++)
                     for (int x = 0; x < 64; x++) {
                         const double d = gmax[g] - e[g * 64 + x];  // >= 0, +inf for -inf entries
                         int q;
@@ -465,6 +487,7 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     }
     cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), qlut.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), kinit.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_G_dev, filt_G.data(), filt_G.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;
@@ -503,7 +526,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
     P.blk_lut_off = pwms->blk_lut_off_dev;
-    P.blk_G = pwms->blk_G_dev;
+    P.blk_G = pwms->hq_G_dev;
     P.kinit = pwms->hq_kinit_dev;
     P.blk_motif = pwms->blk_motif_dev;
     P.lens = pwms->lens_dev;
@@ -526,10 +549,12 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     tfbs_launched(ctx);
     rc = tfbs_end(ctx);
     if (rc) return rc;
-    unsigned long long cnt = 0;
-    TFBS_CHECK_CUDA(cudaMemcpyAsync(&cnt, ctx->hit_count.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long cnt2[2] = {0, 0};
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(cnt2, ctx->hit_count.ptr, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream));
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long cnt = cnt2[0];
     *n_hits = (int64_t)cnt;
+    ctx->last_candidates = (int64_t)cnt2[1];
     const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
     if (out_host && take > 0) {
         TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),

@@ -221,13 +221,25 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
         tf_data["GC_content"] = np.zeros(0)
 
     if similarity_features:
-        if minhash:
-            print(strftime("%x %X | Calculating MinHash similarity score"))
-            tf_data["MinHash"] = [similarity.minhash_similarity(s, true_seqs) for s in seqs]
-        print(strftime("%x %X | Calculating Poisson similarity scores"))
-        pbs = [similarity.pac_similarity(s, true_seqs) for s in seqs]
-        tf_data["PAS"] = [p["PAS"] for p in pbs]
-        tf_data["PPS"] = [p["PPS"] for p in pbs]
+        if len(seqs) and similarity.acgt_only(seqs) and similarity.acgt_only(true_seqs):
+            # all-pairs kernel (tfbs_similarity_sums); k-mer / hash preparation is vectorised host code
+            if minhash:
+                print(strftime("%x %X | Calculating MinHash similarity score"))
+            print(strftime("%x %X | Calculating Poisson similarity scores"))
+            mh, pas, pps = similarity.similarity_columns_gpu(ctx, seqs, true_seqs)
+            if minhash:
+                tf_data["MinHash"] = mh
+            tf_data["PAS"] = pas
+            tf_data["PPS"] = pps
+        else:
+            # IUPAC / lower-case input: keep the reference's exact string semantics on the host
+            if minhash:
+                print(strftime("%x %X | Calculating MinHash similarity score"))
+                tf_data["MinHash"] = [similarity.minhash_similarity(s, true_seqs) for s in seqs]
+            print(strftime("%x %X | Calculating Poisson similarity scores"))
+            pbs = [similarity.pac_similarity(s, true_seqs) for s in seqs]
+            tf_data["PAS"] = [p["PAS"] for p in pbs]
+            tf_data["PPS"] = [p["PPS"] for p in pbs]
 
     if pwms is not None and enc is not None:
         print(strftime("%x %X | Scoring position weight matrices on both strands"))

@@ -73,6 +73,8 @@ int tfbs_last_kernel_ms(tfbs_ctx *ctx, float *ms);
 int tfbs_last_kernel_launches(tfbs_ctx *ctx, int64_t *n);
 /* Total kernels launched through this context since creation (bench.py's gpu_launches). */
 int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n);
+/* How many filter candidates the most recent tfbs_scan_hits verified exactly (>= hits). */
+int tfbs_last_scan_candidates(tfbs_ctx *ctx, int64_t *n);
 /* Region timer: CUDA events recorded on the context's stream; stop synchronises and returns the
  * elapsed device time of everything enqueued in between (kernels and async copies). */
 int tfbs_timer_start(tfbs_ctx *ctx);
@@ -176,6 +178,20 @@ int tfbs_shape_sites(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *shap
 int tfbs_track_sites(tfbs_ctx *ctx, const float *values_host, int64_t n_values,
                      const int64_t *rec_off, const int64_t *rec_ntok, const int64_t *start,
                      const int64_t *end, const int8_t *strand, int64_t S, int32_t W, float *out_host);
+
+/* ---- (4) similarity features ("next" row) ------------------------
+ * All-pairs sums over a true set of U sequences for S candidates, replacing the Python loops of
+ * utils.py:1043-1058 over jaccard_similarity (utils.py:1243-1255) and pac (utils.py:892-949):
+ * out[s] = { sum_u jaccard(true_u, cand_s), sum_u PAS(true_u, cand_s), sum_u PPS(true_u, cand_s) }
+ * (the caller divides by U for the reference's np.mean).  Per sequence the host passes the sorted
+ * unique k-mer codes (2 bits per base, first base most significant) with multiplicities, the
+ * total k-mer count, and the sorted unique MurmurHash3_x86_32(seed 39) values of the canonical
+ * k-mers (utils.py:1259-1269); *_woff / *_hoff are CSR offsets.  One k per call. */
+int tfbs_similarity_sums(tfbs_ctx *ctx, const uint32_t *c_words, const uint16_t *c_counts,
+                         const int32_t *c_woff, const int32_t *c_nk, const uint32_t *c_hash,
+                         const int32_t *c_hoff, int64_t S, const uint32_t *t_words,
+                         const uint16_t *t_counts, const int32_t *t_woff, const int32_t *t_nk,
+                         const uint32_t *t_hash, const int32_t *t_hoff, int64_t U, double *out_host);
 
 /* ---- test hooks (host-only, no device needed) -------------------------------------------
  * The encode kernel converts 4 ASCII bytes per 32-bit word with integer bit tricks; this runs

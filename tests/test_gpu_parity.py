@@ -409,3 +409,35 @@ def test_shape_sites_mode0_property_large(ctx):
             assert np.isnan(out[i, t, ref.size:]).all()
     enc.close()
     tab.close()
+
+
+# ---- (4) similarity features ("next" row f1) ------------------------------------------------------
+def test_similarity_pairs_vs_reference_golden(ctx, golden):
+    from discover_tfbs_b200 import similarity as sm
+
+    for a, b, want in golden["similarity"]["jaccard"]:
+        k = sm._kmer_len(len(a))
+        got = ctx.similarity_sums(sm.prepare([b], k), sm.prepare([a], k))
+        assert got[0, 0] == want, (a, b)
+    for a, b, (pas, pps) in golden["similarity"]["pac"]:
+        k = sm._kmer_len(len(a))
+        got = ctx.similarity_sums(sm.prepare([b], k), sm.prepare([a], k))
+        assert abs(got[0, 1] - pas) < 1e-12 and abs(got[0, 2] - pps) < 1e-12, (a, b)
+
+
+def test_similarity_all_pairs_vs_scalar_host(ctx):
+    """200-bp records (k = 8), low-complexity repeats (k-mer multiplicities > 1) and a mixed-length
+    true set (several k) against the scalar restatement of the reference's loops."""
+    from discover_tfbs_b200 import similarity as sm
+
+    rng = np.random.default_rng(12)
+    def rnd(n, alphabet="ACGT"):
+        return "".join(rng.choice(list(alphabet), size=n))
+    true = [rnd(200) for _ in range(6)] + [rnd(12) for _ in range(5)] + ["ACACACACACAC", "A" * 40 + rnd(20)]
+    cand = [rnd(200) for _ in range(5)] + [rnd(200, "AC") for _ in range(3)] + [true[0], "AC" * 100, rnd(60)]
+    mh, pas, pps = sm.similarity_columns_gpu(ctx, cand, set(true))
+    uniq = set(true)
+    for i, c in enumerate(cand):
+        assert abs(mh[i] - sm.minhash_similarity(c, uniq)) < 1e-12
+        ref = sm.pac_similarity(c, uniq)
+        assert abs(pas[i] - ref["PAS"]) < 1e-12 and abs(pps[i] - ref["PPS"]) < 1e-12, i
