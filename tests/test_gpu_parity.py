@@ -441,3 +441,40 @@ def test_similarity_all_pairs_vs_scalar_host(ctx):
         assert abs(mh[i] - sm.minhash_similarity(c, uniq)) < 1e-12
         ref = sm.pac_similarity(c, uniq)
         assert abs(pas[i] - ref["PAS"]) < 1e-12 and abs(pps[i] - ref["PPS"]) < 1e-12, i
+
+
+# ---- candidate emission ("next" row f2) ----------------------------------------------------------
+def test_exact_match_candidates_equal_string_search(ctx, tmp_path):
+    """Exact-match PWMs at threshold 0 == 100 %-identity full-length matches on both strands
+    (what utils.py:340-398 keeps from BLASTn), emitted as BED6 + `chrom:start-end(strand)` FASTA."""
+    import re
+
+    from discover_tfbs_b200 import candidates as cd
+
+    rng = np.random.default_rng(9)
+    genome = {"chrA": "".join(rng.choice(list("ACGT"), size=30_000)), "chrB": "".join(rng.choice(list("ACGTN"), size=9_000))}
+    motifs = ["ACGTAC", "TGCATN", "CAYRTG", genome["chrA"][100:112]]
+    comp = str.maketrans("ACGTN", "TGCAN")
+    iupac = {"N": "[ACGT]", "Y": "[CT]", "R": "[AG]"}
+    want = []
+    for ci, (chrom, seq) in enumerate(genome.items()):
+        for mi, m in enumerate(motifs):
+            pat = re.compile("(?=(" + "".join(iupac.get(ch, ch) for ch in m) + "))")
+            rc_seq = seq.translate(comp)[::-1]
+            for mt in pat.finditer(seq):
+                want.append((ci, mt.start(), 0, mi, seq[mt.start(): mt.start() + len(m)]))
+            for mt in pat.finditer(rc_seq):
+                s0 = len(seq) - mt.start() - len(m)
+                want.append((ci, s0, 1, mi, rc_seq[mt.start(): mt.start() + len(m)]))
+    want.sort(key=lambda t: (t[0], t[1], t[2], t[3]))
+    got = cd.scan_candidates(genome, [cd.exact_match_pwm(m) for m in motifs], 0.0, names=motifs, ctx=ctx)
+    key = sorted(((list(genome).index(c["chrom"]), c["start"], int(c["strand"] == "-"), c["motif"], c["sequence"]) for c in got))
+    assert key == want and len(want) > 20
+    assert all(c["score"] == 0.0 for c in got)
+    cd.write_bed6(got, tmp_path / "c.bed")
+    cd.write_fasta(got, tmp_path / "c.fasta")
+    recs = list(U.parse_fasta(str(tmp_path / "c.fasta")))
+    chrom, start, end, strand = U.parse_locations([h for h, _ in recs])
+    assert [(c, int(s), int(e)) for c, s, e in zip(chrom, start, end)] == [(c["chrom"], c["start"], c["end"]) for c in got]
+    first = open(tmp_path / "c.bed").readline().rstrip("\n").split("\t")
+    assert len(first) == 6 and first[5] in "+-"
