@@ -37,8 +37,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRing = 48;                 // ring accumulators (multiple of 16 and of 3)
-constexpr int kSeg = 2016;                // window starts per warp per tile (42 ring turns)
+constexpr int kRing = 32;                 // ring accumulators: >= 3*(G-1)+1 for G <= 11, multiple of 16
+constexpr int kSeg = 2016;                // window starts per warp per tile (63 ring turns of 32)
 constexpr int kTilePos = kWarps * kSeg;   // 16128 starts per tile (multiple of 128)
 constexpr int kTileBases = kTilePos + 128;
 constexpr int kTileWords = kTileBases / 16;  // 1016 words  = 4064 B (multiple of 16)
