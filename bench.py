@@ -12,8 +12,9 @@ position per strand).  One unit = one motif evaluated at one start position on b
 A step = encode (ASCII -> 2-bit + mask) + hits-mode scan of the chunk.
   value : inputs (ASCII bytes) already resident in HBM, hits left in HBM; CUDA events on the
           library's stream; L2 flushed (untimed) before every step.
-  e2e   : the same step through the public API with HOST buffers: pinned ASCII -> H2D -> encode ->
-          scan -> hits + count D2H into pinned memory, all inside the timed region.
+  e2e   : the same step through the public API with HOST buffers (tfbs_scan_hits_host): pinned
+          ASCII -> H2D -> encode -> scan -> hits + count D2H into pinned memory, chunk-pipelined on
+          three streams, all inside the timed region.
 """
 import argparse
 import json
@@ -285,8 +286,9 @@ def run_ours(args):
         return ctx.scan_hits(enc, lib, thr, cap=cap, to_host=False)
 
     def step_e2e():
-        enc.reencode(pinned_in.array)
-        return ctx.scan_hits(enc, lib, thr, cap=cap, sort=False, to_host=True, out=hits_out, grow=False)
+        # public end-to-end call: pinned host ASCII -> (H2D | encode + scan | hits D2H) pipelined
+        # over 8 chunks on three streams -> hits in pinned host memory
+        return ctx.scan_hits_host(pinned_in.array, enc, lib, thr, hits_out[:cap], chunks=8)
 
     # ---- resident (value) ------------------------------------------------------------------------
     for _ in range(args.warmup):

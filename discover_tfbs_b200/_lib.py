@@ -53,6 +53,7 @@ _PROTOTYPES = {
     "tfbs_pwms_destroy": (C.c_int, [_vp]),
     "tfbs_scan_dense": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "tfbs_scan_hits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(_i64)]),
+    "tfbs_scan_hits_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, C.POINTER(_i64)]),
     "tfbs_shapes_upload": (C.c_int, [_vp, _vp, _vp, _i32, _pp]),
     "tfbs_shapes_destroy": (C.c_int, [_vp]),
     "tfbs_shape_tracks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -273,6 +274,17 @@ class Context:
             _check(rc)
             break
         return buf[: n.value] if to_host else int(n.value)
+
+    def scan_hits_host(self, ascii_host: np.ndarray, seq: "EncodedSeq", pwms: "MotifLibrary", thresholds,
+                       out: np.ndarray, chunks: int = 8, sort: bool = False):
+        """Chunk-pipelined end-to-end scan of a host buffer (H2D, encode+scan, D2H overlap).
+        `out` is a preallocated HIT_DTYPE array (its size is the capacity); returns out[:n_hits]."""
+        thr = np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, dtype=np.float32), (pwms.M,)))
+        a = as_ascii(ascii_host)
+        n = _i64(0)
+        _check(self._lib.tfbs_scan_hits_host(self._h, _ptr(a), a.size, seq._h, pwms._h, _ptr(thr), _ptr(out),
+                                             out.size, int(chunks), int(sort), C.byref(n)))
+        return out[: n.value]
 
     # -- (3) shape -------------------------------------------------------------------------
     def upload_shapes(self, tables, kinds) -> "ShapeTables":

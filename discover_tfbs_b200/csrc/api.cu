@@ -92,6 +92,9 @@ int tfbs_ctx_create(int device, tfbs_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->pinned_counts, 4096, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_ctx_create: %s", cudaGetErrorString(e));
         delete c;
@@ -119,6 +122,10 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
+    for (cudaEvent_t ev : ctx->pipe_events) cudaEventDestroy(ev);
+    if (ctx->pinned_counts) cudaFreeHost(ctx->pinned_counts);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TFBS_OK;

@@ -43,6 +43,9 @@ struct tfbs_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // per-call kernel bracket
     cudaEvent_t evt0 = nullptr, evt1 = nullptr;  // user region timer
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;  // copy streams of the pipelined host path
+    std::vector<cudaEvent_t> pipe_events;
+    unsigned long long *pinned_counts = nullptr;  // pinned host scratch for per-chunk hit counts
     float last_ms = 0.f;
     int64_t last_launches = 0;
     int64_t total_launches = 0;
@@ -107,6 +110,8 @@ struct tfbs_shapes {
 };
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
+int tfbs_encode_range(tfbs_ctx *ctx, const void *ascii_dev, int64_t valid, tfbs_seq *s, int64_t base,
+                      int64_t cover, cudaStream_t stream);
 
 // RAII-free timing helpers: bracket the kernels of one API call.
 static inline void tfbs_begin(tfbs_ctx *ctx)

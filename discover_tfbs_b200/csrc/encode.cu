@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kEncodeThreads)
 encode_kernel(const uint8_t *__restrict__ ascii, int64_t n, int64_t n_pad,
               uint32_t *__restrict__ packed, uint32_t *__restrict__ mask)
 {
+    // `ascii`, `packed` and `mask` point at the first base of the range being encoded (a multiple
+    // of 2048 bases into the buffer); n = valid bytes of the range, n_pad = bases it must cover.
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (int64_t)blockIdx.x * (kEncodeThreads / 32) + (threadIdx.x >> 5);
     const int64_t warp_stride = (int64_t)gridDim.x * (kEncodeThreads / 32);
@@ -228,6 +230,24 @@ int alloc_seq(tfbs_ctx *ctx, int64_t n, tfbs_seq **out)
     *out = s;
     return TFBS_OK;
 }
+
+}  // namespace
+
+// Encode `valid` bytes at ascii_dev into bases [base, base + cover) of seq (base and cover are
+// multiples of 2048; bytes past `valid` are marked invalid).  Used by the chunk-pipelined host path.
+int tfbs_encode_range(tfbs_ctx *ctx, const void *ascii_dev, int64_t valid, tfbs_seq *s, int64_t base,
+                      int64_t cover, cudaStream_t stream)
+{
+    const int64_t chunks = cover / kBasesPerWarpIter;
+    const int64_t blocks = (chunks + (kEncodeThreads / 32) - 1) / (kEncodeThreads / 32);
+    if (blocks > 0)
+        encode_kernel<<<(unsigned)blocks, kEncodeThreads, 0, stream>>>((const uint8_t *)ascii_dev, valid, cover,
+                                                                      s->packed + (base >> 4), s->mask + (base >> 5));
+    tfbs_launched(ctx);
+    return TFBS_OK;
+}
+
+namespace {
 
 int launch_encode(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq *s)
 {

@@ -50,7 +50,8 @@ constexpr uint32_t kPoison = 0x80008000u;
 struct HitsParams {
     const uint32_t *packed;
     const uint32_t *mask;
-    int64_t n_tiles;
+    int64_t n_tiles;   // tiles scanned by this launch
+    int64_t tile0;     // first tile (chunk-pipelined launches scan a sub-range)
     int32_t n_blocks;
     const uint32_t *qlut;        // per block [G_b][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
@@ -330,7 +331,7 @@ scan_hits_kernel(const HitsParams P, const int lut_groups)
         const uint32_t item = *S.item;
         if (item >= total_items) break;
         const int b = (int)(item / (uint32_t)P.n_tiles);
-        const int64_t tile = (int64_t)(item % (uint32_t)P.n_tiles);
+        const int64_t tile = P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles);
         const int64_t tile_start = tile * kTilePos;
         const bool new_block = b != cur_block;
         if (new_block) G = __ldg(P.blk_G + b);
@@ -523,6 +524,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.packed = seq->packed;
     P.mask = seq->mask;
     P.n_tiles = (n + kTilePos - 1) / kTilePos;
+    P.tile0 = 0;
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
     P.blk_lut_off = pwms->blk_lut_off_dev;
@@ -564,6 +566,126 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     }
     if ((int64_t)cnt > cap) {
         tfbs_set_error("tfbs_scan_hits: %llu hits exceed capacity %lld", cnt, (long long)cap);
+        return TFBS_ERR_OVERFLOW;
+    }
+    return TFBS_OK;
+}
+
+
+// End-to-end entry point for a HOST-resident sequence: the buffer is cut into `chunks` ranges on
+// tile boundaries; H2D copies (stream_in), encode + scan (compute stream) and the D2H copies of
+// every chunk's hits (stream_out) overlap, so the PCIe time hides behind the scan.  Results are the
+// same as tfbs_encode + tfbs_scan_hits (hit order is unspecified unless `sorted`).
+extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                                   const tfbs_pwms *pwms_c, const float *thr, tfbs_hit *out_host, int64_t cap,
+                                   int32_t chunks, int32_t sorted, int64_t *n_hits)
+{
+    TFBS_REQUIRE(ctx && ascii_host && seq && pwms_c && thr && out_host && n_hits && cap >= 0 && n > 0,
+                 "tfbs_scan_hits_host: bad argument");
+    TFBS_REQUIRE(seq->ctx == ctx && pwms_c->ctx == ctx && seq->n == n, "tfbs_scan_hits_host: handle mismatch");
+    tfbs_pwms *pwms = const_cast<tfbs_pwms *>(pwms_c);
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    *n_hits = 0;
+    const int M = pwms->M;
+    int rc = tfbs_scratch_reserve(ctx->hits, (size_t)std::max<int64_t>(cap, 1) * sizeof(tfbs_hit));
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->hit_count, 64);
+    if (rc) return rc;
+    rc = tfbs_scratch_reserve(ctx->thr, (size_t)M * sizeof(float));
+    if (rc) return rc;
+    rc = tfbs_build_hits_tables(pwms, thr);
+    if (rc) return rc;
+    if (seq->staging_bytes < (size_t)n) {
+        if (seq->staging) cudaFree(seq->staging);
+        seq->staging = nullptr;
+        seq->staging_bytes = 0;
+        TFBS_CHECK_CUDA(cudaMalloc(&seq->staging, (size_t)n + 256));
+        seq->staging_bytes = (size_t)n;
+    }
+    const int64_t total_tiles = (n + kTilePos - 1) / kTilePos;
+    TFBS_REQUIRE((total_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits_host: sequence padding too small");
+    int64_t C = std::max<int64_t>(1, std::min<int64_t>(chunks, std::min<int64_t>(total_tiles, 64)));
+    const int64_t tiles_per = (total_tiles + C - 1) / C;
+    C = (total_tiles + tiles_per - 1) / tiles_per;
+    while ((int64_t)ctx->pipe_events.size() < 2 * C + 2) {
+        cudaEvent_t ev;
+        TFBS_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(ev);
+    }
+    cudaEvent_t ev_start = ctx->pipe_events[2 * C], ev_out = ctx->pipe_events[2 * C + 1];
+    const int64_t n_pad_total = seq->n_words * 16;
+
+    TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->thr.ptr, thr, (size_t)M * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TFBS_CHECK_CUDA(cudaMemsetAsync(ctx->hit_count.ptr, 0, 64, ctx->stream));
+    // copy streams start after everything already queued on the compute stream (and the timer)
+    TFBS_CHECK_CUDA(cudaEventRecord(ev_start, ctx->stream));
+    TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream_in, ev_start, 0));
+    TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream_out, ev_start, 0));
+
+    HitsParams P;
+    P.packed = seq->packed;
+    P.mask = seq->mask;
+    P.n_blocks = pwms->n_blocks;
+    P.qlut = pwms->hq_lut_dev;
+    P.blk_lut_off = pwms->blk_lut_off_dev;
+    P.blk_G = pwms->hq_G_dev;
+    P.kinit = pwms->hq_kinit_dev;
+    P.blk_motif = pwms->blk_motif_dev;
+    P.lens = pwms->lens_dev;
+    P.thr = (const float *)ctx->thr.ptr;
+    P.exact = pwms->exact;
+    P.hits = (tfbs_hit *)ctx->hits.ptr;
+    P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
+    P.cap = (unsigned long long)cap;
+    const int lut_groups = pwms->Gmax;
+    const size_t smem = hits_smem_bytes(lut_groups);
+    TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    tfbs_begin(ctx);
+    for (int64_t c = 0; c < C; c++) {
+        const int64_t t0 = c * tiles_per, t1 = std::min<int64_t>(total_tiles, t0 + tiles_per);
+        const int64_t b0 = t0 * kTilePos;
+        // bytes this chunk's scan can touch: its tiles + the 128-base halo (re-copied by the next chunk)
+        const int64_t b1 = std::min<int64_t>(n, t1 * kTilePos + 128);
+        const int64_t cover = (c == C - 1) ? (n_pad_total - b0) : (((t1 * kTilePos + 128 - b0) + 2047) / 2048 * 2048);
+        TFBS_CHECK_CUDA(cudaMemcpyAsync((char *)seq->staging + b0, ascii_host + b0, (size_t)(b1 - b0),
+                                        cudaMemcpyHostToDevice, ctx->stream_in));
+        TFBS_CHECK_CUDA(cudaEventRecord(ctx->pipe_events[2 * c], ctx->stream_in));
+        TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * c], 0));
+        tfbs_encode_range(ctx, (char *)seq->staging + b0, b1 - b0, seq, b0, cover, ctx->stream);
+        P.tile0 = t0;
+        P.n_tiles = t1 - t0;
+        P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 16);
+        TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 4, ctx->stream));
+        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * 2, P.n_tiles * P.n_blocks);
+        scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, lut_groups);
+        tfbs_launched(ctx);
+        TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned_counts + c, ctx->hit_count.ptr, sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        TFBS_CHECK_CUDA(cudaEventRecord(ctx->pipe_events[2 * c + 1], ctx->stream));
+    }
+    // drain: as soon as a chunk's scan is done its hits go home while the next chunk is scanned
+    unsigned long long done = 0;
+    for (int64_t c = 0; c < C; c++) {
+        TFBS_CHECK_CUDA(cudaEventSynchronize(ctx->pipe_events[2 * c + 1]));
+        const unsigned long long upto = std::min<unsigned long long>(ctx->pinned_counts[c], (unsigned long long)cap);
+        if (upto > done) {
+            TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host + done, (tfbs_hit *)ctx->hits.ptr + done,
+                                            (size_t)(upto - done) * sizeof(tfbs_hit), cudaMemcpyDeviceToHost,
+                                            ctx->stream_out));
+            done = upto;
+        }
+    }
+    TFBS_CHECK_CUDA(cudaEventRecord(ev_out, ctx->stream_out));
+    TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out, 0));  // a region timer on the compute stream sees the copies
+    rc = tfbs_end(ctx);
+    if (rc) return rc;
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream_out));
+    const unsigned long long cnt = ctx->pinned_counts[C - 1];
+    *n_hits = (int64_t)cnt;
+    if (sorted && done > 0) std::sort(out_host, out_host + done, HitLess());
+    if ((int64_t)cnt > cap) {
+        tfbs_set_error("tfbs_scan_hits_host: %llu hits exceed capacity %lld", cnt, (long long)cap);
         return TFBS_ERR_OVERFLOW;
     }
     return TFBS_OK;

@@ -139,6 +139,14 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
 int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const float *thr,
                    tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits);
 
+/* End-to-end form for a HOST-resident buffer (ideally pinned, tfbs_host_alloc): `seq` is a handle
+ * of length n (e.g. from a previous tfbs_encode) whose contents are overwritten.  The buffer is cut
+ * into `chunks` ranges; H2D copy, encode + scan and the D2H copy of each range's hits overlap on
+ * three streams.  Same results as tfbs_encode_into + tfbs_scan_hits. */
+int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                        const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
+                        int32_t chunks, int32_t sorted, int64_t *n_hits);
+
 /* ---- (3) DNA-shape pentamer lookup -----------------------------------------------------
  * Replaces DNAshapeR getShape()/getDNAShape() (get_DNA_shapes.R:23-25,
  * create_bkg_seqs.py:365-366) and the text parsing + window slicing the reference does on its

@@ -478,3 +478,28 @@ def test_exact_match_candidates_equal_string_search(ctx, tmp_path):
     assert [(c, int(s), int(e)) for c, s, e in zip(chrom, start, end)] == [(c["chrom"], c["start"], c["end"]) for c in got]
     first = open(tmp_path / "c.bed").readline().rstrip("\n").split("\t")
     assert len(first) == 6 and first[5] in "+-"
+
+
+@pytest.mark.parametrize("n,chunks", [(1000, 4), (16_128, 2), (50_001, 1), (50_001, 3), (200_000, 8), (200_000, 64)])
+def test_pipelined_host_scan_equals_plain_scan(ctx, n, chunks):
+    """tfbs_scan_hits_host (chunked H2D / encode+scan / D2H overlap) == encode + scan_hits."""
+    logodds, lens = synth.pwm_library(n, 40, lmin=6, lmax=30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-3, sample=20_000)
+    seq = synth.genome(n, 7_000_000, n)
+    lib = ctx.upload_pwms(logodds, lens)
+    enc = ctx.encode(seq)
+    want = ctx.scan_hits(enc, lib, thr, sort=True)
+    pin = _lib.PinnedBuffer(n)
+    pin.array[:] = seq
+    scratch = ctx.encode(np.full(n, ord("A"), np.uint8))  # handle whose contents get overwritten
+    out = np.empty(max(want.size, 1) + 16, dtype=_lib.HIT_DTYPE)
+    got = ctx.scan_hits_host(pin.array, scratch, lib, thr, out, chunks=chunks, sort=True)
+    assert got.size == want.size and np.array_equal(got, want)
+    # the handle now holds the same encoding as a plain encode
+    a, b = scratch.download(), enc.download()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(RuntimeError, match="exceed capacity"):
+        ctx.scan_hits_host(pin.array, scratch, lib, thr, out[: max(want.size // 2, 1)], chunks=chunks)
+    for h in (enc, scratch, lib):
+        h.close()
+    pin.close()
