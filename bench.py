@@ -178,7 +178,7 @@ def run_reference(args):
         "note": "reference CPU path = oracle C port (Biopython PSSM semantics); the reference repo has no "
                 "PWM scanner of its own and Biopython/DNAshapeR are absent from the image",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extras(ctx, args, peak):
@@ -388,15 +388,33 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_sample_rate(logodds, lens, thr, args.cpu_seconds)
         except Exception as exc:
             line["cpu_baseline"] = {"error": repr(exc)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL banners,
+    warnings) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level stdout of this process (and NCCL's) now lands on stderr
     if args.impl == "reference":
         run_reference(args)
     else:
