@@ -250,10 +250,15 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
             L = int(lib.lens[m])
             best_f = np.full(len(seqs), np.nan)
             best_r = np.full(len(seqs), np.nan)
-            for i, (s, ln) in enumerate(zip(starts, lens)):
-                if ln >= L:
-                    best_f[i] = np.nanmax(fwd[m, s: s + ln - L + 1]) if not np.isnan(fwd[m, s: s + ln - L + 1]).all() else np.nan
-                    best_r[i] = np.nanmax(rev[m, s: s + ln - L + 1]) if not np.isnan(rev[m, s: s + ln - L + 1]).all() else np.nan
+            with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+                __import__("warnings").simplefilter("ignore", RuntimeWarning)  # all-NaN rows stay NaN
+                for ln in np.unique(lens):
+                    if ln < L:
+                        continue
+                    rows = np.flatnonzero(lens == ln)
+                    idx = starts[rows][:, None] + np.arange(int(ln) - L + 1)[None, :]
+                    best_f[rows] = np.nanmax(fwd[m][idx], axis=1)
+                    best_r[rows] = np.nanmax(rev[m][idx], axis=1)
             tf_data[f"{name}_fwd_max"] = best_f
             tf_data[f"{name}_rev_max"] = best_r
         lib.close()
