@@ -107,6 +107,9 @@ struct tfbs_shapes {
     // float[T][2][1024] on device
     float *tables = nullptr;
     int32_t *kinds_dev = nullptr;
+    // packed int16 centi-unit planes (only when every table value is an exact 2-decimal number)
+    uint32_t *c16_words = nullptr;
+    std::vector<int32_t> c16_kind, c16_row_a, c16_row_b;
 };
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);

@@ -9,6 +9,7 @@
 // little-endian pentamer index that falls straight out of the 2-bit packed words
 // (x = sum code[c-2+k] << 2k); the host re-indexes the caller's big-endian tables once.
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -95,6 +96,114 @@ shape_tracks_kernel(const TrackParams P)
                     v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2[pent[d]], a1[d + 1]), 0.5f) : qnan;
             }
             __stcs(reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
+        }
+    }
+}
+
+// ---- packed centi-unit variant ---------------------------------------------------------------------
+// DNA-shape tables hold 2-decimal values (DNAshapeR prints %.2f).  When every entry v satisfies
+// v == (float)((double)c * 0.01) for an integer |c| < 32768 (checked at upload), two values share one
+// 32-bit word: (track A | track B) for per-nucleotide tracks, (Y1 | Y2) for a per-step track.  That
+// halves the data-dependent LDS.32 per position — the bank conflicts of those loads are what
+// saturates the l1tex data pipe in the fp32-table kernel (71 % of its shared-memory wavefronts,
+// profiles/r01/ncu_full_final_100Mb_raw.csv).  The reconstruction (centi_to_float) is verified
+// against every table entry at upload.
+struct Packed16Params {
+    const uint32_t *packed;
+    const uint32_t *mask;
+    int64_t n_words, n_mask, pitch;
+    const uint32_t *words;  // [NW][1024] little-endian pentamer index
+    int32_t NW;
+    int32_t kind[kMaxTracks];   // 0: two per-nucleotide tracks, 1: one per-step track (Y1 | Y2 << 16)
+    int32_t row_a[kMaxTracks];  // output row of the low half (or of the step track)
+    int32_t row_b[kMaxTracks];  // output row of the high half, -1 if none
+    float *out;
+};
+
+// c / 100 correctly rounded to float with full-rate fp32 ops only (int->float and float<->double
+// conversions run on the quarter-rate pipe): magic-number int->float, then a double-float product
+// with 0.01 = r_hi + r_lo.  The host runs the same sequence for every table entry at upload and
+// only enables this kernel if it reproduces the table bit for bit.
+__host__ __device__ __forceinline__ float centi_to_float(int c)
+{
+#ifdef __CUDA_ARCH__
+    const float cf = __int_as_float(0x4B400000 + c) - 12582912.0f;  // exact for |c| < 2^22
+    const float r_hi = 0.01f, r_lo = 2.2351741291171123e-10f;       // 0.01 - (double)0.01f
+    const float p_hi = __fmul_rn(cf, r_hi);
+    const float p_lo = __fmaf_rn(cf, r_hi, -p_hi);
+    return __fadd_rn(p_hi, __fmaf_rn(cf, r_lo, p_lo));
+#else
+    const float cf = (float)c;
+    const float r_hi = 0.01f, r_lo = 2.2351741291171123e-10f;
+    const float p_hi = cf * r_hi;
+    const float p_lo = fmaf(cf, r_hi, -p_hi);
+    return p_hi + fmaf(cf, r_lo, p_lo);
+#endif
+}
+
+__global__ void __launch_bounds__(kShapeThreads)
+shape_tracks_c16_kernel(const Packed16Params P)
+{
+    extern __shared__ uint32_t s_w[];  // [NW][1024]
+    const int tid = threadIdx.x, lane = tid & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.words);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_w);
+        for (int i = tid; i < P.NW * 256; i += kShapeThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const float qnan = __int_as_float(0x7FC00000);
+    const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
+    for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
+        const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
+        const int64_t b0 = p0 - 4;
+        uint32_t wlo, inv;
+        {
+            const int64_t wi = b0 >> 4;
+            const int sh = (int)(b0 & 15) * 2;
+            const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
+            const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
+            wlo = __funnelshift_r(a0, a1, sh);
+            const int64_t mi = b0 >> 5;
+            const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
+            const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
+            inv = __funnelshift_r(m0, m1, (int)(b0 & 31));
+        }
+        uint32_t pent[kShapePosPerThread + 1];
+        bool ok[kShapePosPerThread + 1];
+#pragma unroll
+        for (int d = 0; d <= kShapePosPerThread; d++) {
+            pent[d] = (wlo >> (2 * (d + 2))) & 1023u;
+            ok[d] = ((inv >> (d + 2)) & 31u) == 0u;
+        }
+        for (int w = 0; w < P.NW; w++) {
+            const uint32_t *tab = s_w + w * 1024;
+            uint32_t u[kShapePosPerThread + 1];
+#pragma unroll
+            for (int d = 0; d < kShapePosPerThread; d++) u[d] = tab[pent[d]];
+            if (P.kind[w] == 0) {
+                float va[kShapePosPerThread], vb[kShapePosPerThread];
+#pragma unroll
+                for (int d = 0; d < kShapePosPerThread; d++) {
+                    va[d] = ok[d] ? centi_to_float((int)(short)(u[d] & 0xFFFFu)) : qnan;
+                    vb[d] = ok[d] ? centi_to_float((int)(short)(u[d] >> 16)) : qnan;
+                }
+                __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(va[0], va[1], va[2], va[3]));
+                if (P.row_b[w] >= 0)
+                    __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_b[w] * P.pitch + p0), make_float4(vb[0], vb[1], vb[2], vb[3]));
+            } else {
+                // the pentamer just past this lane's 4 positions belongs to the next lane
+                u[kShapePosPerThread] = __shfl_down_sync(0xFFFFFFFFu, u[0], 1);
+                if (lane == 31) u[kShapePosPerThread] = tab[pent[kShapePosPerThread]];
+                float v[kShapePosPerThread];
+#pragma unroll
+                for (int d = 0; d < kShapePosPerThread; d++) {
+                    const float y2 = centi_to_float((int)(short)(u[d] >> 16));
+                    const float y1 = centi_to_float((int)(short)(u[d + 1] & 0xFFFFu));
+                    v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2, y1), 0.5f) : qnan;
+                }
+                __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
+            }
         }
     }
 }
@@ -272,6 +381,42 @@ int tfbs_shapes_upload(tfbs_ctx *ctx, const float *tables, const int32_t *kinds,
                 for (int k = 0; k < 5; k++) be = be * 4 + ((x >> (2 * k)) & 3);
                 le[((size_t)t * 2 + plane) * 1024 + x] = tables[((size_t)t * 2 + plane) * 1024 + be];
             }
+    // packed centi-unit planes (see shape_tracks_c16_kernel)
+    {
+        bool centi = true;
+        std::vector<int32_t> cv(le.size());
+        for (size_t i = 0; i < le.size() && centi; i++) {
+            const long c = lrintf(le[i] * 100.0f);
+            cv[i] = (int32_t)c;
+            if (c < -32767 || c > 32767 || centi_to_float((int)c) != le[i]) centi = false;
+        }
+        if (centi) {
+            std::vector<int> pern, step;
+            for (int t = 0; t < T; t++) (kinds[t] == TFBS_SHAPE_PER_NUCLEOTIDE ? pern : step).push_back(t);
+            std::vector<uint32_t> words;
+            auto plane = [&](int t, int pl, int x) { return (uint32_t)(cv[((size_t)t * 2 + pl) * 1024 + x] & 0xFFFF); };
+            for (size_t i = 0; i < pern.size(); i += 2) {
+                const int a = pern[i], b = i + 1 < pern.size() ? pern[i + 1] : -1;
+                s->c16_kind.push_back(0);
+                s->c16_row_a.push_back(a);
+                s->c16_row_b.push_back(b);
+                for (int x = 0; x < 1024; x++) words.push_back(plane(a, 0, x) | (b >= 0 ? plane(b, 0, x) << 16 : 0u));
+            }
+            for (int t : step) {
+                s->c16_kind.push_back(1);
+                s->c16_row_a.push_back(t);
+                s->c16_row_b.push_back(-1);
+                for (int x = 0; x < 1024; x++) words.push_back(plane(t, 0, x) | (plane(t, 1, x) << 16));
+            }
+            cudaError_t e2 = cudaMalloc(&s->c16_words, words.size() * 4);
+            if (e2 == cudaSuccess) e2 = cudaMemcpy(s->c16_words, words.data(), words.size() * 4, cudaMemcpyHostToDevice);
+            if (e2 != cudaSuccess) {
+                cudaGetLastError();
+                if (s->c16_words) cudaFree(s->c16_words);
+                s->c16_words = nullptr;
+            }
+        }
+    }
     cudaError_t e = cudaMalloc(&s->tables, le.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&s->kinds_dev, T * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(s->tables, le.data(), le.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -291,6 +436,7 @@ int tfbs_shapes_destroy(tfbs_shapes *s)
     if (s->ctx) cudaSetDevice(s->ctx->device);
     if (s->tables) cudaFree(s->tables);
     if (s->kinds_dev) cudaFree(s->kinds_dev);
+    if (s->c16_words) cudaFree(s->c16_words);
     delete s;
     return TFBS_OK;
 }
@@ -339,7 +485,23 @@ int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *sha
     P.out = (float *)ctx->tracks.ptr;
     const int64_t grid = std::min<int64_t>(pitch / (kShapeThreads * kShapePosPerThread), (int64_t)ctx->sm_count * 8);
     tfbs_begin(ctx);
-    {
+    if (shapes->c16_words) {
+        Packed16Params Q;
+        Q.packed = seq->packed;
+        Q.mask = seq->mask;
+        Q.n_words = seq->n_words;
+        Q.n_mask = seq->n_mask;
+        Q.pitch = pitch;
+        Q.words = shapes->c16_words;
+        Q.NW = (int32_t)shapes->c16_kind.size();
+        for (int w = 0; w < kMaxTracks; w++) {
+            Q.kind[w] = w < Q.NW ? shapes->c16_kind[w] : 0;
+            Q.row_a[w] = w < Q.NW ? shapes->c16_row_a[w] : 0;
+            Q.row_b[w] = w < Q.NW ? shapes->c16_row_b[w] : -1;
+        }
+        Q.out = P.out;
+        shape_tracks_c16_kernel<<<(unsigned)grid, kShapeThreads, (size_t)Q.NW * 4096, ctx->stream>>>(Q);
+    } else {
         const size_t smem = (size_t)T * 2048 * sizeof(float);
         TFBS_CHECK_CUDA(cudaFuncSetAttribute(shape_tracks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shape_tracks_kernel<<<(unsigned)grid, kShapeThreads, smem, ctx->stream>>>(P);

@@ -294,12 +294,16 @@ def test_shape_tracks_bit_exact_single_record(ctx, n):
 
 @pytest.mark.parametrize("shapes", [("MGW",), ("Roll",), ("MGW", "ProT", "Roll", "HelT"), ("Roll", "MGW", "HelT"),
                                     ("HelT", "EP", "Roll", "MGW", "ProT"),
-                                    ("MGW", "ProT", "EP", "MGW", "Roll", "HelT", "Roll")])
-def test_shape_tracks_every_track_mix(ctx, shapes):
-    """Packed-table kernel specialisations and the generic fall-through (7 tracks, 10 planes)."""
+                                    ("MGW", "ProT", "EP", "MGW", "Roll", "HelT", "Roll", "EP")])
+@pytest.mark.parametrize("two_decimals", [True, False])
+def test_shape_tracks_every_track_mix(ctx, shapes, two_decimals):
+    """Every track mix through both table representations: packed int16 centi-units (tables with
+    exact 2-decimal values, as DNAshapeR's) and plain fp32 (arbitrary values)."""
     rng = np.random.default_rng(len(shapes))
     seq = _noisy_seq(rng, 70_001)
     tables, kinds = dnashape.synthetic_tables(shapes)
+    if not two_decimals:
+        tables = (tables * np.float32(1.0371) + np.float32(0.00123)).astype(np.float32)
     tab = ctx.upload_shapes(tables, kinds)
     enc = ctx.encode(seq)
     got = ctx.shape_tracks(enc, tab)
