@@ -79,13 +79,12 @@ struct tfbs_pwms {
     std::vector<double> logodds;     // host copy [M][Lmax][4]
     // exact matrices for re-scoring: double[M][2][TFBS_MAX_MOTIF_LEN][4] (strand 0 fwd, 1 revcomp)
     double *exact = nullptr;
-    // fp32 k-mer LUTs (k = 3): per motif G[m] groups of 64 float2 (fwd, rev), concatenated
+    // dense mode: fp32 k-mer LUTs (k = 4 for L <= 24, else 3): per motif G groups of 4^k float2 (fwd, rev)
     float2 *lut = nullptr;
     int32_t *lut_off = nullptr;      // [M] offset in float2 units
-    int32_t *glen = nullptr;         // [M] packed (G << 8) | L
-    float *fslack = nullptr;         // [M] fp32 filter slack (upper bound of |fp32 - exact|)
-    std::vector<float> fslack_host;
+    int32_t *glen = nullptr;         // [M] packed (K << 16) | (G << 8) | L
     int64_t lut_entries = 0;
+    size_t dense_lut_bytes = 0;      // shared memory the dense kernel needs for its largest table
     int32_t Gmax = 0;
     // ---- hits mode (scan_hits.cu): motifs sorted by length, 32 per block, one lane each ----
     int32_t n_blocks = 0;

@@ -35,12 +35,14 @@ struct ScanParams {
     float *out_rev;
 };
 
-// Dense mode.  Persistent CTAs; for each motif the 3-mer table is expanded into shared memory as
-// T[g][x][lane] (8 B = fwd, rev) — one private copy per lane, so the 32 data-dependent LDS.64 of a
-// warp hit 32 different bank pairs: no bank conflicts (the v1 layout T[g][x] lost 60 % of its
-// shared-memory wavefronts to conflicts, profiles/r01/ncu_full_v1_raw.csv).  The table is 16 KB
-// aligned so a lookup address is  base | (x << 8)  (one funnel shift + one LOP3), the group offset
-// is an immediate (G is a template parameter) and both strands are accumulated with one packed
+// Dense mode.  Persistent CTAs; for each motif the k-mer table (k = 4 for L <= 24, else 3) is
+// expanded into shared memory as T[g][x][lane & 15] (8 B = fwd, rev): an LDS.64 is served one
+// half-warp at a time, so 16 private copies make every data-dependent load bank-conflict free (the
+// v1 layout T[g][x] lost 60 % of its shared-memory wavefronts to conflicts,
+// profiles/r01/ncu_full_v1_raw.csv) and leave room for 256-entry groups: L = 20 costs 5 loads per
+// window instead of 7.  The table is 32 KB aligned so a lookup address is
+// base | (kmer << 7) | ((lane & 15) << 3)  (one shift + one LOP3), the group offset is an
+// immediate (K, G are template parameters) and both strands are accumulated with one packed
 // add.rn.f32x2.  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 8
 // consecutive starts from a 48-base register window and writes 32 B per strand (streaming stores).
 __device__ __forceinline__ uint64_t lds64(uint32_t addr)
@@ -56,9 +58,11 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
     return r;
 }
 
-template <int G>
+template <int K, int G>
 __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, uint32_t lut_lane_addr)
 {
+    constexpr uint32_t kIndexMask = (uint32_t)((1 << (2 * K)) - 1) << 7;  // entry stride = 16 copies x 8 B
+    constexpr int kGroupBytes = (1 << (2 * K)) * 128;
     const int tid = threadIdx.x;
     const int64_t n_tiles = P.pitch / kTile;
     const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
@@ -66,37 +70,45 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
     float *row_r = P.out_rev + (size_t)m * P.pitch;
     const uint64_t qnan2 = 0x7FC000007FC00000ull;
 
+    // raw words of the current tile (prefetched one tile ahead so the L2 latency of the next
+    // window overlaps the shared-memory work of this one)
+    uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0, rm0 = 0, rm1 = 0, rm2 = 0;
+    auto fetch = [&](int64_t tile) {
+        const int64_t q0 = tile * kTile + (int64_t)tid * kPosPerThread;
+        const uint32_t *wp = P.packed + (q0 >> 4);
+        ra0 = __ldg(wp); ra1 = __ldg(wp + 1); ra2 = __ldg(wp + 2); ra3 = __ldg(wp + 3);
+        const uint32_t *mp = P.mask + (q0 >> 5);
+        rm0 = __ldg(mp); rm1 = __ldg(mp + 1); rm2 = __ldg(mp + 2);
+    };
+    if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
         // 48-base register window starting at p0 (p0 is a multiple of 8)
         uint32_t w0, w1, w2, inv_lo, inv_hi;
         {
-            const uint32_t *wp = P.packed + (p0 >> 4);
             const int sh = (int)(p0 & 15) * 2;
-            const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
-            w0 = __funnelshift_r(a0, a1, sh);
-            w1 = __funnelshift_r(a1, a2, sh);
-            w2 = __funnelshift_r(a2, a3, sh);
-            const uint32_t *mp = P.mask + (p0 >> 5);
+            w0 = __funnelshift_r(ra0, ra1, sh);
+            w1 = __funnelshift_r(ra1, ra2, sh);
+            w2 = __funnelshift_r(ra2, ra3, sh);
             const int msh = (int)(p0 & 31);
-            const uint32_t m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
-            inv_lo = __funnelshift_r(m0, m1, msh);
-            inv_hi = __funnelshift_r(m1, m2, msh);
+            inv_lo = __funnelshift_r(rm0, rm1, msh);
+            inv_hi = __funnelshift_r(rm1, rm2, msh);
         }
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
         uint64_t acc[kPosPerThread];
 #pragma unroll
         for (int g = 0; g < G; g++) {
 #pragma unroll
             for (int p = 0; p < kPosPerThread; p++) {
-                // bits [8,14) of t = 3-mer code at base p0 + p + 3g
-                const uint32_t t = (2 * p >= 8) ? (w0 >> (2 * p - 8)) : (w0 << (8 - 2 * p));
-                const uint64_t v = lds64(((t & 0x3F00u) | lut_lane_addr) + g * 16384);
+                // bits [7, 7+2K) of t = k-mer code at base p0 + p + K*g
+                const uint32_t t = (2 * p >= 7) ? (w0 >> (2 * p - 7)) : (w0 << (7 - 2 * p));
+                const uint64_t v = lds64(((t & kIndexMask) | lut_lane_addr) + g * kGroupBytes);
                 acc[p] = g == 0 ? v : add_f32x2(acc[p], v);
             }
             if (g + 1 < G) {
-                w0 = __funnelshift_r(w0, w1, 6);
-                w1 = __funnelshift_r(w1, w2, 6);
-                w2 >>= 6;
+                w0 = __funnelshift_r(w0, w1, 2 * K);
+                w1 = __funnelshift_r(w1, w2, 2 * K);
+                w2 >>= 2 * K;
             }
         }
         float af[kPosPerThread], ar[kPosPerThread];
@@ -120,27 +132,29 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 scan_dense_kernel(const ScanParams P)
 {
     extern __shared__ uint8_t dense_smem_raw[];
-    // 16 KB-align the table inside the dynamic shared window
+    // 32 KB-align the table inside the dynamic shared window so that an entry address is
+    // base | (kmer << 7) | ((lane & 15) << 3)
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(dense_smem_raw);
-    const uint32_t pad = ((raw + 16383u) & ~16383u) - raw;
-    float2 *s_lut = reinterpret_cast<float2 *>(dense_smem_raw + pad);  // [G][64][32]
+    const uint32_t pad = ((raw + 32767u) & ~32767u) - raw;
+    float2 *s_lut = reinterpret_cast<float2 *>(dense_smem_raw + pad);  // [G][4^K][16]
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t lut_lane_addr = raw + pad + (uint32_t)lane * 8u;
+    const uint32_t lut_lane_addr = raw + pad + (uint32_t)(lane & 15) * 8u;
 
     for (int m = 0; m < P.M; m++) {
         const int32_t gl = __ldg(P.glen + m);
-        const int G = gl >> 8, L = gl & 255;
+        const int K = gl >> 16, G = (gl >> 8) & 255, L = gl & 255;
         __syncthreads();  // everyone is done with the previous motif's table
         {
             const float2 *src = P.lut + __ldg(P.lut_off + m);
-            for (int i = tid; i < G * 64 * 32; i += kScanThreads) s_lut[i] = __ldg(src + (i >> 5));
+            const int total = G << (2 * K + 4);  // G * 4^K entries x 16 copies
+            for (int i = tid; i < total; i += kScanThreads) s_lut[i] = __ldg(src + (i >> 4));
         }
         __syncthreads();
-        switch (G) {
-#define TFBS_DCASE(g) \
-    case g: dense_tiles<g>(P, m, L, lut_lane_addr); break;
-            TFBS_DCASE(1) TFBS_DCASE(2) TFBS_DCASE(3) TFBS_DCASE(4) TFBS_DCASE(5) TFBS_DCASE(6)
-            TFBS_DCASE(7) TFBS_DCASE(8) TFBS_DCASE(9) TFBS_DCASE(10) TFBS_DCASE(11)
+        switch ((K << 8) | G) {
+#define TFBS_DCASE(k, g) \
+    case ((k << 8) | g): dense_tiles<k, g>(P, m, L, lut_lane_addr); break;
+            TFBS_DCASE(4, 1) TFBS_DCASE(4, 2) TFBS_DCASE(4, 3) TFBS_DCASE(4, 4) TFBS_DCASE(4, 5) TFBS_DCASE(4, 6)
+            TFBS_DCASE(3, 9) TFBS_DCASE(3, 10) TFBS_DCASE(3, 11)
 #undef TFBS_DCASE
             default: break;
         }
@@ -190,8 +204,8 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->kmer_f64.assign((size_t)M * 2 * kMaxGroups * 64, 0.0);
     std::vector<int32_t> lut_off(M), glen(M);
     std::vector<float2> lut;
-    p->fslack_host.resize(M);
     int Gmax = 0;
+    size_t dense_lut_bytes = 0;  // largest per-motif table once expanded to 16 lane copies
     for (int m = 0; m < M; m++) {
         const int L = lens[m], G = (L + 2) / 3;
         Gmax = std::max(Gmax, G);
@@ -202,11 +216,8 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
                 F[j * 4 + b] = logodds[((size_t)m * Lmax + j) * 4 + b];
                 R[j * 4 + b] = logodds[((size_t)m * Lmax + (L - 1 - j)) * 4 + (3 - b)];
             }
-        lut_off[m] = (int32_t)lut.size();
-        glen[m] = (G << 8) | L;
-        double sabs = 0.0;
-        for (int g = 0; g < G; g++) {
-            double gmax = 0.0;
+        // hits mode: double 3-mer partial sums (quantised per threshold in scan_hits.cu)
+        for (int g = 0; g < G; g++)
             for (int x = 0; x < 64; x++) {
                 double sf = 0.0, sr = 0.0;
                 for (int j = 0; j < 3 && 3 * g + j < L; j++) {
@@ -216,16 +227,24 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
                 }
                 p->kmer_f64[((size_t)(m * 2 + 0) * kMaxGroups + g) * 64 + x] = sf;
                 p->kmer_f64[((size_t)(m * 2 + 1) * kMaxGroups + g) * 64 + x] = sr;
-                if (std::isfinite(sf)) gmax = std::max(gmax, std::fabs(sf));
-                if (std::isfinite(sr)) gmax = std::max(gmax, std::fabs(sr));
+            }
+        // dense mode: fp32 k-mer tables, k = 4 (256 entries per group) for L <= 24, else k = 3
+        const int K = L <= 24 ? 4 : 3, Gd = (L + K - 1) / K, E = 1 << (2 * K);
+        lut_off[m] = (int32_t)lut.size();
+        glen[m] = (K << 16) | (Gd << 8) | L;
+        dense_lut_bytes = std::max(dense_lut_bytes, (size_t)Gd * E * 16 * sizeof(float2));
+        for (int g = 0; g < Gd; g++)
+            for (int x = 0; x < E; x++) {
+                double sf = 0.0, sr = 0.0;
+                for (int j = 0; j < K && K * g + j < L; j++) {
+                    const int b = (x >> (2 * j)) & 3;
+                    sf += F[(K * g + j) * 4 + b];
+                    sr += R[(K * g + j) * 4 + b];
+                }
                 lut.push_back(make_float2((float)sf, (float)sr));
             }
-            sabs += gmax;
-        }
-        // |fp32 running sum - exact| <= G * 2^-24 * sum_g max|entry| (entry rounding + G-1 adds);
-        // doubled for safety, plus an absolute epsilon
-        p->fslack_host[m] = (float)(2.0 * (G + 1) * std::ldexp(1.0, -24) * sabs + 1e-6);
     }
+    p->dense_lut_bytes = dense_lut_bytes;
     p->Gmax = Gmax;
     p->lut_entries = (int64_t)lut.size();
 
@@ -316,7 +335,7 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
     fill_params(P, seq, pwms, pitch);
     P.out_fwd = (float *)ctx->dense_fwd.ptr;
     P.out_rev = (float *)ctx->dense_rev.ptr;
-    const size_t smem = (size_t)pwms->Gmax * 64 * 32 * sizeof(float2) + 16384;  // + alignment slack
+    const size_t smem = pwms->dense_lut_bytes + 32768;  // + alignment slack
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = std::min<int64_t>(ctx->sm_count, pitch / kTile);
     tfbs_begin(ctx);

@@ -15,7 +15,7 @@
 //     a window is a candidate iff bit 15 of its field is still clear — a proven superset of
 //     {score >= threshold}.
 //   * the warp walks its segment base by base (the 3-mer code is warp-uniform, sliced from the
-//     2-bit packed words staged in shared memory by TMA); G loads feed G of the 48 ring
+//     2-bit packed words staged in shared memory by TMA); G loads feed G of the 32 ring
 //     accumulators held in registers; the accumulator that just received its last group is tested.
 //   * candidates (rare) go to a per-warp shared-memory queue and are verified 32 at a time:
 //     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
