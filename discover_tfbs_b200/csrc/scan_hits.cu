@@ -247,7 +247,7 @@ __device__ __forceinline__ void drain_queue(const PushCtx &C)
 }
 
 // One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 motifs of the
-// resident block.  G = column groups of the block (compile time, so the 48-entry accumulator ring
+// resident block.  G = column groups of the block (compile time, so the 32-entry accumulator ring
 // and all LUT offsets are static).
 template <int G>
 __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s_words, uint32_t lut_lane_addr,
