@@ -118,6 +118,7 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     free_scratch(ctx->misc);
     free_scratch(ctx->flush);
     free_scratch(ctx->thr);
+    free_scratch(ctx->sort);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);

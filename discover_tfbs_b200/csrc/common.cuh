@@ -58,6 +58,7 @@ struct tfbs_ctx {
     tfbs_scratch misc;                  // small argument staging
     tfbs_scratch flush;                 // >L2 buffer for tfbs_flush_l2
     tfbs_scratch thr;                   // per-motif thresholds
+    tfbs_scratch sort;                  // radix-sort double buffers for ordered hit output
 };
 
 struct tfbs_seq {

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cstdlib>
 #include <cstring>
 
@@ -402,6 +403,56 @@ struct HitLess {
     }
 };
 
+// key = (motif, window start, strand): the order PositionSpecificScoringMatrix.search yields hits in
+// (by position, forward before reverse), motif-major
+__global__ void __launch_bounds__(256) hit_keys_kernel(const tfbs_hit *__restrict__ hits, unsigned long long n,
+                                                       unsigned long long *__restrict__ keys)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const tfbs_hit h = hits[i];
+        const unsigned long long rev = h.pos < 0;
+        const unsigned long long pos = (unsigned long long)(rev ? ~h.pos : h.pos);
+        keys[i] = ((unsigned long long)(uint32_t)h.motif << 43) | (pos << 1) | rev;
+    }
+}
+
+// Device-side ordering of the first n hits in ctx->hits (CUB radix sort of 64-bit keys carrying the
+// 16-byte records).  The sorted records end up back in ctx->hits.
+int sort_hits_device(tfbs_ctx *ctx, int64_t n, int M)
+{
+    if (n <= 1) return TFBS_OK;
+    int motif_bits = 1;
+    while ((1 << motif_bits) < M) motif_bits++;
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const tfbs_hit *)nullptr, (tfbs_hit *)nullptr, (int64_t)n, 0, 43 + motif_bits, ctx->stream);
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t need = al((size_t)n * 8) * 2 + al((size_t)n * sizeof(tfbs_hit)) + al(temp_bytes) + 256;
+    int rc = tfbs_scratch_reserve(ctx->sort, need);
+    if (rc) return rc;
+    char *p = (char *)ctx->sort.ptr;
+    unsigned long long *keys = (unsigned long long *)p;
+    p += al((size_t)n * 8);
+    unsigned long long *keys_out = (unsigned long long *)p;
+    p += al((size_t)n * 8);
+    tfbs_hit *hits_out = (tfbs_hit *)p;
+    p += al((size_t)n * sizeof(tfbs_hit));
+    void *temp = p;
+    tfbs_hit *hits = (tfbs_hit *)ctx->hits.ptr;
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    hit_keys_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(hits, (unsigned long long)n, keys);
+    tfbs_launched(ctx);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, hits, hits_out, (int64_t)n, 0,
+                                                    43 + motif_bits, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, hits_out, (size_t)n * sizeof(tfbs_hit), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        tfbs_set_error("sorting hits on the device failed: %s", cudaGetErrorString(e));
+        return TFBS_ERR_CUDA;
+    }
+    return TFBS_OK;
+}
+
 size_t hits_smem_bytes(int lut_groups)
 {
     return 8192 /* alignment slack */ + (size_t)lut_groups * 8192 + kTileWords * 4 + kTileMask * 4 +
@@ -558,12 +609,15 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     *n_hits = (int64_t)cnt;
     ctx->last_candidates = (int64_t)cnt2[1];
     const int64_t take = std::min<int64_t>((int64_t)cnt, cap);
+    if (sorted && take > 1) {
+        rc = sort_hits_device(ctx, take, M);  // also orders the device-resident copy (out_host == NULL)
+        if (rc) return rc;
+    }
     if (out_host && take > 0) {
         TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)take * sizeof(tfbs_hit),
                                         cudaMemcpyDeviceToHost, ctx->stream));
-        TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (sorted) std::sort(out_host, out_host + take, HitLess());
     }
+    TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     if ((int64_t)cnt > cap) {
         tfbs_set_error("tfbs_scan_hits: %llu hits exceed capacity %lld", cnt, (long long)cap);
         return TFBS_ERR_OVERFLOW;

@@ -102,3 +102,35 @@ def test_c5_shard_shape_tracks_properties(ctx):
     enc.close()
     dev.close()
     tab.close()
+
+
+def test_c5_scale_positions_beyond_2_31(ctx):
+    """One flat 3.1 Gb sequence (config C5 as a single record): hit positions are int64 and the
+    part of the scan beyond 2^31 equals an independent scan of the same bases regenerated from the
+    position-addressable generator."""
+    n = 3_100_000_000
+    logodds, lens = synth.pwm_library(5, 4, lmin=10, lmax=20)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-6, gc=0.41, seed=5, sample=2_000_000)
+    lib = ctx.upload_pwms(logodds, lens)
+    dev = ctx.synth_ascii(39, 0, n, gc=0.41)
+    enc = ctx.encode_device(dev.ptr, n)
+    dev.close()
+    hits = ctx.scan_hits(enc, lib, thr, cap=1 << 22, sort=True)
+    enc.close()
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    assert hits.size > 1000 and gpos.max() > 2**31 and gpos.min() >= 0
+    assert np.all(gpos[hits["motif"] == 0][1:] >= gpos[hits["motif"] == 0][:-1])  # sorted per motif
+    # independent check of the last 50 Mb (all positions > 2^31)
+    start = n - 50_000_000
+    tail = ctx.synth_ascii(39, start, 50_000_000, gc=0.41)
+    e2 = ctx.encode_device(tail.ptr, 50_000_000)
+    tail.close()
+    part = ctx.scan_hits(e2, lib, thr, cap=1 << 20, sort=True)
+    e2.close()
+    lib.close()
+    lp = np.where(part["pos"] < 0, ~part["pos"], part["pos"]) + start
+    sel = gpos >= start
+    # windows starting in the first Lmax-1 bases of the tail see the same bases in both scans
+    assert np.array_equal(gpos[sel], lp) and np.array_equal(hits["motif"][sel], part["motif"])
+    assert np.array_equal(hits["score"][sel], part["score"])
+    assert np.array_equal(hits["pos"][sel] < 0, part["pos"] < 0)
