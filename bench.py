@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--motifs", type=int, default=800)
     ap.add_argument("--rate", type=float, default=1e-4, help="expected hit rate per position per strand")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel roofline section")
+    ap.add_argument("--with-shape", action="store_true",
+                    help="config C5 flavour: every step also computes 4 DNA-shape tracks of the chunk")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -58,8 +60,10 @@ def workload(args):
 
 def config_dict(args, n_gpus, per_gpu):
     return {
-        "workload": "C4: 800-PWM JASPAR-sized library (L 6-30) x 100 Mb synthetic genome per GPU, "
-                    "both strands, thresholded hits",
+        "workload": ("C4: 800-PWM JASPAR-sized library (L 6-30) x 100 Mb synthetic genome per GPU, "
+                     "both strands, thresholded hits" if not (args.with_shape or per_gpu != 100_000_000) else
+                     f"C5 flavour: {args.motifs} PWMs x {per_gpu} bp per GPU, hits"
+                     + (" + 4 DNA-shape tracks" if args.with_shape else "")),
         "motifs": args.motifs, "motif_len": "6-30", "genome_bp_per_gpu": per_gpu,
         "genome_bp_total": per_gpu * n_gpus, "hit_rate_target": args.rate, "mode": "hits",
         "sharding": f"chunk+halo x{n_gpus}, no collective", "l2": "flushed before every timed step",
@@ -281,6 +285,13 @@ def run_ours(args):
             torch.cuda.synchronize()
         ctx.sync()
 
+    shape_tab = None
+    if args.with_shape:
+        from discover_tfbs_b200 import dnashape
+        st, sk = dnashape.synthetic_tables(("MGW", "ProT", "Roll", "HelT"))
+        shape_tab = ctx.upload_shapes(st, sk)
+        ctx.shape_tracks(enc, shape_tab, to_host=False)
+
     def step_resident():
         enc.reencode_device(dev_ascii.ptr)
         return ctx.scan_hits(enc, lib, thr, cap=cap, to_host=False)
@@ -298,7 +309,7 @@ def run_ours(args):
     barrier()
     sampler.start()
     launches0 = ctx.total_kernel_launches()
-    step_ms, scan_ms, enc_ms = [], [], []
+    step_ms, scan_ms, enc_ms, shape_ms = [], [], [], []
     for _ in range(args.steps):
         ctx.flush_l2()
         launches_flush = ctx.total_kernel_launches()
@@ -307,6 +318,9 @@ def run_ours(args):
         enc_ms.append(ctx.last_kernel_ms())
         n_hits = ctx.scan_hits(enc, lib, thr, cap=cap, to_host=False)
         scan_ms.append(ctx.last_kernel_ms())
+        if shape_tab is not None:
+            ctx.shape_tracks(enc, shape_tab, to_host=False)
+            shape_ms.append(ctx.last_kernel_ms())
         step_ms.append(ctx.timer_stop())
         del launches_flush
     launches = ctx.total_kernel_launches() - launches0
@@ -377,7 +391,8 @@ def run_ours(args):
                          "peak_gbs": smem_peak / 1e9, "frac": lookups * 4.0 / k_ms / 1e6 / (smem_peak / 1e9),
                          "peak_def": "148 SM x 128 B/clk x sampled SM clock"},
             },
-            "kernel_ms": {"encode": float(np.mean(enc_ms)), "scan_hits": k_ms},
+            "kernel_ms": {"encode": float(np.mean(enc_ms)), "scan_hits": k_ms,
+                          **({"shape_tracks_4": float(np.mean(shape_ms))} if shape_ms else {})},
         }
         if not args.no_extras:
             try:

@@ -106,3 +106,14 @@ def test_shards_run_sequentially_on_one_gpu_match_single_scan(ctx):
     lib.close()
     multi = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=[0])
     assert np.array_equal(multi, want)
+
+
+@pytest.mark.gpu
+def test_threads_drive_every_visible_gpu(ctx):
+    """One host thread per device (ctypes releases the GIL): with 1 GPU this degenerates to the
+    single-device case, with N it exercises N contexts concurrently."""
+    ndev = _lib.device_count()
+    genome, logodds, lens, thr = _workload(n=400_000, M=33)
+    got = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=list(range(ndev)))
+    want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
+    assert np.array_equal(got, want)
