@@ -89,12 +89,12 @@ struct tfbs_pwms {
     int32_t Gmax = 0;
     // ---- hits mode (scan_hits.cu): motifs sorted by length, 32 per block, one lane each ----
     int32_t n_blocks = 0;
-    std::vector<int32_t> blk_G, blk_lut_off, blk_motif;  // [n_blocks], [n_blocks], [n_blocks][32]
-    std::vector<double> kmer_f64;    // [M][2][11][64] double 3-mer partial sums (fwd, revcomp)
+    std::vector<int32_t> blk_A, blk_B, blk_lut_off, blk_motif;  // [n_blocks] x3, [n_blocks][32]
+    std::vector<double> exact_host;  // host copy of `exact`
+    size_t hits_lut_bytes = 0;       // largest block table (A * 32 KB + B * 8 KB)
     int64_t hq_lut_words = 0;        // total uint32 entries of the packed deficit tables
     uint32_t *hq_lut_dev = nullptr, *hq_kinit_dev = nullptr;
-    int32_t *hq_G_dev = nullptr;     // [n_blocks] groups the filter evaluates for the cached thresholds
-    int32_t *blk_G_dev = nullptr, *blk_lut_off_dev = nullptr, *blk_motif_dev = nullptr, *lens_dev = nullptr;
+    int32_t *blk_AB_dev = nullptr, *blk_lut_off_dev = nullptr, *blk_motif_dev = nullptr, *lens_dev = nullptr;
     std::vector<float> hq_thr;       // thresholds the cached tables were built for
     bool hq_valid = false;
 };
@@ -113,6 +113,7 @@ struct tfbs_shapes {
 };
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
+void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
 int tfbs_encode_range(tfbs_ctx *ctx, const void *ascii_dev, int64_t valid, tfbs_seq *s, int64_t base,
                       int64_t cover, cudaStream_t stream);
 

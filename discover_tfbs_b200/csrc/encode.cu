@@ -215,7 +215,7 @@ int alloc_seq(tfbs_ctx *ctx, int64_t n, tfbs_seq **out)
     tfbs_seq *s = new tfbs_seq();
     s->ctx = ctx;
     s->n = n;
-    const int64_t n_pad = ((n + 8191) / 8192) * 8192 + 3 * 8192;  // tiles of every kernel may over-read
+    const int64_t n_pad = ((n + 8191) / 8192) * 8192 + 5 * 8192;  // tiles of every kernel may over-read (hits: 32 256 + 128)
     s->n_words = n_pad / 16;
     s->n_mask = n_pad / 32;
     cudaError_t e = cudaMalloc(&s->packed, (size_t)s->n_words * 4);

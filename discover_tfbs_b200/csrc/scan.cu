@@ -201,7 +201,6 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->logodds.assign(logodds, logodds + (size_t)M * Lmax * 4);
 
     std::vector<double> exact((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
-    p->kmer_f64.assign((size_t)M * 2 * kMaxGroups * 64, 0.0);
     std::vector<int32_t> lut_off(M), glen(M);
     std::vector<float2> lut;
     int Gmax = 0;
@@ -215,18 +214,6 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
             for (int b = 0; b < 4; b++) {
                 F[j * 4 + b] = logodds[((size_t)m * Lmax + j) * 4 + b];
                 R[j * 4 + b] = logodds[((size_t)m * Lmax + (L - 1 - j)) * 4 + (3 - b)];
-            }
-        // hits mode: double 3-mer partial sums (quantised per threshold in scan_hits.cu)
-        for (int g = 0; g < G; g++)
-            for (int x = 0; x < 64; x++) {
-                double sf = 0.0, sr = 0.0;
-                for (int j = 0; j < 3 && 3 * g + j < L; j++) {
-                    const int b = (x >> (2 * j)) & 3;
-                    sf += F[(3 * g + j) * 4 + b];
-                    sr += R[(3 * g + j) * 4 + b];
-                }
-                p->kmer_f64[((size_t)(m * 2 + 0) * kMaxGroups + g) * 64 + x] = sf;
-                p->kmer_f64[((size_t)(m * 2 + 1) * kMaxGroups + g) * 64 + x] = sr;
             }
         // dense mode: fp32 k-mer tables, k = 4 (256 entries per group) for L <= 24, else k = 3
         const int K = L <= 24 ? 4 : 3, Gd = (L + K - 1) / K, E = 1 << (2 * K);
@@ -253,21 +240,29 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     for (int m = 0; m < M; m++) order[m] = m;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
     p->n_blocks = (M + 31) / 32;
-    p->blk_G.assign(p->n_blocks, 1);
+    p->blk_A.assign(p->n_blocks, 0);
+    p->blk_B.assign(p->n_blocks, 1);
     p->blk_lut_off.assign(p->n_blocks, 0);
     p->blk_motif.assign((size_t)p->n_blocks * 32, -1);
+    std::vector<int32_t> blk_AB(p->n_blocks);
     int64_t words = 0;
     for (int b = 0; b < p->n_blocks; b++) {
-        int g = 1;
+        int lmax_b = 1;
         for (int l = 0; l < 32 && b * 32 + l < M; l++) {
             const int m = order[b * 32 + l];
             p->blk_motif[(size_t)b * 32 + l] = m;
-            g = std::max(g, (lens[m] + 2) / 3);
+            lmax_b = std::max(lmax_b, lens[m]);
         }
-        p->blk_G[b] = g;
+        int A = 0, B = 1;
+        tfbs_hits_group_plan(lmax_b, &A, &B);  // A groups of 4 columns + B groups of 3
+        p->blk_A[b] = A;
+        p->blk_B[b] = B;
+        blk_AB[b] = (A << 8) | B;
         p->blk_lut_off[b] = (int32_t)words;
-        words += (int64_t)g * 64 * 32;
+        words += (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32;
+        p->hits_lut_bytes = std::max(p->hits_lut_bytes, (size_t)A * 32768 + (size_t)B * 8192);
     }
+    p->exact_host = exact;
     p->hq_lut_words = words;
 
     cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
@@ -276,12 +271,11 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_lut_dev, (size_t)p->hq_lut_words * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_kinit_dev, (size_t)p->n_blocks * 32 * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->hq_G_dev, (size_t)p->n_blocks * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->blk_G_dev, (size_t)p->n_blocks * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_AB_dev, (size_t)p->n_blocks * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->blk_lut_off_dev, (size_t)p->n_blocks * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->blk_motif_dev, (size_t)p->n_blocks * 32 * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->lens_dev, (size_t)M * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(p->blk_G_dev, p->blk_G.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->blk_AB_dev, blk_AB.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->blk_lut_off_dev, p->blk_lut_off.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->blk_motif_dev, p->blk_motif.data(), (size_t)p->n_blocks * 32 * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lens_dev, lens, (size_t)M * 4, cudaMemcpyHostToDevice);
@@ -308,8 +302,7 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (p->glen) cudaFree(p->glen);
     if (p->hq_lut_dev) cudaFree(p->hq_lut_dev);
     if (p->hq_kinit_dev) cudaFree(p->hq_kinit_dev);
-    if (p->hq_G_dev) cudaFree(p->hq_G_dev);
-    if (p->blk_G_dev) cudaFree(p->blk_G_dev);
+    if (p->blk_AB_dev) cudaFree(p->blk_AB_dev);
     if (p->blk_lut_off_dev) cudaFree(p->blk_lut_off_dev);
     if (p->blk_motif_dev) cudaFree(p->blk_motif_dev);
     if (p->lens_dev) cudaFree(p->lens_dev);

@@ -5,24 +5,26 @@
 // exact-match BLASTn candidate stage (utils.py:340-398, process_blast.sh:32).
 //
 // Design (one warp lane = one motif, so shared-memory LUT reads are bank-conflict free):
-//   * motifs are sorted by length and grouped 32 to a block; a block's table lives in shared
-//     memory as T[g][x][lane] (g = group of 3 motif columns, x = 6-bit 3-mer code, 4 B per
-//     entry): the 32 lanes of a warp read 32 consecutive words for the same (g, x).
-//   * an entry packs two 16-bit fixed-point DEFICITS (how far the 3-mer is below the best 3-mer
+//   * motifs are sorted by length and grouped 32 to a block.  The columns of a block are cut into
+//     A groups of 4 columns followed by B groups of 3 (A, B chosen per block to minimise A + B under
+//     the shared-memory budget: a 4-mer group costs 32 KB, a 3-mer group 8 KB).  The block table
+//     lives in shared memory as T[g][x][lane] (x = 8- or 6-bit k-mer code, 4 B per entry): the 32
+//     lanes of a warp read 32 consecutive words for the same (g, x).
+//   * an entry packs two 16-bit fixed-point DEFICITS (how far the k-mer is below the best k-mer
 //     of that column group, in units chosen from the threshold), forward strand in the high
 //     half, reverse-complement strand in the low half, so one LDS.32 + one IADD scores both
 //     strands.  Deficits are rounded DOWN and capped, fields are sized so sums never carry, and
 //     a window is a candidate iff bit 15 of its field is still clear — a proven superset of
 //     {score >= threshold}.
-//   * the warp walks its segment base by base (the 3-mer code is warp-uniform, sliced from the
-//     2-bit packed words staged in shared memory by TMA); G loads feed G of the 32 ring
+//   * the warp walks its segment base by base (the k-mer code is warp-uniform, sliced from the
+//     2-bit packed words staged in shared memory by TMA); A + B loads feed A + B of the 32 ring
 //     accumulators held in registers; the accumulator that just received its last group is tested.
 //   * candidates (rare) go to a per-warp shared-memory queue and are verified 32 at a time:
 //     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
 //     float, compared with >= — so hit sets and scores are bit-exact.  Hits are compacted with
 //     ballot/popc and one global atomic per warp batch.
-//   * persistent CTAs (2 per SM) pull (motif block, tile) items from an atomic counter in
-//     block-major order, so a CTA re-loads its 8 KB x G table only when the block changes.
+//   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
+//     block-major order, so a CTA re-loads its table (up to 192 KB) only when the block changes.
 #include <algorithm>
 #include <cmath>
 #include <cooperative_groups.h>
@@ -36,17 +38,19 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kRing = 32;                 // ring accumulators: >= 3*(G-1)+1 for G <= 11, multiple of 16
 constexpr int kSeg = 2016;                // window starts per warp per tile (63 ring turns of 32)
-constexpr int kTilePos = kWarps * kSeg;   // 16128 starts per tile (multiple of 128)
+constexpr int kTilePos = kWarps * kSeg;   // 32256 starts per tile (multiple of 128)
 constexpr int kTileBases = kTilePos + 128;
-constexpr int kTileWords = kTileBases / 16;  // 1016 words  = 4064 B (multiple of 16)
-constexpr int kTileMask = kTileBases / 32;   // 508 words   = 2032 B (multiple of 16)
+constexpr int kTileWords = kTileBases / 16;  // 2024 words  = 8096 B (multiple of 16)
+constexpr int kTileMask = kTileBases / 32;   // 1012 words  = 4048 B (multiple of 16)
 constexpr int kQueueCap = 256;            // candidate queue entries per warp
 constexpr int kMaxG = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 constexpr uint32_t kPoison = 0x80008000u;
+constexpr int kLutBudget = 192 * 1024;    // shared memory for one block table (6 x 32 KB)
+constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + kWarps * 4 + 64 * 4 + 32;
 
 struct HitsParams {
     const uint32_t *packed;
@@ -54,9 +58,9 @@ struct HitsParams {
     int64_t n_tiles;   // tiles scanned by this launch
     int64_t tile0;     // first tile (chunk-pipelined launches scan a sub-range)
     int32_t n_blocks;
-    const uint32_t *qlut;        // per block [G_b][64][32] packed deficits
+    const uint32_t *qlut;        // per block [A][256][32] then [B][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
-    const int32_t *blk_G;        // [n_blocks] column groups the filter evaluates (<= groups of the block)
+    const int32_t *blk_AB;       // [n_blocks] (A << 8) | B: 4-column and 3-column groups of the block
     const uint32_t *kinit;       // [n_blocks][32] initial field values (0x7FFF - Dq per strand)
     const int32_t *blk_motif;    // [n_blocks][32] original motif index or -1
     const int32_t *lens;         // [M]
@@ -248,9 +252,10 @@ __device__ __forceinline__ void drain_queue(const PushCtx &C)
 }
 
 // One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 motifs of the
-// resident block.  G = column groups of the block (compile time, so the 32-entry accumulator ring
-// and all LUT offsets are static).
-template <int G>
+// resident block.  A, B = 4-column and 3-column groups of the block (compile time, so the 32-entry
+// accumulator ring and all LUT offsets are static).  Group g < A covers columns 4g..4g+3, group
+// A + j covers columns 4A+3j..4A+3j+2.
+template <int A, int B>
 __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s_words, uint32_t lut_lane_addr,
                                              uint32_t kinit)
 {
@@ -260,26 +265,52 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
     const uint32_t *wptr = s_words + (C.seg_begin >> 4);
     uint32_t wlo = wptr[0], whi = wptr[1];
     int wk = 2;
-    constexpr int kTail = 3 * (G - 1);
+    constexpr int kTail = B > 0 ? 4 * A + 3 * (B - 1) : 4 * (A - 1);  // column offset of the last group
     constexpr int kChunks = (kSeg + kTail + kRing - 1) / kRing;
+    constexpr int kCheck = (kRing - kTail >= 4) ? 4 : ((kRing - kTail >= 2) ? 2 : 1);
+    const uint32_t lut3_lane_addr = lut_lane_addr + A * 32768;
     for (int c = 0; c < kChunks; c++) {
         const int q0 = C.seg_begin + c * kRing;
 #pragma unroll
         for (int j = 0; j < kRing; j++) {
             const int jj = j & 15;
-            // bits [7,13) of t7 = 3-mer code at base q0 + j
+            // bits [7,15) of t7 = 4-mer code at base q0 + j, bits [7,13) = its 3-mer prefix
             const uint32_t t7 = (2 * jj >= 7) ? __funnelshift_r(wlo, whi, 2 * jj - 7) : (wlo << (7 - 2 * jj));
-            const uint32_t addr = (t7 & 0x1F80u) | lut_lane_addr;
+            if (A > 0) {
+                const uint32_t addr4 = (t7 & 0x7F80u) | lut_lane_addr;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const uint32_t v = lds32(addr + g * 8192);
-                const int slot = (j - 3 * g + 2 * kRing) % kRing;
-                if (g == 0) acc[slot] = kinit + v;
-                else acc[slot] += v;
+                for (int g = 0; g < A; g++) {
+                    const uint32_t v = lds32(addr4 + g * 32768);
+                    const int slot = (j - 4 * g + 2 * kRing) % kRing;
+                    if (g == 0) acc[slot] = kinit + v;
+                    else acc[slot] += v;
+                }
             }
-            const int fs = (j - kTail + 2 * kRing) % kRing;
-            const uint32_t cand = ~acc[fs] & kPoison;
-            if (cand) push_candidate(C, cand, q0 + j - kTail);
+            if (B > 0) {
+                const uint32_t addr3 = (t7 & 0x1F80u) | lut3_lane_addr;
+#pragma unroll
+                for (int g = 0; g < B; g++) {
+                    const uint32_t v = lds32(addr3 + g * 8192);
+                    const int slot = (j - 4 * A - 3 * g + 2 * kRing) % kRing;
+                    if (A == 0 && g == 0) acc[slot] = kinit + v;
+                    else acc[slot] += v;
+                }
+            }
+            // Candidate test, amortised over kCheck consecutive steps: bit 15 of a field stays SET
+            // in the AND of the finalised accumulators unless one of them cleared it.  (A finalised
+            // slot is re-opened 32 - kTail steps later, which bounds kCheck.)
+            if ((j % kCheck) == kCheck - 1) {
+                uint32_t all = acc[(j - kTail + 2 * kRing) % kRing];
+#pragma unroll
+                for (int k = 1; k < kCheck; k++) all &= acc[(j - k - kTail + 2 * kRing) % kRing];
+                if (~all & kPoison) {
+#pragma unroll
+                    for (int k = kCheck - 1; k >= 0; k--) {
+                        const uint32_t cand = ~acc[(j - k - kTail + 2 * kRing) % kRing] & kPoison;
+                        if (cand) push_candidate(C, cand, q0 + j - k - kTail);
+                    }
+                }
+            }
             if (jj == 15) {
                 wlo = whi;
                 whi = wptr[wk++];
@@ -288,18 +319,19 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-scan_hits_kernel(const HitsParams P, const int lut_groups)
+__global__ void __launch_bounds__(kThreads, 1)
+scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
 {
     extern __shared__ uint8_t smem_raw[];
-    // carve shared memory; the LUT must start on an 8 KB boundary of the shared window so that
-    // (g << 13) | (x << 7) | (lane << 2) can be OR-ed into the address
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t lut_off = ((raw + 8191u) & ~8191u) - raw;
+    if (smem_base_probe) {  // host asks where the dynamic shared window starts (see hits_smem_plan)
+        if (threadIdx.x == 0) *smem_base_probe = raw;
+        return;
+    }
+    // Shared memory: the small buffers first, then the block table on the next 32 KB boundary of the
+    // shared window so that  (g << 15) | (x << 7) | (lane << 2)  can be OR-ed into the address.
     Smem S;
-    uint8_t *p = smem_raw + lut_off;
-    S.lut = reinterpret_cast<uint32_t *>(p);
-    p += (size_t)lut_groups * 8192;
+    uint8_t *p = smem_raw;
     S.words = reinterpret_cast<uint32_t *>(p);
     p += kTileWords * 4;
     S.mask = reinterpret_cast<uint32_t *>(p);
@@ -315,6 +347,8 @@ scan_hits_kernel(const HitsParams P, const int lut_groups)
     S.bar = reinterpret_cast<uint64_t *>(p);
     p += 16;
     S.item = reinterpret_cast<uint32_t *>(p);
+    const uint32_t lut_addr = (raw + (uint32_t)kSmallBytes + 32767u) & ~32767u;
+    S.lut = reinterpret_cast<uint32_t *>(smem_raw + (lut_addr - raw));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(S.bar, 1);
@@ -325,7 +359,7 @@ scan_hits_kernel(const HitsParams P, const int lut_groups)
     int cur_block = -1;
     uint32_t phase = 0;
     uint32_t kinit = kPoison;
-    int G = 1;
+    int AB = 1;
     for (;;) {
         if (tid == 0) *S.item = atomicAdd(P.work_counter, 1u);
         __syncthreads();
@@ -335,17 +369,17 @@ scan_hits_kernel(const HitsParams P, const int lut_groups)
         const int64_t tile = P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles);
         const int64_t tile_start = tile * kTilePos;
         const bool new_block = b != cur_block;
-        if (new_block) G = __ldg(P.blk_G + b);
+        if (new_block) AB = __ldg(P.blk_AB + b);
         if (tid == 0) {
             // order the previous item's generic-proxy reads before the async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bytes = kTileWords * 4 + kTileMask * 4 + (new_block ? (uint32_t)G * 8192u : 0u);
-            mbar_expect_tx(S.bar, bytes);
+            const int chunks = new_block ? 4 * (AB >> 8) + (AB & 255) : 0;  // 8 KB pieces of the table
+            mbar_expect_tx(S.bar, kTileWords * 4 + kTileMask * 4 + (uint32_t)chunks * 8192u);
             tma_load_1d(S.words, P.packed + (tile_start >> 4), kTileWords * 4, S.bar);
             tma_load_1d(S.mask, P.mask + (tile_start >> 5), kTileMask * 4, S.bar);
             if (new_block) {
                 const uint32_t *src = P.qlut + __ldg(P.blk_lut_off + b);
-                for (int g = 0; g < G; g++) tma_load_1d(S.lut + g * 2048, src + g * 2048, 8192, S.bar);
+                for (int g = 0; g < chunks; g++) tma_load_1d(S.lut + g * 2048, src + g * 2048, 8192, S.bar);
             }
         }
         if (new_block) {
@@ -379,12 +413,16 @@ scan_hits_kernel(const HitsParams P, const int lut_groups)
         C.hits = P.hits;
         C.hit_count = P.hit_count;
         C.cap = P.cap;
-        const uint32_t lut_lane_addr = smem_u32(S.lut) + (uint32_t)lane * 4u;
-        switch (G) {
-#define TFBS_CASE(g) \
-    case g: scan_segment<g>(C, S.words, lut_lane_addr, kinit); break;
-            TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6)
-            TFBS_CASE(7) TFBS_CASE(8) TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11)
+        const uint32_t lut_lane_addr = lut_addr + (uint32_t)lane * 4u;
+        switch (AB) {
+#define TFBS_CASE(a, b) \
+    case ((a << 8) | b): scan_segment<a, b>(C, S.words, lut_lane_addr, kinit); break;
+            // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32
+            TFBS_CASE(0, 1) TFBS_CASE(0, 2) TFBS_CASE(0, 3) TFBS_CASE(1, 0) TFBS_CASE(1, 1) TFBS_CASE(1, 2)
+            TFBS_CASE(1, 3) TFBS_CASE(2, 0) TFBS_CASE(2, 1) TFBS_CASE(2, 2) TFBS_CASE(2, 3) TFBS_CASE(3, 0)
+            TFBS_CASE(3, 1) TFBS_CASE(3, 2) TFBS_CASE(3, 3) TFBS_CASE(3, 5) TFBS_CASE(3, 6) TFBS_CASE(4, 0)
+            TFBS_CASE(4, 1) TFBS_CASE(4, 2) TFBS_CASE(4, 3) TFBS_CASE(4, 4) TFBS_CASE(4, 5) TFBS_CASE(5, 0)
+            TFBS_CASE(5, 1) TFBS_CASE(5, 2) TFBS_CASE(5, 3) TFBS_CASE(5, 4) TFBS_CASE(6, 0)
 #undef TFBS_CASE
             default: break;
         }
@@ -453,13 +491,59 @@ int sort_hits_device(tfbs_ctx *ctx, int64_t n, int M)
     return TFBS_OK;
 }
 
-size_t hits_smem_bytes(int lut_groups)
+// Dynamic shared memory to request: small buffers + padding up to the next 32 KB boundary of the
+// shared window + the largest block table.  The window's base offset is a property of the kernel
+// (reserved + static shared memory), asked once from the kernel itself.
+int hits_smem_plan(tfbs_ctx *ctx, size_t lut_bytes, size_t *smem_out)
 {
-    return 8192 /* alignment slack */ + (size_t)lut_groups * 8192 + kTileWords * 4 + kTileMask * 4 +
-           kWarps * kQueueCap * 4 + kWarps * 4 + 64 * 4 + 16 + 16;
+    static thread_local int64_t cached_base = -1;
+    if (cached_base < 0) {
+        int rc = tfbs_scratch_reserve(ctx->misc, 64);
+        if (rc) return rc;
+        HitsParams dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        scan_hits_kernel<<<1, 32, 1024, ctx->stream>>>(dummy, (uint32_t *)ctx->misc.ptr);
+        uint32_t base = 0;
+        cudaError_t e = cudaMemcpyAsync(&base, ctx->misc.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            tfbs_set_error("scan_hits: shared-memory probe failed: %s", cudaGetErrorString(e));
+            return TFBS_ERR_CUDA;
+        }
+        cached_base = base;
+    }
+    const size_t lut_at = ((size_t)cached_base + kSmallBytes + 32767) / 32768 * 32768;
+    *smem_out = lut_at - (size_t)cached_base + lut_bytes;
+    if (*smem_out > 227 * 1024) {
+        tfbs_set_error("scan_hits: %zu bytes of shared memory needed, 232448 available", *smem_out);
+        return TFBS_ERR_INVALID;
+    }
+    return TFBS_OK;
 }
 
 }  // namespace
+
+// Column grouping of a block whose longest motif has L columns: A groups of 4 columns followed by
+// B groups of 3, minimising A + B (shared-memory loads per window) under the table budget
+// (32 KB per 4-mer group, 8 KB per 3-mer group), ties broken towards the smaller table.
+void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
+{
+    int best_a = 0, best_b = (L + 2) / 3, best_groups = 1 << 30, best_bytes = 1 << 30;
+    for (int a = 0; a <= 6; a++)
+        for (int b = 0; b <= kMaxG; b++) {
+            if (a + b < 1 || 4 * a + 3 * b < L) continue;
+            const int bytes = a * 32768 + b * 8192;
+            if (bytes > kLutBudget) continue;
+            if (a + b < best_groups || (a + b == best_groups && bytes < best_bytes)) {
+                best_groups = a + b;
+                best_bytes = bytes;
+                best_a = a;
+                best_b = b;
+            }
+        }
+    *A_out = best_a;
+    *B_out = best_b;
+}
 
 // Quantise the block tables for a threshold vector (host).  See the header comment for the
 // construction; everything rounds in the direction that keeps {candidates} a superset of {hits}.
@@ -469,36 +553,43 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     if (pw->hq_valid && pw->hq_thr.size() == (size_t)M && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * M) == 0)
         return TFBS_OK;
     const int nb = pw->n_blocks;
-    // The filter may ignore the last column group of a block: a partial deficit is a lower bound of
-    // the full one, so the candidate set stays a superset; every dropped group saves 1/G of the
-    // shared-memory traffic and multiplies the (rare) candidates.  TFBS_HITS_DROP_MIN_G = smallest
-    // block group count for which the last group is dropped (0 = never).
-    int drop_min_g = 0;  // measured on B200 (profiles/r01/drop_group_experiment.txt): never pays off
-    if (const char *e = getenv("TFBS_HITS_DROP_MIN_G")) drop_min_g = atoi(e);
-    std::vector<int32_t> filt_G(nb);
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)nb * 32, kPoison);
+    std::vector<double> ent;  // double k-mer partial sums of one (motif, strand): [group][4^k]
     for (int b = 0; b < nb; b++) {
-        const int Gfull = pw->blk_G[b];
-        const int G = (drop_min_g > 0 && Gfull >= drop_min_g) ? Gfull - 1 : Gfull;
-        filt_G[b] = G;
+        const int A = pw->blk_A[b], B = pw->blk_B[b], G = A + B;
         uint32_t *lut = qlut.data() + pw->blk_lut_off[b];
         const int dq_max = 0x7FFF / G - 3;
         const int capq = dq_max + 2;
+        // group g: first column, width, table offset (words) inside the block table
+        int gcol[2 * kMaxG], gk[2 * kMaxG], goff[2 * kMaxG];
+        for (int g = 0; g < G; g++) {
+            gk[g] = g < A ? 4 : 3;
+            gcol[g] = g < A ? 4 * g : 4 * A + 3 * (g - A);
+            goff[g] = g < A ? g * 256 * 32 : A * 256 * 32 + (g - A) * 64 * 32;
+        }
         for (int l = 0; l < 32; l++) {
             const int m = pw->blk_motif[(size_t)b * 32 + l];
             if (m < 0) continue;
-            const int Gm = (pw->lens[m] + 2) / 3;
+            const int L = pw->lens[m];
             const float t = thr[m];
             uint32_t kfield[2] = {0x8000u, 0x8000u};
             for (int s = 0; s < 2; s++) {
-                const double *e = pw->kmer_f64.data() + ((size_t)(m * 2 + s) * kMaxG) * 64;
-                double gmax[kMaxG];
+                const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s) * TFBS_MAX_MOTIF_LEN) * 4;
+                ent.assign((size_t)G * 256, 0.0);
+                double gmax[2 * kMaxG];
                 double best = 0.0;
                 bool reachable = true;
-                for (int g = 0; g < Gm; g++) {
+                int Gm = 0;  // groups that contain at least one column of this motif
+                for (int g = 0; g < G && gcol[g] < L; g++, Gm++) {
+                    const int E = 1 << (2 * gk[g]);
                     double mx = -INFINITY;
-                    for (int x = 0; x < 64; x++) mx = std::max(mx, e[g * 64 + x]);
+                    for (int x = 0; x < E; x++) {
+                        double v = 0.0;
+                        for (int j = 0; j < gk[g] && gcol[g] + j < L; j++) v += mat[(gcol[g] + j) * 4 + ((x >> (2 * j)) & 3)];
+                        ent[(size_t)g * 256 + x] = v;
+                        mx = std::max(mx, v);
+                    }
                     gmax[g] = mx;
                     best += mx;
                     if (!std::isfinite(mx)) reachable = false;  // a column group of -inf only
@@ -521,25 +612,26 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
                     Dq = (int)std::min(dqv, (double)(dq_max + 1));
                 }
                 kfield[s] = (uint32_t)(0x7FFF - Dq);
-                for (int g = 0; g < std::min(Gm, G); g++)
-                    for (int x = 0; x < 64; x++) {
-                        const double d = gmax[g] - e[g * 64 + x];  // >= 0, +inf for -inf entries
+                for (int g = 0; g < Gm; g++) {
+                    const int E = 1 << (2 * gk[g]);
+                    for (int x = 0; x < E; x++) {
+                        const double d = gmax[g] - ent[(size_t)g * 256 + x];  // >= 0, +inf for -inf entries
                         int q;
                         if (scale == 0.0) q = 0;
                         else {
                             const double v = std::floor(d * scale);
                             q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
                         }
-                        uint32_t &w = lut[((size_t)g * 64 + x) * 32 + l];
+                        uint32_t &w = lut[(size_t)goff[g] + (size_t)x * 32 + l];
                         w |= s == 0 ? ((uint32_t)q << 16) : (uint32_t)q;
                     }
+                }
             }
             kinit[(size_t)b * 32 + l] = (kfield[0] << 16) | kfield[1];
         }
     }
     cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), qlut.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), kinit.size() * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_G_dev, filt_G.data(), filt_G.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;
@@ -579,7 +671,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
     P.blk_lut_off = pwms->blk_lut_off_dev;
-    P.blk_G = pwms->hq_G_dev;
+    P.blk_AB = pwms->blk_AB_dev;
     P.kinit = pwms->hq_kinit_dev;
     P.blk_motif = pwms->blk_motif_dev;
     P.lens = pwms->lens_dev;
@@ -592,13 +684,13 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFFFFF0ll, "tfbs_scan_hits: too many work items");
     TFBS_REQUIRE((P.n_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits: sequence padding too small");
 
-    const int lut_groups = pwms->Gmax;
-    const size_t smem = hits_smem_bytes(lut_groups);
+    size_t smem = 0;
+    rc = hits_smem_plan(ctx, pwms->hits_lut_bytes, &smem);
+    if (rc) return rc;
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (int64_t)ctx->sm_count * 2;
-    grid = std::min<int64_t>(grid, P.n_tiles * P.n_blocks);
+    const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
     tfbs_begin(ctx);
-    scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, lut_groups);
+    scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
     tfbs_launched(ctx);
     rc = tfbs_end(ctx);
     if (rc) return rc;
@@ -682,7 +774,7 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
     P.blk_lut_off = pwms->blk_lut_off_dev;
-    P.blk_G = pwms->hq_G_dev;
+    P.blk_AB = pwms->blk_AB_dev;
     P.kinit = pwms->hq_kinit_dev;
     P.blk_motif = pwms->blk_motif_dev;
     P.lens = pwms->lens_dev;
@@ -691,8 +783,9 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     P.hits = (tfbs_hit *)ctx->hits.ptr;
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
-    const int lut_groups = pwms->Gmax;
-    const size_t smem = hits_smem_bytes(lut_groups);
+    size_t smem = 0;
+    rc = hits_smem_plan(ctx, pwms->hits_lut_bytes, &smem);
+    if (rc) return rc;
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     tfbs_begin(ctx);
@@ -711,8 +804,8 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
         P.n_tiles = t1 - t0;
         P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 16);
         TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 4, ctx->stream));
-        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * 2, P.n_tiles * P.n_blocks);
-        scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, lut_groups);
+        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
+        scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
         tfbs_launched(ctx);
         TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned_counts + c, ctx->hit_count.ptr, sizeof(unsigned long long),
                                         cudaMemcpyDeviceToHost, ctx->stream));
