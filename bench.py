@@ -362,17 +362,8 @@ def run_ours(args):
         # hits kernel: one LDS.32 per (lane, base, column group); motifs are sorted by descending
         # length and grouped 32 per block; a block of longest motif L uses A 4-column + B 3-column
         # groups (tfbs_hits_group_plan in csrc/scan_hits.cu: minimise A + B under 192 KB of tables)
-        def plan(L):
-            best = None
-            for a in range(7):
-                for b in range(12):
-                    if a + b >= 1 and 4 * a + 3 * b >= L and 32 * a + 8 * b <= 192:
-                        key = (a + b, 32 * a + 8 * b)
-                        if best is None or key < best:
-                            best = key
-            return best[0]
         order = np.sort(np.asarray(lens))[::-1]
-        blk_groups = [plan(int(order[i])) for i in range(0, len(order), 32)]
+        blk_groups = [sum(_lib.hits_group_plan(int(order[i]))) for i in range(0, len(order), 32)]
         lookups = float(n_scan) * 32.0 * float(sum(blk_groups))
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         smem_peak = 148 * 128 * sm_mhz * 1e6  # bytes/s of shared-memory bandwidth at the sampled clock

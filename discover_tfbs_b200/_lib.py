@@ -61,6 +61,7 @@ _PROTOTYPES = {
     "tfbs_track_sites": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "tfbs_similarity_sums": (C.c_int, [_vp] + [_vp] * 6 + [_i64] + [_vp] * 6 + [_i64, _vp]),
     "tfbs_debug_swar4": (C.c_int, [_u32, C.POINTER(_u32), C.POINTER(_u32)]),
+    "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
 }
 
 _lib = None
@@ -96,6 +97,13 @@ def _check(rc, allow=()):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
+
+
+def hits_group_plan(L: int):
+    """(A, B): 4-column and 3-column groups the hits kernel uses for a block of longest motif L."""
+    a, b = _i32(0), _i32(0)
+    _check(load().tfbs_debug_hits_group_plan(int(L), C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def device_count() -> int:

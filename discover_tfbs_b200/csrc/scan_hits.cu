@@ -424,7 +424,9 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
             TFBS_CASE(4, 1) TFBS_CASE(4, 2) TFBS_CASE(4, 3) TFBS_CASE(4, 4) TFBS_CASE(4, 5) TFBS_CASE(5, 0)
             TFBS_CASE(5, 1) TFBS_CASE(5, 2) TFBS_CASE(5, 3) TFBS_CASE(5, 4) TFBS_CASE(6, 0)
 #undef TFBS_CASE
-            default: break;
+            default:  // no instantiation for this grouping: report it instead of silently skipping
+                if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)AB));
+                break;
         }
         drain_queue(C);
         __syncthreads();  // tile buffers and S.item are reused by the next item
@@ -680,7 +682,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.hits = (tfbs_hit *)ctx->hits.ptr;
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
-    P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 16);
+    P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 24);
     TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFFFFF0ll, "tfbs_scan_hits: too many work items");
     TFBS_REQUIRE((P.n_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits: sequence padding too small");
 
@@ -694,9 +696,11 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     tfbs_launched(ctx);
     rc = tfbs_end(ctx);
     if (rc) return rc;
-    unsigned long long cnt2[2] = {0, 0};
+    unsigned long long cnt2[3] = {0, 0, 0};
     TFBS_CHECK_CUDA(cudaMemcpyAsync(cnt2, ctx->hit_count.ptr, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream));
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    TFBS_REQUIRE(cnt2[2] == 0, "tfbs_scan_hits: no kernel instantiation for column grouping A=%u B=%u",
+                 (unsigned)((cnt2[2] >> 8) & 255), (unsigned)(cnt2[2] & 255));
     const unsigned long long cnt = cnt2[0];
     *n_hits = (int64_t)cnt;
     ctx->last_candidates = (int64_t)cnt2[1];
@@ -802,7 +806,7 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
         tfbs_encode_range(ctx, (char *)seq->staging + b0, b1 - b0, seq, b0, cover, ctx->stream);
         P.tile0 = t0;
         P.n_tiles = t1 - t0;
-        P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 16);
+        P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 24);
         TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 4, ctx->stream));
         const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
         scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
@@ -828,6 +832,12 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     rc = tfbs_end(ctx);
     if (rc) return rc;
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream_out));
+    {
+        unsigned long long flag = 0;
+        TFBS_CHECK_CUDA(cudaMemcpy(&flag, (char *)ctx->hit_count.ptr + 16, sizeof(flag), cudaMemcpyDeviceToHost));
+        TFBS_REQUIRE(flag == 0, "tfbs_scan_hits_host: no kernel instantiation for column grouping A=%u B=%u",
+                     (unsigned)((flag >> 8) & 255), (unsigned)(flag & 255));
+    }
     const unsigned long long cnt = ctx->pinned_counts[C - 1];
     *n_hits = (int64_t)cnt;
     if (sorted && done > 0) std::sort(out_host, out_host + done, HitLess());
@@ -835,5 +845,18 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
         tfbs_set_error("tfbs_scan_hits_host: %llu hits exceed capacity %lld", cnt, (long long)cap);
         return TFBS_ERR_OVERFLOW;
     }
+    return TFBS_OK;
+}
+
+
+// Test hook (host only): the column grouping the hits kernel uses for a block whose longest motif
+// has L columns.
+extern "C" int tfbs_debug_hits_group_plan(int32_t L, int32_t *A, int32_t *B)
+{
+    if (!A || !B || L < 1 || L > TFBS_MAX_MOTIF_LEN) return TFBS_ERR_INVALID;
+    int a = 0, b = 0;
+    tfbs_hits_group_plan(L, &a, &b);
+    *A = a;
+    *B = b;
     return TFBS_OK;
 }

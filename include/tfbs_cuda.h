@@ -205,6 +205,9 @@ int tfbs_similarity_sums(tfbs_ctx *ctx, const uint32_t *c_words, const uint16_t 
  * The encode kernel converts 4 ASCII bytes per 32-bit word with integer bit tricks; this runs
  * the same inline function on the host so the CPU test-suite can check it exhaustively. */
 int tfbs_debug_swar4(uint32_t four_ascii_bytes, uint32_t *codes8, uint32_t *valid4);
+/* Column grouping of the hits kernel for a motif block of maximum length L: A groups of 4 columns
+ * + B groups of 3 (the kernel is instantiated for every pair this can return for L = 1..32). */
+int tfbs_debug_hits_group_plan(int32_t L, int32_t *A, int32_t *B);
 
 #ifdef __cplusplus
 }

@@ -168,3 +168,15 @@ def test_parse_fasta_and_locations(tmp_path):
 def test_tokens_to_values_rule():
     v = U._tokens_to_values(["NA", "5.12", "", "-3.40", "x"])
     assert v.tolist() == [0.0, 5.12, 0.0, -3.4, 0.0]
+
+
+def test_hits_group_plan_is_covered_by_kernel_instantiations():
+    """Every (A, B) the planner can return for L = 1..32 must have a scan_segment<A, B> case."""
+    src = open(os.path.join(ROOT, "discover_tfbs_b200", "csrc", "scan_hits.cu")).read()
+    cases = {(int(a), int(b)) for a, b in re.findall(r"TFBS_CASE\((\d+), (\d+)\)", src)}
+    for L in range(1, 33):
+        a, b = _lib.hits_group_plan(L)
+        assert 4 * a + 3 * b >= L and 32 * a + 8 * b <= 192 and (a, b) in cases, (L, a, b)
+        # optimal: no admissible grouping with fewer loads
+        assert all(not (4 * x + 3 * y >= L and 32 * x + 8 * y <= 192 and 1 <= x + y < a + b)
+                   for x in range(7) for y in range(12))
