@@ -51,29 +51,29 @@ shape_tracks_kernel(const TrackParams P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
+    // raw words of the current sub-tile, fetched one iteration ahead (hides the L2 latency)
+    uint32_t ra0 = 0, ra1 = 0, rm0 = 0xFFFFFFFFu, rm1 = 0xFFFFFFFFu;
+    auto fetch = [&](int64_t sub) {
+        const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
+        ra0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
+        ra1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
+        rm0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
+        rm1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+    };
+    if ((int64_t)blockIdx.x < n_sub) fetch(blockIdx.x);
     for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
-        // 32-base register window starting at base b0 = p0 - 4 (a multiple of 4, may be -4):
+        // 16-base register window starting at base b0 = p0 - 4 (a multiple of 4, may be -4):
         // pentamer centred at p0 + d starts at window base d + 2
         const int64_t b0 = p0 - 4;
-        uint32_t wlo, whi, inv;
-        {
-            const int64_t wi = b0 >> 4;
-            const int sh = (int)(b0 & 15) * 2;
-            const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
-            const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
-            wlo = __funnelshift_r(a0, a1, sh);
-            whi = a1 >> sh;  // only bits below 2*12 + 10 of the window are used (sh <= 24)
-            const int64_t mi = b0 >> 5;
-            const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
-            const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
-            inv = __funnelshift_r(m0, m1, (int)(b0 & 31));
-        }
+        const uint32_t wlo = __funnelshift_r(ra0, ra1, (int)(b0 & 15) * 2);
+        const uint32_t inv = __funnelshift_r(rm0, rm1, (int)(b0 & 31));
+        if (sub + gridDim.x < n_sub) fetch(sub + gridDim.x);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
         for (int d = 0; d <= kShapePosPerThread; d++) {
-            pent[d] = __funnelshift_r(wlo, whi, 2 * (d + 2)) & 1023u;
+            pent[d] = (wlo >> (2 * (d + 2))) & 1023u;
             ok[d] = ((inv >> (d + 2)) & 31u) == 0u;
         }
         for (int t = 0; t < P.T; t++) {
@@ -106,7 +106,7 @@ shape_tracks_kernel(const TrackParams P)
 // 32-bit word: (track A | track B) for per-nucleotide tracks, (Y1 | Y2) for a per-step track.  That
 // halves the data-dependent LDS.32 per position — the bank conflicts of those loads are what
 // saturates the l1tex data pipe in the fp32-table kernel (71 % of its shared-memory wavefronts,
-// profiles/r01/ncu_full_final_100Mb_raw.csv).  The reconstruction (centi_to_float) is verified
+// profiles/r01/ncu_full_final_100Mb_raw.csv).  The reconstruction (centi_from_biased) is verified
 // against every table entry at upload.
 struct Packed16Params {
     const uint32_t *packed;
@@ -120,24 +120,21 @@ struct Packed16Params {
     float *out;
 };
 
-// c / 100 correctly rounded to float with full-rate fp32 ops only (int->float and float<->double
-// conversions run on the quarter-rate pipe): magic-number int->float, then a double-float product
-// with 0.01 = r_hi + r_lo.  The host runs the same sequence for every table entry at upload and
-// only enables this kernel if it reproduces the table bit for bit.
-__host__ __device__ __forceinline__ float centi_to_float(int c)
+// c / 100 correctly rounded to float with 4 full-rate ops (int->float and float<->double
+// conversions run on the quarter-rate pipe).  The table stores the biased value h = c + 32768 in 16
+// bits; OR-ing it under the exponent of 2^23 gives the float 2^23 + h exactly, one subtraction gives
+// c, and c * 0.01 is formed as fma(c, r_hi, c * r_lo) with 0.01 = r_hi + r_lo.  The host runs the same
+// sequence for every table entry at upload and only enables this kernel if it reproduces the table
+// bit for bit.
+__host__ __device__ __forceinline__ float centi_from_biased(uint32_t h)  // h in [0, 65535]
 {
+    const float r_hi = 0.01f, r_lo = 2.2351741811588166e-10f;  // 0.01 - (double)0.01f
 #ifdef __CUDA_ARCH__
-    const float cf = __int_as_float(0x4B400000 + c) - 12582912.0f;  // exact for |c| < 2^22
-    const float r_hi = 0.01f, r_lo = 2.2351741291171123e-10f;       // 0.01 - (double)0.01f
-    const float p_hi = __fmul_rn(cf, r_hi);
-    const float p_lo = __fmaf_rn(cf, r_hi, -p_hi);
-    return __fadd_rn(p_hi, __fmaf_rn(cf, r_lo, p_lo));
+    const float cf = __uint_as_float(0x4B000000u | h) - 8421376.0f;  // (2^23 + h) - (2^23 + 32768)
+    return __fmaf_rn(cf, r_hi, __fmul_rn(cf, r_lo));
 #else
-    const float cf = (float)c;
-    const float r_hi = 0.01f, r_lo = 2.2351741291171123e-10f;
-    const float p_hi = cf * r_hi;
-    const float p_lo = fmaf(cf, r_hi, -p_hi);
-    return p_hi + fmaf(cf, r_lo, p_lo);
+    const float cf = (float)((int)h - 32768);
+    return fmaf(cf, r_hi, cf * r_lo);
 #endif
 }
 
@@ -154,21 +151,22 @@ shape_tracks_c16_kernel(const Packed16Params P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
+    // raw words of the current sub-tile, fetched one iteration ahead (hides the L2 latency)
+    uint32_t ra0 = 0, ra1 = 0, rm0 = 0xFFFFFFFFu, rm1 = 0xFFFFFFFFu;
+    auto fetch = [&](int64_t sub) {
+        const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
+        ra0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
+        ra1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
+        rm0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
+        rm1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+    };
+    if ((int64_t)blockIdx.x < n_sub) fetch(blockIdx.x);
     for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
         const int64_t b0 = p0 - 4;
-        uint32_t wlo, inv;
-        {
-            const int64_t wi = b0 >> 4;
-            const int sh = (int)(b0 & 15) * 2;
-            const uint32_t a0 = ld_words_guard(P.packed, wi, P.n_words, 0u);
-            const uint32_t a1 = ld_words_guard(P.packed, wi + 1, P.n_words, 0u);
-            wlo = __funnelshift_r(a0, a1, sh);
-            const int64_t mi = b0 >> 5;
-            const uint32_t m0 = ld_words_guard(P.mask, mi, P.n_mask, 0xFFFFFFFFu);
-            const uint32_t m1 = ld_words_guard(P.mask, mi + 1, P.n_mask, 0xFFFFFFFFu);
-            inv = __funnelshift_r(m0, m1, (int)(b0 & 31));
-        }
+        const uint32_t wlo = __funnelshift_r(ra0, ra1, (int)(b0 & 15) * 2);
+        const uint32_t inv = __funnelshift_r(rm0, rm1, (int)(b0 & 31));
+        if (sub + gridDim.x < n_sub) fetch(sub + gridDim.x);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
@@ -185,8 +183,8 @@ shape_tracks_c16_kernel(const Packed16Params P)
                 float va[kShapePosPerThread], vb[kShapePosPerThread];
 #pragma unroll
                 for (int d = 0; d < kShapePosPerThread; d++) {
-                    va[d] = ok[d] ? centi_to_float((int)(short)(u[d] & 0xFFFFu)) : qnan;
-                    vb[d] = ok[d] ? centi_to_float((int)(short)(u[d] >> 16)) : qnan;
+                    va[d] = ok[d] ? centi_from_biased(u[d] & 0xFFFFu) : qnan;
+                    vb[d] = ok[d] ? centi_from_biased(u[d] >> 16) : qnan;
                 }
                 __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(va[0], va[1], va[2], va[3]));
                 if (P.row_b[w] >= 0)
@@ -198,8 +196,8 @@ shape_tracks_c16_kernel(const Packed16Params P)
                 float v[kShapePosPerThread];
 #pragma unroll
                 for (int d = 0; d < kShapePosPerThread; d++) {
-                    const float y2 = centi_to_float((int)(short)(u[d] >> 16));
-                    const float y1 = centi_to_float((int)(short)(u[d + 1] & 0xFFFFu));
+                    const float y2 = centi_from_biased(u[d] >> 16);
+                    const float y1 = centi_from_biased(u[d + 1] & 0xFFFFu);
                     v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2, y1), 0.5f) : qnan;
                 }
                 __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
@@ -388,13 +386,13 @@ int tfbs_shapes_upload(tfbs_ctx *ctx, const float *tables, const int32_t *kinds,
         for (size_t i = 0; i < le.size() && centi; i++) {
             const long c = lrintf(le[i] * 100.0f);
             cv[i] = (int32_t)c;
-            if (c < -32767 || c > 32767 || centi_to_float((int)c) != le[i]) centi = false;
+            if (c < -32767 || c > 32767 || centi_from_biased((uint32_t)(c + 32768)) != le[i]) centi = false;
         }
         if (centi) {
             std::vector<int> pern, step;
             for (int t = 0; t < T; t++) (kinds[t] == TFBS_SHAPE_PER_NUCLEOTIDE ? pern : step).push_back(t);
             std::vector<uint32_t> words;
-            auto plane = [&](int t, int pl, int x) { return (uint32_t)(cv[((size_t)t * 2 + pl) * 1024 + x] & 0xFFFF); };
+            auto plane = [&](int t, int pl, int x) { return (uint32_t)(cv[((size_t)t * 2 + pl) * 1024 + x] + 32768) & 0xFFFFu; };
             for (size_t i = 0; i < pern.size(); i += 2) {
                 const int a = pern[i], b = i + 1 < pern.size() ? pern[i + 1] : -1;
                 s->c16_kind.push_back(0);
