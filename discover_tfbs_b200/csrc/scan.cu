@@ -19,8 +19,8 @@
 namespace {
 
 constexpr int kScanThreads = 1024;                   // one persistent CTA per SM
-constexpr int kPosPerThread = 8;
-constexpr int kTile = kScanThreads * kPosPerThread;  // 8192 window starts per sub-tile
+constexpr int kPosPerThread = 4;
+constexpr int kTile = kScanThreads * kPosPerThread;  // 4096 window starts per sub-tile
 constexpr int kMaxGroups = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 
 struct ScanParams {
@@ -43,8 +43,9 @@ struct ScanParams {
 // window instead of 7.  The table is 32 KB aligned so a lookup address is
 // base | (kmer << 7) | ((lane & 15) << 3)  (one shift + one LOP3), the group offset is an
 // immediate (K, G are template parameters) and both strands are accumulated with one packed
-// add.rn.f32x2.  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 8
-// consecutive starts from a 48-base register window and writes 32 B per strand (streaming stores).
+// add.rn.f32x2.  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 4
+// consecutive starts from a 48-base register window and writes 16 B per strand (streaming stores,
+// 512 contiguous bytes per warp).
 __device__ __forceinline__ uint64_t lds64(uint32_t addr)
 {
     uint64_t v;
@@ -83,7 +84,7 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
     if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
-        // 48-base register window starting at p0 (p0 is a multiple of 8)
+        // 48-base register window starting at p0 (p0 is a multiple of 4)
         uint32_t w0, w1, w2, inv_lo, inv_hi;
         {
             const int sh = (int)(p0 & 15) * 2;
@@ -119,12 +120,10 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
             af[p] = __uint_as_float((uint32_t)a);
             ar[p] = __uint_as_float((uint32_t)(a >> 32));
         }
-        float4 *of = reinterpret_cast<float4 *>(row_f + p0);
-        float4 *orv = reinterpret_cast<float4 *>(row_r + p0);
-        __stcs(of, make_float4(af[0], af[1], af[2], af[3]));
-        __stcs(of + 1, make_float4(af[4], af[5], af[6], af[7]));
-        __stcs(orv, make_float4(ar[0], ar[1], ar[2], ar[3]));
-        __stcs(orv + 1, make_float4(ar[4], ar[5], ar[6], ar[7]));
+        // one fully contiguous 512 B store per warp and strand (a stride-32 B pattern writes half
+        // sectors: twice the L1->XBAR sector traffic and store wavefronts, ncu r01)
+        __stcs(reinterpret_cast<float4 *>(row_f + p0), make_float4(af[0], af[1], af[2], af[3]));
+        __stcs(reinterpret_cast<float4 *>(row_r + p0), make_float4(ar[0], ar[1], ar[2], ar[3]));
     }
 }
 
