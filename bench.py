@@ -79,7 +79,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc = index, [], None  # lines: (arrival time, text)
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -91,14 +92,28 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def stop(self):
+        """Summary of the samples that arrived inside [mark_begin, mark_end] (the timed regions);
+        nvidia-smi needs ~1 s to start on an 8-GPU box, so it is launched before the warm-up and,
+        if the timed window is shorter than the sampling period, the warm-up samples are used."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
+        inside = [ln for t, ln in self.lines if self.t_begin is not None and self.t_begin <= t <= (self.t_end or 1e30) + 0.1]
+        window = "timed region"
+        if len(inside) < 2:
+            inside, window = [ln for _, ln in self.lines], "warm-up + timed region"
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -111,7 +126,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peak_gbs():
@@ -302,12 +317,13 @@ def run_ours(args):
         return ctx.scan_hits_host(pinned_in.array, enc, lib, thr, hits_out[:cap], chunks=8)
 
     # ---- resident (value) ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         ctx.flush_l2()
         step_resident()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.total_kernel_launches()
     step_ms, scan_ms, enc_ms, shape_ms = [], [], [], []
     for _ in range(args.steps):
@@ -325,7 +341,6 @@ def run_ours(args):
         del launches_flush
     launches = ctx.total_kernel_launches() - launches0
     barrier()
-    clocks = sampler.stop()
     t_resident = float(np.sum(step_ms)) / 1e3
 
     # ---- end to end --------------------------------------------------------------------------------
@@ -339,6 +354,8 @@ def run_ours(args):
         got = step_e2e()
         e2e_ms.append(ctx.timer_stop())
     barrier()
+    sampler.mark_end()
+    clocks = sampler.stop()
     t_e2e = float(np.sum(e2e_ms)) / 1e3
     d2h = int(got.size) * 16 + 8
     h2d = int(n_scan) + 8 * len(lens)

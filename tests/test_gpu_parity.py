@@ -507,3 +507,38 @@ def test_pipelined_host_scan_equals_plain_scan(ctx, n, chunks):
     for h in (enc, scratch, lib):
         h.close()
     pin.close()
+
+
+def test_example_genome_to_feature_table(ctx, tmp_path):
+    """examples/predict_features.py: genome -> exact-match candidates -> feature table whose shape
+    columns equal the oracle's tracks sliced the reference's way."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "predict_features", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "predict_features.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(31)
+    genome = {"chr1": "".join(rng.choice(list("ACGT"), size=60_000)), "chr2": "".join(rng.choice(list("ACGT"), size=25_000))}
+    motif = genome["chr1"][500:512]
+    gpath, fpath = tmp_path / "g.fasta", tmp_path / "fg.fasta"
+    gpath.write_text("".join(f">{k}\n{v}\n" for k, v in genome.items()))
+    fg = [(f"chr1:{s}-{s + 12}(+)", genome["chr1"][s:s + 12]) for s in (500, 2000, 9000)]
+    fpath.write_text("".join(f">{n}\n{s}\n" for n, s in fg))
+    tables, kinds = dnashape.synthetic_tables()
+    cands, table = mod.run(str(gpath), str(fpath), [motif, "TGACTCA", "CANNTG"], str(tmp_path / "pred"), tables, kinds, ctx)
+    assert len(cands) == table.shape[0] > 50
+    assert list(table.columns[:6]) == ["location", "sequence", "GC_content", "MinHash", "PAS", "PPS"]
+    assert any(c["chrom"] == "chr1" and c["start"] == 500 and c["strand"] == "+" for c in cands)
+    # shape columns of a few rows vs the oracle (reference slicing: L+1 values, reversed on '-')
+    tr = {k: so.tracks(v, tables, kinds) for k, v in genome.items()}
+    for i in rng.integers(0, table.shape[0], size=25):
+        chrom, s, e, sd = U.parse_locations([table["location"][i]])
+        for t, shape in enumerate(dnashape.SHAPES):
+            ntok = len(genome[chrom[0]]) - (1 if kinds[t] else 0)
+            idx = np.arange(s[0], e[0] + 1) if sd[0] > 0 else np.arange(e[0], s[0] - 1, -1)
+            idx = idx[idx <= ntok]
+            want = [0.0 if (j == ntok or np.isnan(tr[chrom[0]][t, j])) else float("%.2f" % tr[chrom[0]][t, j]) for j in idx]
+            got = [table[f"{shape}_{w + 1:02d}"][i] for w in range(len(want))]
+            assert got == want, (table["location"][i], shape)
