@@ -1,0 +1,1 @@
+"""Stub package (test infrastructure; see oracle/stubs/README.md)."""
