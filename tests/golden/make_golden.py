@@ -191,6 +191,34 @@ def main():
                               "shapes_data_df": pack(ns["shapes_data_df"]),
                               "negative_data_df": pack(ns["negative_data_df"])}
 
+    # ---- legacy BED-driven API get_shape_data (utils.py:554-602; no caller in the reference) ------
+    with tempfile.TemporaryDirectory() as tmp:
+        shapefiles = []
+        for shape in SHAPES:
+            path = os.path.join(tmp, f"genome_oneline.fasta.{shape}")
+            with open(path, "w") as fh:
+                for chrom in genome:
+                    fh.write(f">{chrom}\n" + ",".join(shape_tokens[shape][chrom]) + "\n")  # tokens end with ''
+            shapefiles.append(path)
+        bed_rows = []
+        for chrom, seq in genome.items():
+            n = len(seq)
+            for _ in range(6):
+                L = int(rng.integers(6, 21))
+                s0 = int(rng.integers(1, n - L - 1))
+                bed_rows.append((chrom, s0, s0 + L, "site", "1.0", "+" if rng.random() < 0.5 else "-"))
+            bed_rows.append((chrom, n - 10, n, "edge", "1.0", "+"))
+            bed_rows.append((chrom, 1, 13, "edge", "1.0", "-"))
+        bed_path = os.path.join(tmp, "sites.bed")
+        with open(bed_path, "w") as fh:
+            for r in bed_rows:
+                fh.write("\t".join(str(x) for x in r) + "\n")
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            gsd = ref.get_shape_data(bed_path, shapefiles)
+        gold["get_shape_data"] = {"bed": [list(r) for r in bed_rows], "out": gsd}
+
     out = os.path.join(HERE, "reference_golden.json")
     with open(out, "w") as fh:
         json.dump(gold, fh, indent=0, separators=(",", ":"))

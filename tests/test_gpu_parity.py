@@ -542,3 +542,18 @@ def test_example_genome_to_feature_table(ctx, tmp_path):
             want = [0.0 if (j == ntok or np.isnan(tr[chrom[0]][t, j])) else float("%.2f" % tr[chrom[0]][t, j]) for j in idx]
             got = [table[f"{shape}_{w + 1:02d}"][i] for w in range(len(want))]
             assert got == want, (table["location"][i], shape)
+
+
+def test_legacy_get_shape_data_vs_reference_golden(ctx, golden, tmp_path):
+    """utils.get_shape_data (BED-driven legacy API, utils.py:554-602): keys '{shape}_pos_{i}', index 0
+    of every slice skipped, values equal to the reference's."""
+    gs = golden["get_shape_data"]
+    files = []
+    for shape in golden["meta"]["shapes"]:
+        path = tmp_path / f"genome_oneline.fasta.{shape}"
+        path.write_text("".join(f">{c}\n" + ",".join(golden["shape_tokens"][shape][c]) + "\n" for c in golden["genome"]))
+        files.append(str(path))
+    bed = tmp_path / "sites.bed"
+    bed.write_text("".join("\t".join(str(x) for x in r) + "\n" for r in gs["bed"]))
+    got = U.get_shape_data(str(bed), files)
+    assert got == gs["out"]
