@@ -557,3 +557,46 @@ def test_legacy_get_shape_data_vs_reference_golden(ctx, golden, tmp_path):
     bed.write_text("".join("\t".join(str(x) for x in r) + "\n" for r in gs["bed"]))
     got = U.get_shape_data(str(bed), files)
     assert got == gs["out"]
+
+
+@pytest.mark.parametrize("from_sequence", [False, True])
+def test_build_features_driver_vs_reference_golden(ctx, golden, tmp_path, from_sequence):
+    """discover_tfbs_b200.build_features.main with the reference's command line: the feather it writes
+    equals what build_features.py:200-261 yields from the reference's own tables (goldens), both with
+    the ten DNAshapeR text files and with --genome-fasta (shapes from sequence on the GPU)."""
+    from discover_tfbs_b200 import build_features as bf
+
+    ft, bg = golden["feature_table"], golden["background"]
+    shapes = golden["meta"]["shapes"]
+    (tmp_path / "fg.fasta").write_text("".join(f">{n}\n{s}\n" for n, s in ft["fg"]))
+    (tmp_path / "fg.bed").write_text("")
+    (tmp_path / "bkg.fasta").write_text("".join(f">{n}\n{s}\n" for n, s in bg["records"]))
+    (tmp_path / "genome.fasta").write_text("".join(f">{c}\n{s}\n" for c, s in golden["genome"].items()))
+    bkg_files, gw_files = [], []
+    for shape in shapes:
+        p = tmp_path / f"bkg.fasta.{shape}"
+        p.write_text(bg["shape_file_text"][shape])
+        bkg_files.append(str(p))
+        q = tmp_path / f"genome_oneline.fasta.{shape}"
+        q.write_text("".join(f">{c}\n" + ",".join(golden["shape_tokens"][shape][c]) + "\n" for c in golden["genome"]))
+        gw_files.append(str(q))
+    out = tmp_path / "train.feather"
+    argv = ["tec1", str(tmp_path / "fg.fasta"), str(tmp_path / "fg.bed"), str(tmp_path / "bkg.fasta"), *bkg_files,
+            *gw_files, str(out), str(tmp_path / "pca.pdf")]
+    if from_sequence:
+        argv += ["--genome-fasta", str(tmp_path / "genome.fasta")]
+    bf.main(argv)
+    got = pd.read_feather(out)
+    pos = pd.DataFrame(ft["fg_table"]["rows"], columns=ft["fg_table"]["columns"])
+    pos.insert(1, "seq_type", "True")
+    neg = pd.DataFrame(bg["negative_data_df"]["rows"], columns=bg["negative_data_df"]["columns"])
+    if "seq_type" not in neg.columns:
+        neg.insert(1, "seq_type", "Not_True")
+    want = pd.concat([pos, neg], sort=False).dropna(axis=1).reset_index()
+    assert list(got.columns) == list(want.columns)
+    for col in got.columns:
+        if col in ("location", "sequence", "seq_type"):
+            assert list(got[col]) == list(want[col]), col
+        else:
+            a, b = got[col].to_numpy(dtype=np.float64), want[col].astype(float).to_numpy()
+            assert np.max(np.abs(a - b)) <= (1e-12 if col in ("MinHash", "PAS", "PPS") else 0.0), col
