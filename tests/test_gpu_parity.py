@@ -600,3 +600,39 @@ def test_build_features_driver_vs_reference_golden(ctx, golden, tmp_path, from_s
         else:
             a, b = got[col].to_numpy(dtype=np.float64), want[col].astype(float).to_numpy()
             assert np.max(np.abs(a - b)) <= (1e-12 if col in ("MinHash", "PAS", "PPS") else 0.0), col
+
+
+def test_error_conventions(ctx):
+    """Every failure is an int status + message (RuntimeError in Python); nothing aborts the process."""
+    good = np.zeros((1, 8, 4))
+    with pytest.raises(RuntimeError, match="NaN"):
+        bad = good.copy()
+        bad[0, 3, 1] = np.nan
+        ctx.upload_pwms(bad)
+    with pytest.raises(RuntimeError, match=r"\+inf|NaN"):
+        bad = good.copy()
+        bad[0, 0, 0] = np.inf
+        ctx.upload_pwms(bad)
+    with pytest.raises(RuntimeError, match="Lmax"):
+        ctx.upload_pwms(np.zeros((1, 40, 4)))
+    with pytest.raises(RuntimeError, match="length"):
+        ctx.upload_pwms(np.zeros((2, 8, 4)), lens=[8, 0])
+    with pytest.raises(RuntimeError, match="kinds"):
+        ctx.upload_shapes(np.zeros((1, 2, 1024), np.float32), [7])
+    enc = ctx.encode(b"ACGTACGTAC")
+    with pytest.raises(RuntimeError, match="out of range"):
+        enc.gc_counts([5], [50])
+    tables, kinds = dnashape.synthetic_tables()
+    tab = ctx.upload_shapes(tables, kinds)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ctx.shape_tracks(enc, tab, [0], [999])
+    other = _lib.Context(0)
+    lib_other = other.upload_pwms(good)
+    with pytest.raises(RuntimeError, match="another context"):
+        ctx.scan_dense(enc, lib_other)
+    lib_other.close()
+    other.close()
+    # the context is still usable after every error
+    assert enc.gc_counts([0], [10])[0] == 5
+    enc.close()
+    tab.close()
