@@ -636,3 +636,33 @@ def test_error_conventions(ctx):
     assert enc.gc_counts([0], [10])[0] == 5
     enc.close()
     tab.close()
+
+
+def test_hits_fuzz_against_oracle(ctx):
+    """40 random (length, library, threshold) configurations, bit-exact against the oracle: covers
+    segment/tile edges (multiples of 2016 / 32 256), every column grouping, N-runs and floods."""
+    rng = np.random.default_rng(2024)
+    sizes = [1, 31, 2015, 2016, 2017, 32_255, 32_256, 32_257, 64_513]
+    for case in range(40):
+        n = int(sizes[case]) if case < len(sizes) else int(rng.integers(1, 70_000))
+        M = int(rng.integers(1, 70))
+        lmax = int(rng.integers(1, 33))
+        lmin = int(rng.integers(1, lmax + 1))
+        logodds, lens = synth.pwm_library(1000 + case, M, lmin=lmin, lmax=lmax, alpha=float(rng.choice([0.1, 0.3, 1.0])))
+        if case % 5 == 0:
+            logodds = np.where(rng.random(logodds.shape) < 0.03, -np.inf, logodds)
+        rate = float(rng.choice([3e-2, 1e-2, 1e-3]))
+        thr = synth.thresholds_for_rate(np.where(np.isinf(logodds), -20.0, logodds), lens, rate=rate, sample=4000,
+                                        seed=case)
+        seq = _noisy_seq(rng, n) if case % 2 else synth.genome(case, int(rng.integers(0, 10**9)), n)
+        enc = ctx.encode(seq)
+        lib = ctx.upload_pwms(logodds, lens)
+        hits = ctx.scan_hits(enc, lib, thr, cap=1 << 16, sort=True)
+        with np.errstate(invalid="ignore"):
+            pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+        gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+        ok = (hits.size == cnt and np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
+              and np.array_equal((hits["pos"] < 0).astype(np.int32), strand) and np.array_equal(hits["score"], score))
+        assert ok, (case, n, M, lmin, lmax, rate, hits.size, cnt)
+        enc.close()
+        lib.close()
