@@ -71,31 +71,39 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
     float *row_r = P.out_rev + (size_t)m * P.pitch;
     const uint64_t qnan2 = 0x7FC000007FC00000ull;
 
-    // raw words of the current tile (prefetched one tile ahead so the L2 latency of the next
-    // window overlaps the shared-memory work of this one)
-    uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0, rm0 = 0, rm1 = 0, rm2 = 0;
+    // raw words of the current tile and of the next two (prefetch distance 2: one round of the 32
+    // resident warps is shorter than an HBM round trip, ncu showed long-scoreboard stalls at
+    // distance 1).  3 packed words (96 bases from a 16-base boundary) and 2 mask words cover the
+    // 4 + 32 bases a thread can touch.
+    struct Raw { uint32_t a0, a1, a2, m0, m1; };
     auto fetch = [&](int64_t tile) {
+        Raw r;
         const int64_t q0 = tile * kTile + (int64_t)tid * kPosPerThread;
         const uint32_t *wp = P.packed + (q0 >> 4);
-        ra0 = __ldg(wp); ra1 = __ldg(wp + 1); ra2 = __ldg(wp + 2); ra3 = __ldg(wp + 3);
+        r.a0 = __ldg(wp); r.a1 = __ldg(wp + 1); r.a2 = __ldg(wp + 2);
         const uint32_t *mp = P.mask + (q0 >> 5);
-        rm0 = __ldg(mp); rm1 = __ldg(mp + 1); rm2 = __ldg(mp + 2);
+        r.m0 = __ldg(mp); r.m1 = __ldg(mp + 1);
+        return r;
     };
-    if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    Raw cur = {0, 0, 0, 0, 0}, nxt = cur;
+    if ((int64_t)blockIdx.x < n_tiles) cur = fetch(blockIdx.x);
+    if ((int64_t)blockIdx.x + stride < n_tiles) nxt = fetch(blockIdx.x + stride);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += stride) {
         const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
         // 48-base register window starting at p0 (p0 is a multiple of 4)
         uint32_t w0, w1, w2, inv_lo, inv_hi;
         {
             const int sh = (int)(p0 & 15) * 2;
-            w0 = __funnelshift_r(ra0, ra1, sh);
-            w1 = __funnelshift_r(ra1, ra2, sh);
-            w2 = __funnelshift_r(ra2, ra3, sh);
+            w0 = __funnelshift_r(cur.a0, cur.a1, sh);
+            w1 = __funnelshift_r(cur.a1, cur.a2, sh);
+            w2 = cur.a2 >> sh;
             const int msh = (int)(p0 & 31);
-            inv_lo = __funnelshift_r(rm0, rm1, msh);
-            inv_hi = __funnelshift_r(rm1, rm2, msh);
+            inv_lo = __funnelshift_r(cur.m0, cur.m1, msh);
+            inv_hi = cur.m1 >> msh;
         }
-        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        cur = nxt;
+        if (tile + 2 * stride < n_tiles) nxt = fetch(tile + 2 * stride);
         uint64_t acc[kPosPerThread];
 #pragma unroll
         for (int g = 0; g < G; g++) {
