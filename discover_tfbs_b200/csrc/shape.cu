@@ -51,24 +51,31 @@ shape_tracks_kernel(const TrackParams P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
-    // raw words of the current sub-tile, fetched one iteration ahead (hides the L2 latency)
-    uint32_t ra0 = 0, ra1 = 0, rm0 = 0xFFFFFFFFu, rm1 = 0xFFFFFFFFu;
+    // raw words of the current sub-tile and of the next two (prefetch distance 2 hides the HBM
+    // round trip behind two rounds of the resident warps)
+    struct Raw { uint32_t a0, a1, m0, m1; };
     auto fetch = [&](int64_t sub) {
+        Raw r;
         const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
-        ra0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
-        ra1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
-        rm0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
-        rm1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        r.a0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
+        r.a1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
+        r.m0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
+        r.m1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        return r;
     };
-    if ((int64_t)blockIdx.x < n_sub) fetch(blockIdx.x);
-    for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    Raw cur = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu}, nxt = cur;
+    if ((int64_t)blockIdx.x < n_sub) cur = fetch(blockIdx.x);
+    if ((int64_t)blockIdx.x + stride < n_sub) nxt = fetch(blockIdx.x + stride);
+    for (int64_t sub = blockIdx.x; sub < n_sub; sub += stride) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
         // 16-base register window starting at base b0 = p0 - 4 (a multiple of 4, may be -4):
         // pentamer centred at p0 + d starts at window base d + 2
         const int64_t b0 = p0 - 4;
-        const uint32_t wlo = __funnelshift_r(ra0, ra1, (int)(b0 & 15) * 2);
-        const uint32_t inv = __funnelshift_r(rm0, rm1, (int)(b0 & 31));
-        if (sub + gridDim.x < n_sub) fetch(sub + gridDim.x);
+        const uint32_t wlo = __funnelshift_r(cur.a0, cur.a1, (int)(b0 & 15) * 2);
+        const uint32_t inv = __funnelshift_r(cur.m0, cur.m1, (int)(b0 & 31));
+        cur = nxt;
+        if (sub + 2 * stride < n_sub) nxt = fetch(sub + 2 * stride);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
@@ -151,22 +158,29 @@ shape_tracks_c16_kernel(const Packed16Params P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
-    // raw words of the current sub-tile, fetched one iteration ahead (hides the L2 latency)
-    uint32_t ra0 = 0, ra1 = 0, rm0 = 0xFFFFFFFFu, rm1 = 0xFFFFFFFFu;
+    // raw words of the current sub-tile and of the next two (prefetch distance 2 hides the HBM
+    // round trip behind two rounds of the resident warps)
+    struct Raw { uint32_t a0, a1, m0, m1; };
     auto fetch = [&](int64_t sub) {
+        Raw r;
         const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
-        ra0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
-        ra1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
-        rm0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
-        rm1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        r.a0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
+        r.a1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
+        r.m0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
+        r.m1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        return r;
     };
-    if ((int64_t)blockIdx.x < n_sub) fetch(blockIdx.x);
-    for (int64_t sub = blockIdx.x; sub < n_sub; sub += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    Raw cur = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu}, nxt = cur;
+    if ((int64_t)blockIdx.x < n_sub) cur = fetch(blockIdx.x);
+    if ((int64_t)blockIdx.x + stride < n_sub) nxt = fetch(blockIdx.x + stride);
+    for (int64_t sub = blockIdx.x; sub < n_sub; sub += stride) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
         const int64_t b0 = p0 - 4;
-        const uint32_t wlo = __funnelshift_r(ra0, ra1, (int)(b0 & 15) * 2);
-        const uint32_t inv = __funnelshift_r(rm0, rm1, (int)(b0 & 31));
-        if (sub + gridDim.x < n_sub) fetch(sub + gridDim.x);
+        const uint32_t wlo = __funnelshift_r(cur.a0, cur.a1, (int)(b0 & 15) * 2);
+        const uint32_t inv = __funnelshift_r(cur.m0, cur.m1, (int)(b0 & 31));
+        cur = nxt;
+        if (sub + 2 * stride < n_sub) nxt = fetch(sub + 2 * stride);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
