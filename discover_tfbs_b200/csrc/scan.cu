@@ -71,9 +71,8 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
     float *row_r = P.out_rev + (size_t)m * P.pitch;
     const uint64_t qnan2 = 0x7FC000007FC00000ull;
 
-    // raw words of the current tile and of the next two (prefetch distance 2: one round of the 32
-    // resident warps is shorter than an HBM round trip, ncu showed long-scoreboard stalls at
-    // distance 1).  3 packed words (96 bases from a 16-base boundary) and 2 mask words cover the
+    // raw words are prefetched three tiles ahead (one round of the 32 resident warps is shorter
+    // than an HBM round trip; ncu showed long-scoreboard stalls at smaller distances).  3 packed words (96 bases from a 16-base boundary) and 2 mask words cover the
     // 4 + 32 bases a thread can touch.
     struct Raw { uint32_t a0, a1, a2, m0, m1; };
     auto fetch = [&](int64_t tile) {
@@ -86,10 +85,8 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
         return r;
     };
     const int64_t stride = gridDim.x;
-    Raw cur = {0, 0, 0, 0, 0}, nxt = cur;
-    if ((int64_t)blockIdx.x < n_tiles) cur = fetch(blockIdx.x);
-    if ((int64_t)blockIdx.x + stride < n_tiles) nxt = fetch(blockIdx.x + stride);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += stride) {
+    // one tile: build the register window from raw words, score, store
+    auto process = [&](int64_t tile, const Raw &cur) {
         const int64_t p0 = tile * kTile + (int64_t)tid * kPosPerThread;
         // 48-base register window starting at p0 (p0 is a multiple of 4)
         uint32_t w0, w1, w2, inv_lo, inv_hi;
@@ -102,8 +99,6 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
             inv_lo = __funnelshift_r(cur.m0, cur.m1, msh);
             inv_hi = cur.m1 >> msh;
         }
-        cur = nxt;
-        if (tile + 2 * stride < n_tiles) nxt = fetch(tile + 2 * stride);
         uint64_t acc[kPosPerThread];
 #pragma unroll
         for (int g = 0; g < G; g++) {
@@ -132,6 +127,27 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
         // sectors: twice the L1->XBAR sector traffic and store wavefronts, ncu r01)
         __stcs(reinterpret_cast<float4 *>(row_f + p0), make_float4(af[0], af[1], af[2], af[3]));
         __stcs(reinterpret_cast<float4 *>(row_r + p0), make_float4(ar[0], ar[1], ar[2], ar[3]));
+    };
+    // three register sets rotate without moves (a move would wait for the load it copies), so a
+    // set is consumed two full iterations after its loads were issued
+    const Raw zero = {0, 0, 0, 0, 0};
+    int64_t tile = blockIdx.x;
+    Raw r0 = tile < n_tiles ? fetch(tile) : zero;
+    Raw r1 = tile + stride < n_tiles ? fetch(tile + stride) : zero;
+    Raw r2 = tile + 2 * stride < n_tiles ? fetch(tile + 2 * stride) : zero;
+    while (true) {
+        if (tile >= n_tiles) break;
+        process(tile, r0);
+        if (tile + 3 * stride < n_tiles) r0 = fetch(tile + 3 * stride);
+        tile += stride;
+        if (tile >= n_tiles) break;
+        process(tile, r1);
+        if (tile + 3 * stride < n_tiles) r1 = fetch(tile + 3 * stride);
+        tile += stride;
+        if (tile >= n_tiles) break;
+        process(tile, r2);
+        if (tile + 3 * stride < n_tiles) r2 = fetch(tile + 3 * stride);
+        tile += stride;
     }
 }
 
