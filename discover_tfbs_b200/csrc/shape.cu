@@ -51,8 +51,7 @@ shape_tracks_kernel(const TrackParams P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
-    // raw words of the current sub-tile and of the next two (prefetch distance 2 hides the HBM
-    // round trip behind two rounds of the resident warps)
+    // raw words are prefetched three sub-tiles ahead (hides the HBM round trip)
     struct Raw { uint32_t a0, a1, m0, m1; };
     auto fetch = [&](int64_t sub) {
         Raw r;
@@ -64,18 +63,13 @@ shape_tracks_kernel(const TrackParams P)
         return r;
     };
     const int64_t stride = gridDim.x;
-    Raw cur = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu}, nxt = cur;
-    if ((int64_t)blockIdx.x < n_sub) cur = fetch(blockIdx.x);
-    if ((int64_t)blockIdx.x + stride < n_sub) nxt = fetch(blockIdx.x + stride);
-    for (int64_t sub = blockIdx.x; sub < n_sub; sub += stride) {
+    auto process = [&](int64_t sub, const Raw &cur) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
         // 16-base register window starting at base b0 = p0 - 4 (a multiple of 4, may be -4):
         // pentamer centred at p0 + d starts at window base d + 2
         const int64_t b0 = p0 - 4;
         const uint32_t wlo = __funnelshift_r(cur.a0, cur.a1, (int)(b0 & 15) * 2);
         const uint32_t inv = __funnelshift_r(cur.m0, cur.m1, (int)(b0 & 31));
-        cur = nxt;
-        if (sub + 2 * stride < n_sub) nxt = fetch(sub + 2 * stride);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
@@ -104,6 +98,26 @@ shape_tracks_kernel(const TrackParams P)
             }
             __stcs(reinterpret_cast<float4 *>(P.out + (size_t)t * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
         }
+    };
+    // three register sets rotate without moves (a move would wait for the load it copies)
+    const Raw none = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    int64_t sub = blockIdx.x;
+    Raw r0 = sub < n_sub ? fetch(sub) : none;
+    Raw r1 = sub + stride < n_sub ? fetch(sub + stride) : none;
+    Raw r2 = sub + 2 * stride < n_sub ? fetch(sub + 2 * stride) : none;
+    while (true) {
+        if (sub >= n_sub) break;
+        process(sub, r0);
+        if (sub + 3 * stride < n_sub) r0 = fetch(sub + 3 * stride);
+        sub += stride;
+        if (sub >= n_sub) break;
+        process(sub, r1);
+        if (sub + 3 * stride < n_sub) r1 = fetch(sub + 3 * stride);
+        sub += stride;
+        if (sub >= n_sub) break;
+        process(sub, r2);
+        if (sub + 3 * stride < n_sub) r2 = fetch(sub + 3 * stride);
+        sub += stride;
     }
 }
 
@@ -158,8 +172,7 @@ shape_tracks_c16_kernel(const Packed16Params P)
     __syncthreads();
     const float qnan = __int_as_float(0x7FC00000);
     const int64_t n_sub = P.pitch / (kShapeThreads * kShapePosPerThread);
-    // raw words of the current sub-tile and of the next two (prefetch distance 2 hides the HBM
-    // round trip behind two rounds of the resident warps)
+    // raw words are prefetched three sub-tiles ahead (hides the HBM round trip)
     struct Raw { uint32_t a0, a1, m0, m1; };
     auto fetch = [&](int64_t sub) {
         Raw r;
@@ -171,16 +184,11 @@ shape_tracks_c16_kernel(const Packed16Params P)
         return r;
     };
     const int64_t stride = gridDim.x;
-    Raw cur = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu}, nxt = cur;
-    if ((int64_t)blockIdx.x < n_sub) cur = fetch(blockIdx.x);
-    if ((int64_t)blockIdx.x + stride < n_sub) nxt = fetch(blockIdx.x + stride);
-    for (int64_t sub = blockIdx.x; sub < n_sub; sub += stride) {
+    auto process = [&](int64_t sub, const Raw &cur) {
         const int64_t p0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread;
         const int64_t b0 = p0 - 4;
         const uint32_t wlo = __funnelshift_r(cur.a0, cur.a1, (int)(b0 & 15) * 2);
         const uint32_t inv = __funnelshift_r(cur.m0, cur.m1, (int)(b0 & 31));
-        cur = nxt;
-        if (sub + 2 * stride < n_sub) nxt = fetch(sub + 2 * stride);
         uint32_t pent[kShapePosPerThread + 1];
         bool ok[kShapePosPerThread + 1];
 #pragma unroll
@@ -217,6 +225,26 @@ shape_tracks_c16_kernel(const Packed16Params P)
                 __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
             }
         }
+    };
+    // three register sets rotate without moves (a move would wait for the load it copies)
+    const Raw none = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    int64_t sub = blockIdx.x;
+    Raw r0 = sub < n_sub ? fetch(sub) : none;
+    Raw r1 = sub + stride < n_sub ? fetch(sub + stride) : none;
+    Raw r2 = sub + 2 * stride < n_sub ? fetch(sub + 2 * stride) : none;
+    while (true) {
+        if (sub >= n_sub) break;
+        process(sub, r0);
+        if (sub + 3 * stride < n_sub) r0 = fetch(sub + 3 * stride);
+        sub += stride;
+        if (sub >= n_sub) break;
+        process(sub, r1);
+        if (sub + 3 * stride < n_sub) r1 = fetch(sub + 3 * stride);
+        sub += stride;
+        if (sub >= n_sub) break;
+        process(sub, r2);
+        if (sub + 3 * stride < n_sub) r2 = fetch(sub + 3 * stride);
+        sub += stride;
     }
 }
 
