@@ -66,8 +66,9 @@ struct tfbs_seq {
     int64_t n = 0;          // bases
     int64_t n_words = 0;    // packed words allocated (padded, zero-filled past n)
     int64_t n_mask = 0;     // mask words allocated (padded, all-ones past n)
-    uint32_t *packed = nullptr;
-    uint32_t *mask = nullptr;
+    uint32_t *packed = nullptr;     // first word of base 0; 64 words before it are allocated too
+    uint32_t *mask = nullptr;       // (packed: zeros, mask: all ones) so kernels may read index -1
+    uint32_t *packed_base = nullptr, *mask_base = nullptr;  // what cudaMalloc returned
     void *staging = nullptr;   // device ASCII staging for tfbs_encode (host input)
     size_t staging_bytes = 0;
 };

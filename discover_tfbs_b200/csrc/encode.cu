@@ -218,12 +218,22 @@ int alloc_seq(tfbs_ctx *ctx, int64_t n, tfbs_seq **out)
     const int64_t n_pad = ((n + 8191) / 8192) * 8192 + 5 * 8192;  // tiles of every kernel may over-read (hits: 32 256 + 128)
     s->n_words = n_pad / 16;
     s->n_mask = n_pad / 32;
-    cudaError_t e = cudaMalloc(&s->packed, (size_t)s->n_words * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->mask, (size_t)s->n_mask * 4);
+    // 64-word front pad (bases "-1024..-1": code 0, invalid) lets the shape kernels read the window
+    // left of position 0 without bounds checks
+    constexpr int kFrontPad = 64;
+    cudaError_t e = cudaMalloc(&s->packed_base, (size_t)(s->n_words + kFrontPad) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->mask_base, (size_t)(s->n_mask + kFrontPad) * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->packed_base, 0, kFrontPad * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->mask_base, 0xFF, kFrontPad * 4, ctx->stream);
+    if (e == cudaSuccess) {
+        s->packed = s->packed_base + kFrontPad;
+        s->mask = s->mask_base + kFrontPad;
+    }
     if (e != cudaSuccess) {
         tfbs_set_error("cudaMalloc for a %lld-base sequence failed: %s", (long long)n,
                        cudaGetErrorString(e));
-        if (s->packed) cudaFree(s->packed);
+        if (s->packed_base) cudaFree(s->packed_base);
+        if (s->mask_base) cudaFree(s->mask_base);
         delete s;
         return TFBS_ERR_NOMEM;
     }
@@ -336,8 +346,8 @@ int tfbs_seq_destroy(tfbs_seq *seq)
 {
     if (!seq) return TFBS_OK;
     if (seq->ctx) cudaSetDevice(seq->ctx->device);
-    if (seq->packed) cudaFree(seq->packed);
-    if (seq->mask) cudaFree(seq->mask);
+    if (seq->packed_base) cudaFree(seq->packed_base);
+    if (seq->mask_base) cudaFree(seq->mask_base);
     if (seq->staging) cudaFree(seq->staging);
     delete seq;
     return TFBS_OK;

@@ -56,10 +56,13 @@ shape_tracks_kernel(const TrackParams P)
     auto fetch = [&](int64_t sub) {
         Raw r;
         const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
-        r.a0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
-        r.a1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
-        r.m0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
-        r.m1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        // q0 >= -4: the encoded buffers carry a front pad, so index -1 is readable (invalid bases)
+        const uint32_t *wp = P.packed + (q0 >> 4);
+        const uint32_t *mp = P.mask + (q0 >> 5);
+        r.a0 = __ldg(wp);
+        r.a1 = __ldg(wp + 1);
+        r.m0 = __ldg(mp);
+        r.m1 = __ldg(mp + 1);
         return r;
     };
     const int64_t stride = gridDim.x;
@@ -136,8 +139,8 @@ struct Packed16Params {
     const uint32_t *words;  // [NW][1024] little-endian pentamer index
     int32_t NW;
     int32_t kind[kMaxTracks];   // 0: two per-nucleotide tracks, 1: one per-step track (Y1 | Y2 << 16)
-    int32_t row_a[kMaxTracks];  // output row of the low half (or of the step track)
-    int32_t row_b[kMaxTracks];  // output row of the high half, -1 if none
+    int64_t off_a[kMaxTracks];  // row * pitch of the low half (or of the step track)
+    int64_t off_b[kMaxTracks];  // row * pitch of the high half, -1 if none
     float *out;
 };
 
@@ -177,10 +180,13 @@ shape_tracks_c16_kernel(const Packed16Params P)
     auto fetch = [&](int64_t sub) {
         Raw r;
         const int64_t q0 = sub * (kShapeThreads * kShapePosPerThread) + tid * kShapePosPerThread - 4;
-        r.a0 = ld_words_guard(P.packed, q0 >> 4, P.n_words, 0u);
-        r.a1 = ld_words_guard(P.packed, (q0 >> 4) + 1, P.n_words, 0u);
-        r.m0 = ld_words_guard(P.mask, q0 >> 5, P.n_mask, 0xFFFFFFFFu);
-        r.m1 = ld_words_guard(P.mask, (q0 >> 5) + 1, P.n_mask, 0xFFFFFFFFu);
+        // q0 >= -4: the encoded buffers carry a front pad, so index -1 is readable (invalid bases)
+        const uint32_t *wp = P.packed + (q0 >> 4);
+        const uint32_t *mp = P.mask + (q0 >> 5);
+        r.a0 = __ldg(wp);
+        r.a1 = __ldg(wp + 1);
+        r.m0 = __ldg(mp);
+        r.m1 = __ldg(mp + 1);
         return r;
     };
     const int64_t stride = gridDim.x;
@@ -208,9 +214,9 @@ shape_tracks_c16_kernel(const Packed16Params P)
                     va[d] = ok[d] ? centi_from_biased(u[d] & 0xFFFFu) : qnan;
                     vb[d] = ok[d] ? centi_from_biased(u[d] >> 16) : qnan;
                 }
-                __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(va[0], va[1], va[2], va[3]));
-                if (P.row_b[w] >= 0)
-                    __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_b[w] * P.pitch + p0), make_float4(vb[0], vb[1], vb[2], vb[3]));
+                __stcs(reinterpret_cast<float4 *>(P.out + P.off_a[w] + p0), make_float4(va[0], va[1], va[2], va[3]));
+                if (P.off_b[w] >= 0)
+                    __stcs(reinterpret_cast<float4 *>(P.out + P.off_b[w] + p0), make_float4(vb[0], vb[1], vb[2], vb[3]));
             } else {
                 // the pentamer just past this lane's 4 positions belongs to the next lane
                 u[kShapePosPerThread] = __shfl_down_sync(0xFFFFFFFFu, u[0], 1);
@@ -222,7 +228,7 @@ shape_tracks_c16_kernel(const Packed16Params P)
                     const float y1 = centi_from_biased(u[d + 1] & 0xFFFFu);
                     v[d] = (ok[d] && ok[d + 1]) ? __fmul_rn(__fadd_rn(y2, y1), 0.5f) : qnan;
                 }
-                __stcs(reinterpret_cast<float4 *>(P.out + (size_t)P.row_a[w] * P.pitch + p0), make_float4(v[0], v[1], v[2], v[3]));
+                __stcs(reinterpret_cast<float4 *>(P.out + P.off_a[w] + p0), make_float4(v[0], v[1], v[2], v[3]));
             }
         }
     };
@@ -536,8 +542,8 @@ int tfbs_shape_tracks(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_shapes *sha
         Q.NW = (int32_t)shapes->c16_kind.size();
         for (int w = 0; w < kMaxTracks; w++) {
             Q.kind[w] = w < Q.NW ? shapes->c16_kind[w] : 0;
-            Q.row_a[w] = w < Q.NW ? shapes->c16_row_a[w] : 0;
-            Q.row_b[w] = w < Q.NW ? shapes->c16_row_b[w] : -1;
+            Q.off_a[w] = w < Q.NW ? (int64_t)shapes->c16_row_a[w] * pitch : 0;
+            Q.off_b[w] = (w < Q.NW && shapes->c16_row_b[w] >= 0) ? (int64_t)shapes->c16_row_b[w] * pitch : -1;
         }
         Q.out = P.out;
         shape_tracks_c16_kernel<<<(unsigned)grid, kShapeThreads, (size_t)Q.NW * 4096, ctx->stream>>>(Q);
