@@ -192,34 +192,9 @@ struct PushCtx {
     unsigned long long cap;
 };
 
-// Cold path: a lane found a candidate field (bit 31 = forward, bit 15 = reverse).
-__device__ __noinline__ void push_candidate(const PushCtx &C, uint32_t cand, int p)
-{
-    if (p < C.seg_begin || p >= C.seg_end) return;  // ring lead-in / overshoot of the last turn
-#pragma unroll
-    for (int strand = 0; strand < 2; strand++) {
-        if (!(cand & (strand ? 0x00008000u : 0x80000000u))) continue;
-        const uint32_t slot = atomicAdd(C.qcount, 1u);
-        if (slot < (uint32_t)kQueueCap) {
-            C.queue[slot] = (uint32_t)p | ((uint32_t)C.lane << 16) | ((uint32_t)strand << 31);
-        } else {
-            // queue full (pathological thresholds): verify right here, divergently
-            int m;
-            float f;
-            if (verify(*C.V, p, C.lane, strand, &m, &f)) {
-                cg::coalesced_group g = cg::coalesced_threads();
-                unsigned long long base = 0;
-                if (g.thread_rank() == 0) base = atomicAdd(C.hit_count, (unsigned long long)g.size());
-                base = g.shfl(base, 0);
-                store_hit(C.hits, base + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, f);
-            }
-        }
-    }
-}
-
 // Warp-synchronous verification of the queued candidates, 32 at a time; hits are compacted with
 // ballot/popc and one atomic per batch.
-__device__ __forceinline__ void drain_queue(const PushCtx &C)
+__device__ __noinline__ void drain_queue(const PushCtx &C)
 {
     __syncwarp();
     const uint32_t cnt = min(*C.qcount, (uint32_t)kQueueCap);
@@ -249,6 +224,64 @@ __device__ __forceinline__ void drain_queue(const PushCtx &C)
         *C.qcount = 0;
     }
     __syncwarp();
+}
+
+// Cold path, entered by the WHOLE warp when any lane of a check group has a candidate field (bit 31 =
+// forward, bit 15 = reverse clear).  a0..a3 are the finalised accumulators of window starts
+// p_first .. p_first+3 (unused slots = kPoison).  One warp-wide OR tells which (start, strand)
+// pairs have candidates at all (usually one); each of those is compacted into the warp's queue with
+// ballot/popc — the queue is warp-private and every access is warp-synchronous, so no atomics and
+// no lane-by-lane serialisation when hits are dense.
+__device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           int p_first)
+{
+    // bit 2k + s of `mine`: this lane has a candidate at start p_first + k on strand s
+    uint32_t mine = 0;
+    {
+        const uint32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int p = p_first + k;
+            if (p >= C.seg_begin && p < C.seg_end) {  // ring lead-in / overshoot of the last turn
+                const uint32_t cand = ~a[k] & kPoison;
+                mine |= ((cand >> 31) & 1u) << (2 * k);
+                mine |= ((cand >> 15) & 1u) << (2 * k + 1);
+            }
+        }
+    }
+    uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mine);
+    const uint32_t lt = (1u << C.lane) - 1u;
+    while (any) {
+        const int bit = __ffs(any) - 1;
+        any &= any - 1u;
+        const bool c = (mine >> bit) & 1u;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, c);
+        uint32_t base = 0;
+        if (C.lane == 0) {
+            base = *C.qcount;
+            *C.qcount = base + (uint32_t)__popc(b);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (c) {
+            const int p = p_first + (bit >> 1), strand = bit & 1;
+            const uint32_t slot = base + (uint32_t)__popc(b & lt);
+            if (slot < (uint32_t)kQueueCap) {
+                C.queue[slot] = (uint32_t)p | ((uint32_t)C.lane << 16) | ((uint32_t)strand << 31);
+            } else {
+                // queue full (flood thresholds): verify right here, divergently
+                int m;
+                float f;
+                if (verify(*C.V, p, C.lane, strand, &m, &f)) {
+                    cg::coalesced_group g = cg::coalesced_threads();
+                    unsigned long long hb = 0;
+                    if (g.thread_rank() == 0) hb = atomicAdd(C.hit_count, (unsigned long long)g.size());
+                    hb = g.shfl(hb, 0);
+                    store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, f);
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 motifs of the
@@ -298,24 +331,23 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
             }
             // Candidate test, amortised over kCheck consecutive steps: bit 15 of a field stays SET
             // in the AND of the finalised accumulators unless one of them cleared it.  (A finalised
-            // slot is re-opened 32 - kTail steps later, which bounds kCheck.)
+            // slot is re-opened 32 - kTail steps later, which bounds kCheck.)  The vote keeps the
+            // branch warp-uniform, so the cold path can compact candidates cooperatively.
             if ((j % kCheck) == kCheck - 1) {
-                uint32_t all = acc[(j - kTail + 2 * kRing) % kRing];
+                uint32_t fin[4] = {kPoison, kPoison, kPoison, kPoison};
 #pragma unroll
-                for (int k = 1; k < kCheck; k++) all &= acc[(j - k - kTail + 2 * kRing) % kRing];
-                if (~all & kPoison) {
-#pragma unroll
-                    for (int k = kCheck - 1; k >= 0; k--) {
-                        const uint32_t cand = ~acc[(j - k - kTail + 2 * kRing) % kRing] & kPoison;
-                        if (cand) push_candidate(C, cand, q0 + j - k - kTail);
-                    }
-                }
+                for (int k = 0; k < kCheck; k++) fin[k] = acc[(j - (kCheck - 1 - k) - kTail + 2 * kRing) % kRing];
+                const uint32_t all = fin[0] & fin[1] & fin[2] & fin[3];
+                if (__any_sync(0xFFFFFFFFu, (~all & kPoison) != 0u))
+                    push_group(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail);
             }
             if (jj == 15) {
                 wlo = whi;
                 whi = wptr[wk++];
             }
         }
+        // all lanes are converged again here: verify queued candidates before the queue can fill up
+        if (*C.qcount >= (uint32_t)kQueueCap / 2) drain_queue(C);
     }
 }
 
