@@ -403,7 +403,7 @@ def run_ours(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, from the
                 # committed ncu --set full capture profiles/r01/ncu_full_final_100Mb_raw.csv (part of the
                 # 297 MB of hits is still in L2 when the kernel ends)
-                "traffic": 74.44e6 + 119.06e6 if (args.motifs == 800 and per_gpu == 100_000_000) else None,
+                "traffic": 76.19e6 + 116.30e6 if (args.motifs == 800 and per_gpu == 100_000_000) else None,
                 "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
                 "note": "hits mode at 800 motifs is bounded by shared-memory LUT bandwidth, not HBM "
