@@ -450,11 +450,8 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
 #define TFBS_CASE(a, b) \
     case ((a << 8) | b): scan_segment<a, b>(C, S.words, lut_lane_addr, kinit); break;
             // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32
-            TFBS_CASE(0, 1) TFBS_CASE(0, 2) TFBS_CASE(0, 3) TFBS_CASE(1, 0) TFBS_CASE(1, 1) TFBS_CASE(1, 2)
-            TFBS_CASE(1, 3) TFBS_CASE(2, 0) TFBS_CASE(2, 1) TFBS_CASE(2, 2) TFBS_CASE(2, 3) TFBS_CASE(3, 0)
-            TFBS_CASE(3, 1) TFBS_CASE(3, 2) TFBS_CASE(3, 3) TFBS_CASE(3, 5) TFBS_CASE(3, 6) TFBS_CASE(4, 0)
-            TFBS_CASE(4, 1) TFBS_CASE(4, 2) TFBS_CASE(4, 3) TFBS_CASE(4, 4) TFBS_CASE(4, 5) TFBS_CASE(5, 0)
-            TFBS_CASE(5, 1) TFBS_CASE(5, 2) TFBS_CASE(5, 3) TFBS_CASE(5, 4) TFBS_CASE(6, 0)
+            TFBS_CASE(1, 0) TFBS_CASE(2, 0) TFBS_CASE(3, 0) TFBS_CASE(4, 0) TFBS_CASE(5, 0) TFBS_CASE(6, 0)
+            TFBS_CASE(5, 2) TFBS_CASE(5, 3) TFBS_CASE(5, 4)
 #undef TFBS_CASE
             default:  // no instantiation for this grouping: report it instead of silently skipping
                 if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)AB));
@@ -559,18 +556,18 @@ int hits_smem_plan(tfbs_ctx *ctx, size_t lut_bytes, size_t *smem_out)
 
 // Column grouping of a block whose longest motif has L columns: A groups of 4 columns followed by
 // B groups of 3, minimising A + B (shared-memory loads per window) under the table budget
-// (32 KB per 4-mer group, 8 KB per 3-mer group), ties broken towards the smaller table.
+// (32 KB per 4-mer group, 8 KB per 3-mer group).
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 {
-    int best_a = 0, best_b = (L + 2) / 3, best_groups = 1 << 30, best_bytes = 1 << 30;
+    // minimise A + B; among the minimal groupings take the one with the most 4-column groups, which
+    // leaves only 9 distinct (A, B) pairs for L = 1..32 (kernel instantiations, compile time)
+    int best_a = 0, best_b = (L + 2) / 3, best_groups = 1 << 30;
     for (int a = 0; a <= 6; a++)
         for (int b = 0; b <= kMaxG; b++) {
             if (a + b < 1 || 4 * a + 3 * b < L) continue;
-            const int bytes = a * 32768 + b * 8192;
-            if (bytes > kLutBudget) continue;
-            if (a + b < best_groups || (a + b == best_groups && bytes < best_bytes)) {
+            if (a * 32768 + b * 8192 > kLutBudget) continue;
+            if (a + b < best_groups || (a + b == best_groups && a > best_a)) {
                 best_groups = a + b;
-                best_bytes = bytes;
                 best_a = a;
                 best_b = b;
             }
