@@ -10,7 +10,6 @@ PWM with a score threshold generalises it.
 """
 import numpy as np
 
-from . import _lib
 from .pssm import default_context
 from .synth import join_records
 

@@ -20,7 +20,7 @@ from time import strftime
 import numpy as np
 import pandas as pd
 
-from . import _lib, dnashape, similarity
+from . import dnashape, similarity
 from .pssm import default_context
 from .synth import join_records
 

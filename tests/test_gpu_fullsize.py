@@ -3,7 +3,7 @@ oracle would need hours there): cross-kernel consistency, shard invariance, idem
 import numpy as np
 import pytest
 
-from discover_tfbs_b200 import _lib, dnashape, sharding, synth
+from discover_tfbs_b200 import dnashape, sharding, synth
 
 pytestmark = pytest.mark.gpu
 
