@@ -128,3 +128,80 @@ class MotifScanner:
     def units(self, n: int) -> int:
         """motif x bp units of one scan of an n-base buffer: sum_m (n - L_m + 1)."""
         return int(sum(max(n - int(L) + 1, 0) for L in self.lens))
+
+
+# ---- motif input and threshold selection (host helpers; Biopython-shaped) ---------------------------
+def read_jaspar(path_or_text, pseudocounts=0.5, background=None):
+    """Parse JASPAR-format count matrices (the format `Bio.motifs.parse(handle, "jaspar")` reads):
+
+        >MA0001.1 AGL3
+        A  [ 0  3 79 ... ]
+        C  [94 75  4 ... ]
+        G  [ 1  0  3 ... ]
+        T  [ 2 19 11 ... ]
+
+    Returns [(name, logodds float64[L][4]), ...] after normalize(pseudocounts) and log_odds(background)."""
+    import os
+    import re
+
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    motifs, name, rows = [], None, {}
+
+    def flush():
+        if name is not None and len(rows) == 4:
+            counts = np.array([rows[b] for b in LETTERS], dtype=np.float64).T
+            motifs.append((name, log_odds(normalize(counts, pseudocounts), background)))
+
+    for line in text.splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith(">"):
+            flush()
+            name, rows = line[1:].strip(), {}
+        else:
+            m = re.match(r"^([ACGT])\s*\[?\s*([^\]]*)\]?\s*$", line)
+            if m:
+                rows[m.group(1)] = [float(x) for x in m.group(2).split()]
+    flush()
+    return motifs
+
+
+def score_distribution(logodds, background=None, precision=1000):
+    """Discretised exact score distribution of a PSSM under an i.i.d. background — the dynamic
+    programme behind Biopython's `pssm.distribution(precision=10**3)` (Bio/motifs/thresholds.py):
+    scores are binned into `precision` steps between the minimum and maximum attainable score.
+    Returns (scores float64[precision+1], probability mass float64[precision+1])."""
+    m = np.asarray(logodds, dtype=np.float64)
+    bg = np.full(4, 0.25) if background is None else np.array([float(background[b]) for b in LETTERS])
+    bg = bg / bg.sum()
+    finite = np.where(np.isfinite(m), m, np.nan)
+    lo = float(np.nansum(np.nanmin(finite, axis=1)))
+    hi = float(np.nansum(np.nanmax(finite, axis=1)))
+    step = (hi - lo) / precision if hi > lo else 1.0
+    dist = np.zeros(precision + 1)
+    dist[0] = 1.0
+    offset = 0.0  # score represented by bin 0 so far
+    for j in range(m.shape[0]):
+        colmin = float(np.nanmin(finite[j]))
+        new = np.zeros(precision + 1)
+        for b in range(4):
+            if not np.isfinite(m[j, b]):
+                continue  # -inf: the window can never reach any finite threshold
+            shift = int(round((m[j, b] - colmin) / step))
+            if shift == 0:
+                new += dist * bg[b]
+            else:
+                new[shift:] += dist[:-shift] * bg[b]
+        dist = new
+        offset += colmin
+    return lo + step * np.arange(precision + 1), dist
+
+
+def threshold_fpr(logodds, fpr, background=None, precision=1000):
+    """Smallest score threshold whose false-positive rate under the background is <= fpr
+    (Biopython: `pssm.distribution().threshold_fpr(fpr)`)."""
+    scores, mass = score_distribution(logodds, background, precision)
+    tail = np.cumsum(mass[::-1])[::-1]  # P(score >= scores[i])
+    ok = np.flatnonzero(tail <= fpr)
+    return float(scores[ok[0]]) if ok.size else float(scores[-1] + (scores[1] - scores[0]))

@@ -180,3 +180,32 @@ def test_hits_group_plan_is_covered_by_kernel_instantiations():
         # optimal: no admissible grouping with fewer loads
         assert all(not (4 * x + 3 * y >= L and 32 * x + 8 * y <= 192 and 1 <= x + y < a + b)
                    for x in range(7) for y in range(12))
+
+
+def test_read_jaspar_and_threshold_fpr():
+    from discover_tfbs_b200 import pssm
+
+    text = """>MA0004.1 Arnt
+A  [ 4 19  0  0  0  0 ]
+C  [16  0 20  0  0  0 ]
+G  [ 0  1  0 20  0 20 ]
+T  [ 0  0  0  0 20  0 ]
+>MA0006.1 Ahr::Arnt
+A  [ 3  0  0  0  0  0 ]
+C  [ 8  0 23  0  0  0 ]
+G  [ 2 23  0 23  0 24 ]
+T  [11  1  1  1 24  0 ]
+"""
+    motifs = pssm.read_jaspar(text, pseudocounts=0.5)
+    assert [n for n, _ in motifs] == ["MA0004.1 Arnt", "MA0006.1 Ahr::Arnt"]
+    lo = motifs[0][1]
+    assert lo.shape == (6, 4) and np.isclose(lo[0, 1], np.log2((16.5 / 22) / 0.25))
+    # the DP distribution agrees with brute-force enumeration of all 4^6 windows
+    scores, mass = pssm.score_distribution(lo, precision=2000)
+    assert abs(mass.sum() - 1.0) < 1e-12
+    idx = np.indices((4,) * 6).reshape(6, -1)
+    brute = lo[np.arange(6)[:, None], idx].sum(axis=0)
+    for fpr in (0.2, 0.05, 0.01, 0.001):
+        thr = pssm.threshold_fpr(lo, fpr, precision=2000)
+        achieved = (brute >= thr).mean()
+        assert achieved <= fpr * 1.05 + 1e-3 and achieved >= fpr * 0.3 - 1e-3, (fpr, achieved)
