@@ -378,12 +378,13 @@ def run_ours(args):
         k_ms = float(np.mean(scan_ms))
         mat_bytes = float(sum(2 * 4 * int(L) * 4 for L in lens))
         algo_bytes = 0.375 * n_scan + mat_bytes + 16.0 * n_hits
-        # hits kernel: one LDS.32 per (lane, base, column group); motifs are sorted by descending
-        # length and grouped 32 per block; a block of longest motif L uses A 4-column + B 3-column
-        # groups (tfbs_hits_group_plan in csrc/scan_hits.cu: minimise A + B under 192 KB of tables)
-        order = np.sort(np.asarray(lens))[::-1]
-        blk_groups = [sum(_lib.hits_group_plan(int(order[i]))) for i in range(0, len(order), 32)]
-        lookups = float(n_scan) * 32.0 * float(sum(blk_groups))
+        # hits kernel: one LDS.32 per (lane, base, column group).  Motifs are sorted by descending
+        # length and cut into blocks (tfbs_hits_block_plan in csrc/scan_hits.cu): a block of longest
+        # motif L uses A 4-column + B 3-column groups (minimal A + B under 192 KB of tables) and holds
+        # 32 motifs (16-bit filter fields) or 64 motifs (8-bit fields; at most 6 groups, chosen per block
+        # from the thresholds by the cost model in tfbs_build_hits_tables)
+        blocks = lib.hits_blocks()
+        lookups = float(n_scan) * 32.0 * float(sum(a + b for a, b, _, _ in blocks))
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         smem_peak = 148 * 128 * sm_mhz * 1e6  # bytes/s of shared-memory bandwidth at the sampled clock
         line = {
@@ -411,7 +412,9 @@ def run_ours(args):
                 "smem": {"lookups_per_s": lookups / k_ms * 1e3, "peak_lookups_per_s": 148 * 32 * sm_mhz * 1e6,
                          "lut_bytes_per_launch": lookups * 4.0, "achieved_gbs": lookups * 4.0 / k_ms / 1e6,
                          "peak_gbs": smem_peak / 1e9, "frac": lookups * 4.0 / k_ms / 1e6 / (smem_peak / 1e9),
-                         "peak_def": "148 SM x 128 B/clk x sampled SM clock"},
+                         "peak_def": "148 SM x 128 B/clk x sampled SM clock",
+                         "blocks": {"wide_32_motifs": sum(1 for b in blocks if not b[2]),
+                                    "narrow_64_motifs": sum(1 for b in blocks if b[2])}},
             },
             "kernel_ms": {"encode": float(np.mean(enc_ms)), "scan_hits": k_ms,
                           **({"shape_tracks_4": float(np.mean(shape_ms))} if shape_ms else {})},

@@ -62,6 +62,8 @@ _PROTOTYPES = {
     "tfbs_similarity_sums": (C.c_int, [_vp] + [_vp] * 6 + [_i64] + [_vp] * 6 + [_i64, _vp]),
     "tfbs_debug_swar4": (C.c_int, [_u32, C.POINTER(_u32), C.POINTER(_u32)]),
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "tfbs_debug_hits_block_plan": (C.c_int, [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
 }
 
 _lib = None
@@ -104,6 +106,19 @@ def hits_group_plan(L: int):
     a, b = _i32(0), _i32(0)
     _check(load().tfbs_debug_hits_group_plan(int(L), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def hits_block_plan(lens, narrow_max_groups: int = 9):
+    """[(A, B, narrow, n_motifs), ...]: the blocks the hits kernel cuts a library into (longest
+    motifs first) when every block of at most `narrow_max_groups` column groups is taken in narrow
+    form (64 motifs, 8-bit filter fields; wide blocks hold 32 with 16-bit fields).  A scan decides
+    narrow/wide per block from the thresholds: see MotifLibrary.hits_blocks()."""
+    a = np.ascontiguousarray(lens, dtype=np.int32)
+    out = np.zeros((max(a.size, 1), 4), dtype=np.int32)
+    nb = _i32(0)
+    _check(load().tfbs_debug_hits_block_plan(a.ctypes.data_as(C.POINTER(_i32)), int(a.size), int(narrow_max_groups),
+                                             out.ctypes.data_as(C.POINTER(_i32)), C.byref(nb)))
+    return [tuple(int(v) for v in row) for row in out[: nb.value]]
 
 
 def device_count() -> int:
@@ -414,6 +429,16 @@ class MotifLibrary(_Handle):
         self.logodds = logodds
         self.lens = lens
         self.M = int(logodds.shape[0])
+
+    def hits_blocks(self):
+        """[(A, B, narrow, n_motifs), ...] of the last hits scan of this library (empty before the
+        first): per block the column groups, whether it ran in narrow form (64 motifs, 8-bit filter
+        fields) or wide (32 motifs, 16-bit), and its motif count."""
+        out = np.zeros((max((self.M + 31) // 32, 1), 4), dtype=np.int32)
+        nb = _i32(0)
+        _check(self.ctx._lib.tfbs_pwms_hits_blocks(self._h, out.ctypes.data_as(C.POINTER(_i32)), out.shape[0],
+                                                   C.byref(nb)))
+        return [tuple(int(v) for v in row) for row in out[: nb.value]]
 
 
 class ShapeTables(_Handle):

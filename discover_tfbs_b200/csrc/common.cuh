@@ -88,9 +88,12 @@ struct tfbs_pwms {
     int64_t lut_entries = 0;
     size_t dense_lut_bytes = 0;      // shared memory the dense kernel needs for its largest table
     int32_t Gmax = 0;
-    // ---- hits mode (scan_hits.cu): motifs sorted by length, 32 per block, one lane each ----
-    int32_t n_blocks = 0;
-    std::vector<int32_t> blk_A, blk_B, blk_lut_off, blk_motif;  // [n_blocks] x3, [n_blocks][32]
+    // ---- hits mode (scan_hits.cu): motifs sorted by length and cut into blocks.  A WIDE block
+    // holds 32 motifs (one per lane, 16-bit filter fields), a NARROW block 64 (two per lane, 8-bit
+    // fields).  The cut depends on the thresholds, so it is made with the filter tables.
+    std::vector<int32_t> order, lens_desc;  // motif indices by descending length, their lengths
+    int32_t n_blocks = 0, n_blocks_max = 0; // blocks of the current plan / capacity of the device arrays
+    std::vector<int32_t> blk_A, blk_B, blk_narrow, blk_count, blk_lut_off, blk_motif;  // [n_blocks] x5, [n_blocks][64]
     std::vector<double> exact_host;  // host copy of `exact`
     size_t hits_lut_bytes = 0;       // largest block table (A * 32 KB + B * 8 KB)
     int64_t hq_lut_words = 0;        // total uint32 entries of the packed deficit tables
@@ -115,6 +118,11 @@ struct tfbs_shapes {
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
+// One block of the hits-mode plan: A 4-column + B 3-column groups, narrow (64 motifs, 8-bit fields)
+// or wide (32 motifs, 16-bit fields), motifs [first, first + count) of the length-sorted order.
+struct tfbs_hits_block { int A, B, narrow, first, count; };
+#define TFBS_BLOCK_SLOTS 64          // motif slots per hits-mode block (32 used by a wide block)
+#define TFBS_NARROW_MAX_GROUPS 9     // narrow blocks: 8-bit fields leave (128 - 2G) / (G - 1) quantisation steps
 int tfbs_encode_range(tfbs_ctx *ctx, const void *ascii_dev, int64_t valid, tfbs_seq *s, int64_t base,
                       int64_t cover, cudaStream_t stream);
 

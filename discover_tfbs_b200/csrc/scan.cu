@@ -13,6 +13,7 @@
 //   hits mode (scan_hits.cu): packed fixed-point filter + exact double re-scoring of candidates.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -258,30 +259,21 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->Gmax = Gmax;
     p->lut_entries = (int64_t)lut.size();
 
-    // hits mode: motifs sorted by descending length, 32 per block (one warp lane each)
-    std::vector<int32_t> order(M);
-    for (int m = 0; m < M; m++) order[m] = m;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-    p->n_blocks = (M + 31) / 32;
-    p->blk_A.assign(p->n_blocks, 0);
-    p->blk_B.assign(p->n_blocks, 1);
-    p->blk_lut_off.assign(p->n_blocks, 0);
-    p->blk_motif.assign((size_t)p->n_blocks * 32, -1);
-    std::vector<int32_t> blk_AB(p->n_blocks);
+    // hits mode: motifs sorted by descending length.  The cut into blocks (32 motifs with 16-bit filter
+    // fields or 64 with 8-bit fields) depends on the thresholds and is made with the filter tables
+    // (tfbs_build_hits_tables in scan_hits.cu); here the device arrays are sized for the largest plan,
+    // 32 motifs per block throughout.
+    p->order.resize(M);
+    for (int m = 0; m < M; m++) p->order[m] = m;
+    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    p->lens_desc.resize(M);
+    for (int i = 0; i < M; i++) p->lens_desc[i] = lens[p->order[i]];
+    p->n_blocks = 0;
+    p->n_blocks_max = (M + 31) / 32;
     int64_t words = 0;
-    for (int b = 0; b < p->n_blocks; b++) {
-        int lmax_b = 1;
-        for (int l = 0; l < 32 && b * 32 + l < M; l++) {
-            const int m = order[b * 32 + l];
-            p->blk_motif[(size_t)b * 32 + l] = m;
-            lmax_b = std::max(lmax_b, lens[m]);
-        }
+    for (int i = 0; i < M; i += 32) {
         int A = 0, B = 1;
-        tfbs_hits_group_plan(lmax_b, &A, &B);  // A groups of 4 columns + B groups of 3
-        p->blk_A[b] = A;
-        p->blk_B[b] = B;
-        blk_AB[b] = (A << 8) | B;
-        p->blk_lut_off[b] = (int32_t)words;
+        tfbs_hits_group_plan(p->lens_desc[i], &A, &B);
         words += (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32;
         p->hits_lut_bytes = std::max(p->hits_lut_bytes, (size_t)A * 32768 + (size_t)B * 8192);
     }
@@ -293,14 +285,11 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     if (e == cudaSuccess) e = cudaMalloc(&p->lut_off, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_lut_dev, (size_t)p->hq_lut_words * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->hq_kinit_dev, (size_t)p->n_blocks * 32 * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->blk_AB_dev, (size_t)p->n_blocks * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->blk_lut_off_dev, (size_t)p->n_blocks * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&p->blk_motif_dev, (size_t)p->n_blocks * 32 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->hq_kinit_dev, (size_t)p->n_blocks_max * 32 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_AB_dev, (size_t)p->n_blocks_max * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_lut_off_dev, (size_t)p->n_blocks_max * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->blk_motif_dev, (size_t)p->n_blocks_max * TFBS_BLOCK_SLOTS * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->lens_dev, (size_t)M * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(p->blk_AB_dev, blk_AB.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(p->blk_lut_off_dev, p->blk_lut_off.data(), (size_t)p->n_blocks * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(p->blk_motif_dev, p->blk_motif.data(), (size_t)p->n_blocks * 32 * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lens_dev, lens, (size_t)M * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->exact, exact.data(), exact.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice);

@@ -23,6 +23,13 @@
 //     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
 //     float, compared with >= — so hit sets and scores are bit-exact.  Hits are compacted with
 //     ballot/popc and one global atomic per warp batch.
+//   * NARROW blocks: 64 motifs per block, two per lane, four 8-bit fields per entry (motif lane: fwd,
+//     rev; motif lane + 32: fwd, rev).  The same LDS.32 + IADD now scores two motifs, halving
+//     shared-memory traffic per motif — the resource this kernel is bound by.  Only
+//     (128 - 2G) / (G - 1) quantisation steps fit without carries, so the filter is coarser (1.1x the
+//     candidates at G = 3, 2.4x at G = 5, 78x at G = 9; profiles/field8_simulation.py) and the exact
+//     verifier, which keeps the hit set bit-exact, has more to do.  Narrow or wide is therefore
+//     chosen per block and per threshold vector by a cost model (tfbs_build_hits_tables).
 //   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
 //     block-major order, so a CTA re-loads its table (up to 192 KB) only when the block changes.
 #include <algorithm>
@@ -48,9 +55,10 @@ constexpr int kTileWords = kTileBases / 16;  // 2024 words  = 8096 B (multiple o
 constexpr int kTileMask = kTileBases / 32;   // 1012 words  = 4048 B (multiple of 16)
 constexpr int kQueueCap = 256;            // candidate queue entries per warp
 constexpr int kMaxG = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
-constexpr uint32_t kPoison = 0x80008000u;
+constexpr uint32_t kPoison = 0x80008000u;        // flag bits of the two 16-bit fields (wide blocks)
+constexpr uint32_t kPoisonNarrow = 0x80808080u;  // flag bits of the four 8-bit fields (narrow blocks)
 constexpr int kLutBudget = 192 * 1024;    // shared memory for one block table (6 x 32 KB)
-constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + kWarps * 4 + 64 * 4 + 32;
+constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + kWarps * 4 + 2 * TFBS_BLOCK_SLOTS * 4 + 32;
 
 struct HitsParams {
     const uint32_t *packed;
@@ -60,9 +68,9 @@ struct HitsParams {
     int32_t n_blocks;
     const uint32_t *qlut;        // per block [A][256][32] then [B][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
-    const int32_t *blk_AB;       // [n_blocks] (A << 8) | B: 4-column and 3-column groups of the block
-    const uint32_t *kinit;       // [n_blocks][32] initial field values (0x7FFF - Dq per strand)
-    const int32_t *blk_motif;    // [n_blocks][32] original motif index or -1
+    const int32_t *blk_AB;       // [n_blocks] (narrow << 16) | (A << 8) | B: 4- and 3-column groups of the block
+    const uint32_t *kinit;       // [n_blocks][32] initial field values per lane (0x7FFF - Dq or 0x7F - Dq each)
+    const int32_t *blk_motif;    // [n_blocks][64] original motif index or -1 (slot = lane + 32 * half)
     const int32_t *lens;         // [M]
     const float *thr;            // [M]
     const double *exact;         // [M][2][32][4]
@@ -79,8 +87,8 @@ struct Smem {
     uint32_t *mask;      // [kTileMask]
     uint32_t *queue;     // [kWarps][kQueueCap]
     uint32_t *qcount;    // [kWarps]
-    int32_t *motif;      // [32]
-    int32_t *len;        // [32]
+    int32_t *motif;      // [64]
+    int32_t *len;        // [64]
     uint64_t *bar;       // mbarrier
     uint32_t *item;      // broadcast slot
 };
@@ -207,7 +215,7 @@ __device__ __noinline__ void drain_queue(const PushCtx &C)
             const uint32_t e = C.queue[i];
             p = (int)(e & 0xFFFFu);
             strand = (int)(e >> 31);
-            hit = verify(*C.V, p, (int)((e >> 16) & 31u), strand, &m, &f);
+            hit = verify(*C.V, p, (int)((e >> 16) & 63u), strand, &m, &f);
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
         if (ballot) {
@@ -226,16 +234,19 @@ __device__ __noinline__ void drain_queue(const PushCtx &C)
     __syncwarp();
 }
 
-// Cold path, entered by the WHOLE warp when any lane of a check group has a candidate field (bit 31 =
-// forward, bit 15 = reverse clear).  a0..a3 are the finalised accumulators of window starts
-// p_first .. p_first+3 (unused slots = kPoison).  One warp-wide OR tells which (start, strand)
-// pairs have candidates at all (usually one); each of those is compacted into the warp's queue with
+// Cold path, entered by the WHOLE warp when any lane of a check group has a candidate field (its flag
+// bit clear).  NF = fields per accumulator word: 2 (wide: bit 31 forward, bit 15 reverse) or 4 (narrow:
+// bits 31 / 23 = motif slot `lane` forward / reverse, bits 15 / 7 = motif slot `lane + 32`).
+// a0..a3 are the finalised accumulators of window starts p_first .. p_first+3 (unused slots: all flag
+// bits set).  One warp-wide OR tells which (start, field) pairs have candidates at all (usually one); each of those is compacted into the warp's queue with
 // ballot/popc — the queue is warp-private and every access is warp-synchronous, so no atomics and
 // no lane-by-lane serialisation when hits are dense.
+template <int NF>
 __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                            int p_first)
 {
-    // bit 2k + s of `mine`: this lane has a candidate at start p_first + k on strand s
+    constexpr int FB = 32 / NF;  // field width
+    // bit NF * k + f of `mine`: this lane has a candidate at start p_first + k in field f
     uint32_t mine = 0;
     {
         const uint32_t a[4] = {a0, a1, a2, a3};
@@ -243,9 +254,9 @@ __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32
         for (int k = 0; k < 4; k++) {
             const int p = p_first + k;
             if (p >= C.seg_begin && p < C.seg_end) {  // ring lead-in / overshoot of the last turn
-                const uint32_t cand = ~a[k] & kPoison;
-                mine |= ((cand >> 31) & 1u) << (2 * k);
-                mine |= ((cand >> 15) & 1u) << (2 * k + 1);
+                const uint32_t cand = ~a[k];
+#pragma unroll
+                for (int f = 0; f < NF; f++) mine |= ((cand >> (31 - FB * f)) & 1u) << (NF * k + f);
             }
         }
     }
@@ -263,20 +274,21 @@ __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32
         }
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (c) {
-            const int p = p_first + (bit >> 1), strand = bit & 1;
+            const int p = p_first + bit / NF, f = bit % NF, strand = f & 1;
+            const int ml = C.lane + 32 * (f >> 1);  // motif slot of the block
             const uint32_t slot = base + (uint32_t)__popc(b & lt);
             if (slot < (uint32_t)kQueueCap) {
-                C.queue[slot] = (uint32_t)p | ((uint32_t)C.lane << 16) | ((uint32_t)strand << 31);
+                C.queue[slot] = (uint32_t)p | ((uint32_t)ml << 16) | ((uint32_t)strand << 31);
             } else {
                 // queue full (flood thresholds): verify right here, divergently
                 int m;
-                float f;
-                if (verify(*C.V, p, C.lane, strand, &m, &f)) {
+                float sc;
+                if (verify(*C.V, p, ml, strand, &m, &sc)) {
                     cg::coalesced_group g = cg::coalesced_threads();
                     unsigned long long hb = 0;
                     if (g.thread_rank() == 0) hb = atomicAdd(C.hit_count, (unsigned long long)g.size());
                     hb = g.shfl(hb, 0);
-                    store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, f);
+                    store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, sc);
                 }
             }
         }
@@ -284,17 +296,18 @@ __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32
     }
 }
 
-// One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 motifs of the
-// resident block.  A, B = 4-column and 3-column groups of the block (compile time, so the 32-entry
-// accumulator ring and all LUT offsets are static).  Group g < A covers columns 4g..4g+3, group
+// One warp scans window starts [seg_begin, seg_end) of the staged tile for the 32 (wide) or 64
+// (NARROW) motifs of the resident block.  A, B = 4-column and 3-column groups of the block (compile
+// time, so the 32-entry accumulator ring and all LUT offsets are static).  Group g < A covers columns 4g..4g+3, group
 // A + j covers columns 4A+3j..4A+3j+2.
-template <int A, int B>
+template <int A, int B, bool NARROW>
 __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s_words, uint32_t lut_lane_addr,
                                              uint32_t kinit)
 {
+    constexpr uint32_t PM = NARROW ? kPoisonNarrow : kPoison;
     uint32_t acc[kRing];
 #pragma unroll
-    for (int i = 0; i < kRing; i++) acc[i] = kPoison;
+    for (int i = 0; i < kRing; i++) acc[i] = PM;
     const uint32_t *wptr = s_words + (C.seg_begin >> 4);
     uint32_t wlo = wptr[0], whi = wptr[1];
     int wk = 2;
@@ -334,12 +347,12 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
             // slot is re-opened 32 - kTail steps later, which bounds kCheck.)  The vote keeps the
             // branch warp-uniform, so the cold path can compact candidates cooperatively.
             if ((j % kCheck) == kCheck - 1) {
-                uint32_t fin[4] = {kPoison, kPoison, kPoison, kPoison};
+                uint32_t fin[4] = {PM, PM, PM, PM};
 #pragma unroll
                 for (int k = 0; k < kCheck; k++) fin[k] = acc[(j - (kCheck - 1 - k) - kTail + 2 * kRing) % kRing];
                 const uint32_t all = fin[0] & fin[1] & fin[2] & fin[3];
-                if (__any_sync(0xFFFFFFFFu, (~all & kPoison) != 0u))
-                    push_group(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail);
+                if (__any_sync(0xFFFFFFFFu, (~all & PM) != 0u))
+                    push_group<NARROW ? 4 : 2>(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail);
             }
             if (jj == 15) {
                 wlo = whi;
@@ -373,9 +386,9 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
     S.qcount = reinterpret_cast<uint32_t *>(p);
     p += kWarps * 4;
     S.motif = reinterpret_cast<int32_t *>(p);
-    p += 32 * 4;
+    p += TFBS_BLOCK_SLOTS * 4;
     S.len = reinterpret_cast<int32_t *>(p);
-    p += 32 * 4;
+    p += TFBS_BLOCK_SLOTS * 4;
     S.bar = reinterpret_cast<uint64_t *>(p);
     p += 16;
     S.item = reinterpret_cast<uint32_t *>(p);
@@ -405,7 +418,7 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         if (tid == 0) {
             // order the previous item's generic-proxy reads before the async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const int chunks = new_block ? 4 * (AB >> 8) + (AB & 255) : 0;  // 8 KB pieces of the table
+            const int chunks = new_block ? 4 * ((AB >> 8) & 255) + (AB & 255) : 0;  // 8 KB pieces of the table
             mbar_expect_tx(S.bar, kTileWords * 4 + kTileMask * 4 + (uint32_t)chunks * 8192u);
             tma_load_1d(S.words, P.packed + (tile_start >> 4), kTileWords * 4, S.bar);
             tma_load_1d(S.mask, P.mask + (tile_start >> 5), kTileMask * 4, S.bar);
@@ -415,8 +428,8 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
             }
         }
         if (new_block) {
-            if (tid < 32) {
-                const int m = __ldg(P.blk_motif + b * 32 + tid);
+            if (tid < TFBS_BLOCK_SLOTS) {
+                const int m = __ldg(P.blk_motif + b * TFBS_BLOCK_SLOTS + tid);
                 S.motif[tid] = m;
                 S.len[tid] = m >= 0 ? __ldg(P.lens + m) : 0;
             }
@@ -447,14 +460,17 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         C.cap = P.cap;
         const uint32_t lut_lane_addr = lut_addr + (uint32_t)lane * 4u;
         switch (AB) {
-#define TFBS_CASE(a, b) \
-    case ((a << 8) | b): scan_segment<a, b>(C, S.words, lut_lane_addr, kinit); break;
-            // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32
-            TFBS_CASE(1, 0) TFBS_CASE(2, 0) TFBS_CASE(3, 0) TFBS_CASE(4, 0) TFBS_CASE(5, 0) TFBS_CASE(6, 0)
-            TFBS_CASE(5, 2) TFBS_CASE(5, 3) TFBS_CASE(5, 4)
+#define TFBS_CASE(a, b, n) \
+    case ((n << 16) | (a << 8) | b): scan_segment<a, b, n != 0>(C, S.words, lut_lane_addr, kinit); break;
+            // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32 ...
+            TFBS_CASE(1, 0, 0) TFBS_CASE(2, 0, 0) TFBS_CASE(3, 0, 0) TFBS_CASE(4, 0, 0) TFBS_CASE(5, 0, 0)
+            TFBS_CASE(6, 0, 0) TFBS_CASE(5, 2, 0) TFBS_CASE(5, 3, 0) TFBS_CASE(5, 4, 0)
+            // ... and the narrow form of those with at most TFBS_NARROW_MAX_GROUPS groups
+            TFBS_CASE(1, 0, 1) TFBS_CASE(2, 0, 1) TFBS_CASE(3, 0, 1) TFBS_CASE(4, 0, 1) TFBS_CASE(5, 0, 1)
+            TFBS_CASE(6, 0, 1) TFBS_CASE(5, 2, 1) TFBS_CASE(5, 3, 1) TFBS_CASE(5, 4, 1)
 #undef TFBS_CASE
             default:  // no instantiation for this grouping: report it instead of silently skipping
-                if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)AB));
+                if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)(AB & 0xFFFF)));
                 break;
         }
         drain_queue(C);
@@ -576,93 +592,199 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
     *B_out = best_b;
 }
 
-// Quantise the block tables for a threshold vector (host).  See the header comment for the
-// construction; everything rounds in the direction that keeps {candidates} a superset of {hits}.
+// ---- block plan + filter tables (host) ------------------------------------------------------------
+// Cost model of the narrow/wide choice, in warp-wide shared-memory loads per window start (measured on
+// B200 at 100 Mb x 800 PWMs, profiles/r01/SUMMARY.md): a candidate handed to the exact verifier costs
+// about as much as 48 loads; a narrow block saves the loads of the second of the two wide blocks it
+// replaces, and its 8-bit fields inflate the candidate count by about kInflation[G].
+constexpr double kCandidateCost = 48.0;
+constexpr double kInflation[TFBS_NARROW_MAX_GROUPS + 1] = {1.0, 1.02, 1.05, 1.15, 1.45, 2.4, 5.2, 11.0, 30.0, 78.0};
+
+// Narrow-block policy from the environment: -1 = cost model (default), 0 = never, g >= 1 = always
+// when the block has at most g groups (A/B measurements and tests).
+static int narrow_override()
+{
+    const char *env = getenv("TFBS_HITS_NARROW");
+    if (!env || env[0] < '0' || env[0] > '9') return -1;
+    return std::min(atoi(env), TFBS_NARROW_MAX_GROUPS);
+}
+
+// Cut `M` motifs (lengths in descending order) into blocks.  At each step the block is sized for its
+// longest motif; if that needs at most TFBS_NARROW_MAX_GROUPS groups and more than 32 motifs are left,
+// accept(first, count, A, B) decides whether the next (up to) 64 motifs form one narrow block.
+// emit(block) is called for every block before the next one is considered.
+template <class Accept, class Emit>
+static void cut_blocks(const int32_t *lens_desc, int M, Accept accept, Emit emit)
+{
+    for (int i = 0; i < M;) {
+        tfbs_hits_block K;
+        tfbs_hits_group_plan(lens_desc[i], &K.A, &K.B);
+        K.first = i;
+        K.narrow = 0;
+        if (K.A + K.B <= TFBS_NARROW_MAX_GROUPS && M - i > 32 && accept(i, std::min(M - i, 64), K.A, K.B)) K.narrow = 1;
+        K.count = std::min(M - i, K.narrow ? 64 : 32);
+        emit(K);
+        i += K.count;
+    }
+}
+
+// Fill the filter table and the initial field values of one block.  `lut` (A * 8192 + B * 2048 words)
+// and kinit (32 words) are overwritten.  Everything rounds in the direction that keeps {candidates} a
+// superset of {hits}.  Returns the expected number of candidates per window start (all fields of the
+// block, uniform i.i.d. bases) for a narrow block, 0 for a wide one (not needed by the cost model).
+static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *motifs, int count, int A, int B,
+                         bool narrow, uint32_t *lut, uint32_t *kinit)
+{
+    const int G = A + B;
+    const int FB = narrow ? 8 : 16;                   // field width
+    const int fmax = (1 << (FB - 1)) - 1;             // 0x7F / 0x7FFF: largest value with the flag bit clear
+    std::fill(lut, lut + (size_t)A * 8192 + (size_t)B * 2048, 0u);
+    for (int lane = 0; lane < 32; lane++) kinit[lane] = narrow ? kPoisonNarrow : kPoison;
+    // group g: first column, width, table offset (words) inside the block table
+    int gcol[2 * kMaxG], gk[2 * kMaxG], goff[2 * kMaxG];
+    for (int g = 0; g < G; g++) {
+        gk[g] = g < A ? 4 : 3;
+        gcol[g] = g < A ? 4 * g : 4 * A + 3 * (g - A);
+        goff[g] = g < A ? g * 256 * 32 : A * 256 * 32 + (g - A) * 64 * 32;
+    }
+    std::vector<double> ent((size_t)G * 256);  // double k-mer partial sums of one (motif, strand)
+    double expected = 0.0;
+    for (int l = 0; l < count; l++) {
+        const int m = motifs[l];
+        const int lane = l & 31, half = l >> 5;
+        const int L = pw->lens[m];
+        const float t = thr[m];
+        for (int s = 0; s < 2; s++) {
+            const int shift = 32 - FB * (2 * half + s + 1);  // wide: fwd 16, rev 0; narrow: 24, 16, 8, 0
+            const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s) * TFBS_MAX_MOTIF_LEN) * 4;
+            double gmax[2 * kMaxG];
+            double best = 0.0;
+            bool reachable = true;
+            int Gm = 0;  // groups that contain at least one column of this motif
+            for (int g = 0; g < G && gcol[g] < L; g++, Gm++) {
+                const int E = 1 << (2 * gk[g]);
+                double mx = -INFINITY;
+                for (int x = 0; x < E; x++) {
+                    double v = 0.0;
+                    for (int j = 0; j < gk[g] && gcol[g] + j < L; j++) v += mat[(gcol[g] + j) * 4 + ((x >> (2 * j)) & 3)];
+                    ent[(size_t)g * 256 + x] = v;
+                    mx = std::max(mx, v);
+                }
+                gmax[g] = mx;
+                best += mx;
+                if (!std::isfinite(mx)) reachable = false;  // a column group of -inf only
+            }
+            // Quantisation steps for the deficit budget.  No carry out of a field needs
+            //   (fmax - Dq) + Gm * capq <= 2 * fmax + 1   with  Dq >= dq_max, capq = dq_max + 2:
+            // wide fields take the block-wide bound, narrow ones the bound of their own Gm.
+            int dq_max;
+            if (!narrow) dq_max = 0x7FFF / G - 3;
+            else dq_max = Gm <= 1 ? 100 : std::min(100, (128 - 2 * Gm) / (Gm - 1));
+            const int capq = dq_max + 2;
+            if (std::isnan(t)) reachable = false;
+            // D: how much a hit may lose against the best possible score (plus slack for the
+            // float rounding of the oracle's comparison and double summation order)
+            double D = reachable ? (best - (double)t) : -1.0;
+            if (reachable && std::isfinite(D)) D += std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(best) * 1e-12 + 1e-9;
+            if (!reachable || D < 0.0) continue;  // field stays poisoned: never a candidate
+            double scale;
+            int Dq;
+            if (std::isinf(D)) {
+                scale = 0.0;  // threshold -inf: everything is a candidate
+                Dq = 1;
+            } else {
+                scale = (double)dq_max / std::max(D, 1e-300);
+                if (!std::isfinite(scale)) scale = 1e300;
+                const double dqv = std::floor(D * scale) + 1.0;
+                Dq = (int)std::min(dqv, (double)(dq_max + 1));
+                Dq = std::max(Dq, dq_max);  // D * scale == dq_max up to rounding; keeps the no-carry bound
+            }
+            kinit[lane] = (kinit[lane] & ~((uint32_t)(2 * fmax + 1) << shift)) | ((uint32_t)(fmax - Dq) << shift);
+            // pass[v]: probability that the quantised deficits of the groups so far sum to v <= Dq
+            double pass[128], next[128];
+            if (narrow) {
+                std::fill(pass, pass + 128, 0.0);
+                pass[0] = 1.0;
+            }
+            for (int g = 0; g < Gm; g++) {
+                const int E = 1 << (2 * gk[g]);
+                double hist[128];
+                if (narrow) std::fill(hist, hist + 128, 0.0);
+                for (int x = 0; x < E; x++) {
+                    const double d = gmax[g] - ent[(size_t)g * 256 + x];  // >= 0, +inf for -inf entries
+                    int q;
+                    if (scale == 0.0) q = 0;
+                    else {
+                        const double v = std::floor(d * scale);
+                        q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
+                    }
+                    lut[(size_t)goff[g] + (size_t)x * 32 + lane] |= (uint32_t)q << shift;
+                    if (narrow && q <= Dq) hist[q] += 1.0 / E;
+                }
+                if (narrow) {
+                    std::fill(next, next + Dq + 1, 0.0);
+                    for (int v = 0; v <= Dq; v++)
+                        if (pass[v] > 0.0)
+                            for (int q = 0; v + q <= Dq; q++) next[v + q] += pass[v] * hist[q];
+                    std::copy(next, next + Dq + 1, pass);
+                }
+            }
+            if (narrow)
+                for (int v = 0; v <= Dq; v++) expected += pass[v];
+        }
+    }
+    return narrow ? expected : 0.0;
+}
+
+// Plan the blocks and quantise their tables for a threshold vector; cached per threshold vector.
 int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
 {
     const int M = pw->M;
     if (pw->hq_valid && pw->hq_thr.size() == (size_t)M && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * M) == 0)
         return TFBS_OK;
-    const int nb = pw->n_blocks;
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
-    std::vector<uint32_t> kinit((size_t)nb * 32, kPoison);
-    std::vector<double> ent;  // double k-mer partial sums of one (motif, strand): [group][4^k]
-    for (int b = 0; b < nb; b++) {
-        const int A = pw->blk_A[b], B = pw->blk_B[b], G = A + B;
-        uint32_t *lut = qlut.data() + pw->blk_lut_off[b];
-        const int dq_max = 0x7FFF / G - 3;
-        const int capq = dq_max + 2;
-        // group g: first column, width, table offset (words) inside the block table
-        int gcol[2 * kMaxG], gk[2 * kMaxG], goff[2 * kMaxG];
-        for (int g = 0; g < G; g++) {
-            gk[g] = g < A ? 4 : 3;
-            gcol[g] = g < A ? 4 * g : 4 * A + 3 * (g - A);
-            goff[g] = g < A ? g * 256 * 32 : A * 256 * 32 + (g - A) * 64 * 32;
-        }
-        for (int l = 0; l < 32; l++) {
-            const int m = pw->blk_motif[(size_t)b * 32 + l];
-            if (m < 0) continue;
-            const int L = pw->lens[m];
-            const float t = thr[m];
-            uint32_t kfield[2] = {0x8000u, 0x8000u};
-            for (int s = 0; s < 2; s++) {
-                const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s) * TFBS_MAX_MOTIF_LEN) * 4;
-                ent.assign((size_t)G * 256, 0.0);
-                double gmax[2 * kMaxG];
-                double best = 0.0;
-                bool reachable = true;
-                int Gm = 0;  // groups that contain at least one column of this motif
-                for (int g = 0; g < G && gcol[g] < L; g++, Gm++) {
-                    const int E = 1 << (2 * gk[g]);
-                    double mx = -INFINITY;
-                    for (int x = 0; x < E; x++) {
-                        double v = 0.0;
-                        for (int j = 0; j < gk[g] && gcol[g] + j < L; j++) v += mat[(gcol[g] + j) * 4 + ((x >> (2 * j)) & 3)];
-                        ent[(size_t)g * 256 + x] = v;
-                        mx = std::max(mx, v);
-                    }
-                    gmax[g] = mx;
-                    best += mx;
-                    if (!std::isfinite(mx)) reachable = false;  // a column group of -inf only
-                }
-                if (std::isnan(t)) reachable = false;
-                // D: how much a hit may lose against the best possible score (plus slack for the
-                // float rounding of the oracle's comparison and double summation order)
-                double D = reachable ? (best - (double)t) : -1.0;
-                if (reachable && std::isfinite(D)) D += std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(best) * 1e-12 + 1e-9;
-                if (!reachable || D < 0.0) continue;  // field stays poisoned: never a candidate
-                double scale;
-                int Dq;
-                if (std::isinf(D)) {
-                    scale = 0.0;  // threshold -inf: everything is a candidate
-                    Dq = 1;
-                } else {
-                    scale = (double)dq_max / std::max(D, 1e-300);
-                    if (!std::isfinite(scale)) scale = 1e300;
-                    const double dqv = std::floor(D * scale) + 1.0;
-                    Dq = (int)std::min(dqv, (double)(dq_max + 1));
-                }
-                kfield[s] = (uint32_t)(0x7FFF - Dq);
-                for (int g = 0; g < Gm; g++) {
-                    const int E = 1 << (2 * gk[g]);
-                    for (int x = 0; x < E; x++) {
-                        const double d = gmax[g] - ent[(size_t)g * 256 + x];  // >= 0, +inf for -inf entries
-                        int q;
-                        if (scale == 0.0) q = 0;
-                        else {
-                            const double v = std::floor(d * scale);
-                            q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
-                        }
-                        uint32_t &w = lut[(size_t)goff[g] + (size_t)x * 32 + l];
-                        w |= s == 0 ? ((uint32_t)q << 16) : (uint32_t)q;
-                    }
-                }
-            }
-            kinit[(size_t)b * 32 + l] = (kfield[0] << 16) | kfield[1];
-        }
-    }
-    cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), qlut.size() * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), kinit.size() * 4, cudaMemcpyHostToDevice);
+    std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
+    const int force = narrow_override();
+    int64_t words = 0;   // table words of the blocks emitted so far
+    int nb = 0;
+    const int32_t *order = pw->order.data();
+    // the narrow form of a block is built in place; a rejected one is overwritten by the wide form below
+    auto accept = [&](int first, int count, int A, int B) -> bool {
+        if (force == 0) return false;
+        const double cand = fill_block(pw, thr, order + first, count, A, B, true, qlut.data() + words, kinit.data() + (size_t)nb * 32);
+        const int G = A + B;
+        if (force > 0) return G <= force;
+        // loads saved per window = the groups of the second wide block this narrow block absorbs
+        int A2 = 0, B2 = 1;
+        tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
+        return kCandidateCost * cand * (1.0 - 1.0 / kInflation[G]) < (double)(A2 + B2);
+    };
+    pw->blk_A.clear();
+    pw->blk_B.clear();
+    pw->blk_narrow.clear();
+    pw->blk_count.clear();
+    pw->blk_lut_off.clear();
+    pw->blk_motif.assign((size_t)pw->n_blocks_max * TFBS_BLOCK_SLOTS, -1);
+    std::vector<int32_t> blk_AB;
+    cut_blocks(pw->lens_desc.data(), M, accept, [&](const tfbs_hits_block &K) {
+        if (!K.narrow)
+            fill_block(pw, thr, order + K.first, K.count, K.A, K.B, false, qlut.data() + words, kinit.data() + (size_t)nb * 32);
+        for (int l = 0; l < K.count; l++) pw->blk_motif[(size_t)nb * TFBS_BLOCK_SLOTS + l] = order[K.first + l];
+        pw->blk_A.push_back(K.A);
+        pw->blk_B.push_back(K.B);
+        pw->blk_narrow.push_back(K.narrow);
+        pw->blk_count.push_back(K.count);
+        pw->blk_lut_off.push_back((int32_t)words);
+        blk_AB.push_back((K.narrow << 16) | (K.A << 8) | K.B);
+        words += (int64_t)K.A * 8192 + (int64_t)K.B * 2048;
+        nb++;
+    });
+    pw->n_blocks = nb;
+    cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), (size_t)words * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), (size_t)nb * 32 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_AB_dev, blk_AB.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_lut_off_dev, pw->blk_lut_off.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_motif_dev, pw->blk_motif.data(), (size_t)nb * TFBS_BLOCK_SLOTS * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;
@@ -877,6 +999,46 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     return TFBS_OK;
 }
 
+
+// Test hook (host only): the blocks a library of the given motif lengths (any order) is cut into when
+// every block of at most `narrow_max_groups` column groups is taken in narrow form (the scan itself
+// decides per block from the thresholds, see tfbs_pwms_hits_blocks).
+// out[b] = {A, B, narrow, motifs in the block}; at most M blocks are written.
+extern "C" int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_max_groups, int32_t *out,
+                                          int32_t *n_blocks)
+{
+    if (!lens || !out || !n_blocks || M < 1) return TFBS_ERR_INVALID;
+    std::vector<int32_t> d(lens, lens + M);
+    for (int32_t L : d)
+        if (L < 1 || L > TFBS_MAX_MOTIF_LEN) return TFBS_ERR_INVALID;
+    std::stable_sort(d.begin(), d.end(), [](int a, int b) { return a > b; });
+    int nb = 0;
+    cut_blocks(d.data(), M, [&](int, int, int A, int B) { return A + B <= narrow_max_groups; },
+               [&](const tfbs_hits_block &K) {
+                   out[4 * nb + 0] = K.A;
+                   out[4 * nb + 1] = K.B;
+                   out[4 * nb + 2] = K.narrow;
+                   out[4 * nb + 3] = K.count;
+                   nb++;
+               });
+    *n_blocks = nb;
+    return TFBS_OK;
+}
+
+// The blocks the last tfbs_scan_hits / tfbs_scan_hits_host call on this library used (chosen per
+// threshold vector by the cost model): out[b] = {A, B, narrow, motifs}; `cap` = blocks `out` can hold.
+extern "C" int tfbs_pwms_hits_blocks(const tfbs_pwms *pwms, int32_t *out, int32_t cap, int32_t *n_blocks)
+{
+    if (!pwms || !n_blocks) return TFBS_ERR_INVALID;
+    *n_blocks = pwms->hq_valid ? pwms->n_blocks : 0;
+    for (int b = 0; out && b < *n_blocks && b < cap; b++) {
+        out[4 * b + 0] = pwms->blk_A[b];
+        out[4 * b + 1] = pwms->blk_B[b];
+        out[4 * b + 2] = pwms->blk_narrow[b];
+        out[4 * b + 3] = pwms->blk_count[b];
+    }
+    return TFBS_OK;
+}
 
 // Test hook (host only): the column grouping the hits kernel uses for a block whose longest motif
 // has L columns.

@@ -146,6 +146,11 @@ int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, co
 int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
                         const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
                         int32_t chunks, int32_t sorted, int64_t *n_hits);
+/* The blocks the last hits scan of this library used: narrow (64 motifs, 8-bit filter fields) or wide
+ * (32 motifs, 16-bit) is chosen per block from the thresholds by a cost model (expected candidates
+ * against shared-memory loads saved).  out[4b..4b+3] = {A, B, narrow, motifs}; `cap` = blocks `out`
+ * holds (out may be NULL to query *n_blocks).  Diagnostics for bench.py's shared-memory roofline. */
+int tfbs_pwms_hits_blocks(const tfbs_pwms *pwms, int32_t *out, int32_t cap, int32_t *n_blocks);
 
 /* ---- (3) DNA-shape pentamer lookup -----------------------------------------------------
  * Replaces DNAshapeR getShape()/getDNAShape() (get_DNA_shapes.R:23-25,
@@ -208,6 +213,12 @@ int tfbs_debug_swar4(uint32_t four_ascii_bytes, uint32_t *codes8, uint32_t *vali
 /* Column grouping of the hits kernel for a motif block of maximum length L: A groups of 4 columns
  * + B groups of 3 (the kernel is instantiated for every pair this can return for L = 1..32). */
 int tfbs_debug_hits_group_plan(int32_t L, int32_t *A, int32_t *B);
+/* Blocks the hits kernel cuts a library of M motif lengths (any order) into, longest first, when every
+ * block of at most narrow_max_groups column groups is taken in narrow form:
+ * out[4b..4b+3] = {A, B, narrow, motifs in block b}; `out` holds 4 * M int32, *n_blocks is set.
+ * A narrow block carries 64 motifs (8-bit filter fields), a wide block 32 (16-bit fields). */
+int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_max_groups, int32_t *out,
+                               int32_t *n_blocks);
 
 #ifdef __cplusplus
 }

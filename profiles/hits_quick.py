@@ -20,10 +20,17 @@ print("parity ok on 300 kb:", cnt, "hits")
 n = 100_000_000
 dev = ctx.synth_ascii(39, 0, n, gc=0.41)
 enc = ctx.encode_device(dev.ptr, n)
-ms = []
-for i in range(4):
-    ctx.flush_l2()
-    hits = ctx.scan_hits(enc, lib, thr, cap=1 << 25, to_host=False)
-    ms.append(ctx.last_kernel_ms())
 units = sum(n - int(L) + 1 for L in lens)
-print(f"scan_hits: {min(ms):.2f} ms (all {[round(m,2) for m in ms]}), {units / min(ms) / 1e6:.1f} G units/s, hits {hits}, candidates {ctx.last_scan_candidates()}")
+for narrow in ("", "6", "9", "0"):  # cost model (default); narrow blocks forced up to 6 / 9 groups; wide only
+    os.environ.pop("TFBS_HITS_NARROW", None)
+    if narrow:
+        os.environ["TFBS_HITS_NARROW"] = narrow
+    lib2 = ctx.upload_pwms(logodds, lens)
+    ms = []
+    for i in range(4):
+        ctx.flush_l2()
+        hits = ctx.scan_hits(enc, lib2, thr, cap=1 << 25, to_host=False)
+        ms.append(ctx.last_kernel_ms())
+    print(f"scan_hits narrow={narrow}: {min(ms):.2f} ms (all {[round(m,2) for m in ms]}), {units / min(ms) / 1e6:.1f} G units/s, "
+          f"hits {hits}, candidates {ctx.last_scan_candidates()}")
+    lib2.close()

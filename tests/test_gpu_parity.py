@@ -666,3 +666,83 @@ def test_hits_fuzz_against_oracle(ctx):
         assert ok, (case, n, M, lmin, lmax, rate, hits.size, cnt)
         enc.close()
         lib.close()
+
+
+@pytest.mark.parametrize("kind", ["rate", "flood", "minus_inf"])
+def test_hits_narrow_blocks_equal_wide_blocks_and_oracle(ctx, kind, monkeypatch):
+    """Libraries of more than 32 short motifs may be scanned in NARROW blocks (64 motifs, 8-bit filter
+    fields).  The hit set must stay bit-exact against the oracle and identical to the wide-block
+    scan, while the coarser filter may only ADD candidates.  TFBS_HITS_NARROW forces the form
+    (9 = narrow wherever more than 32 motifs are left, 0 = never); unset, a cost model decides."""
+    rng = np.random.default_rng(64)
+    M = 150
+    logodds, lens = synth.pwm_library(640, M, lmin=3, lmax=32)
+    seq = synth.genome(64, 123_456_789, 70_000)
+    seq[30_000:30_050] = ord("N")
+    if kind == "minus_inf":
+        logodds = np.where(rng.random(logodds.shape) < 0.03, -np.inf, logodds)
+    if kind == "flood":
+        seq = seq[:3000]
+        thr = np.full(M, -1e30, np.float32)
+        thr[::3] = 1e30
+    else:
+        thr = synth.thresholds_for_rate(np.where(np.isinf(logodds), -20.0, logodds), lens, rate=1e-3, sample=20_000)
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+    enc = ctx.encode(seq)
+    results = {}
+    for narrow in ("9", "0", None):
+        if narrow is None:
+            monkeypatch.delenv("TFBS_HITS_NARROW", raising=False)
+        else:
+            monkeypatch.setenv("TFBS_HITS_NARROW", narrow)
+        lib = ctx.upload_pwms(logodds, lens)
+        assert lib.hits_blocks() == []
+        hits = ctx.scan_hits(enc, lib, thr, cap=1 << 20, sort=True)
+        results[narrow] = (hits.copy(), ctx.last_scan_candidates(), lib.hits_blocks())
+        lib.close()
+    enc.close()
+    hits, cand_narrow, blocks_narrow = results["9"]
+    wide, cand_wide, blocks_wide = results["0"]
+    auto, cand_auto, blocks_auto = results[None]
+    assert blocks_narrow == _lib.hits_block_plan(lens, 9) and sum(b[2] for b in blocks_narrow) == 2
+    assert blocks_wide == _lib.hits_block_plan(lens, 0) and len(blocks_wide) == (M + 31) // 32
+    assert sum(b[3] for b in blocks_auto) == M
+    assert hits.size == cnt and cnt > 0
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    assert np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
+    assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
+    assert np.array_equal(hits["score"], score)
+    assert np.array_equal(hits, wide) and np.array_equal(hits, auto)
+    if kind == "flood":
+        # everything is a candidate: the cost model must not pick the coarser filter
+        assert not any(b[2] for b in blocks_auto)
+    else:  # (inline verification of a full queue is not counted, so only compare below flood level)
+        assert cand_narrow >= cand_auto >= cand_wide >= cnt
+
+
+def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
+    """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
+    narrow blocks for the short motifs; the plan follows the thresholds of each call."""
+    monkeypatch.delenv("TFBS_HITS_NARROW", raising=False)
+    logodds, lens = synth.pwm_library(641, 200, lmin=6, lmax=30)
+    seq = synth.genome(65, 1_000_000, 50_000)
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    sparse = synth.thresholds_for_rate(logodds, lens, rate=1e-4, sample=50_000)
+    h1 = ctx.scan_hits(enc, lib, sparse, sort=True)
+    plan_sparse = lib.hits_blocks()
+    dense = synth.thresholds_for_rate(logodds, lens, rate=3e-2, sample=20_000)
+    ctx.scan_hits(enc, lib, dense, cap=1 << 22, sort=False)
+    plan_dense = lib.hits_blocks()
+    h3 = ctx.scan_hits(enc, lib, sparse, sort=True)  # back to the first thresholds: same plan, same hits
+    assert lib.hits_blocks() == plan_sparse and np.array_equal(h1, h3)
+    assert any(b[2] for b in plan_sparse)
+    assert sum(b[2] for b in plan_dense) < sum(b[2] for b in plan_sparse)
+    for a, b, narrow, count in plan_sparse:
+        assert count <= (64 if narrow else 32)
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, sparse)
+    assert h1.size == cnt and np.array_equal(h1["score"], score) and np.array_equal(h1["motif"], mot)
+    enc.close()
+    lib.close()

@@ -173,10 +173,14 @@ def test_tokens_to_values_rule():
 def test_hits_group_plan_is_covered_by_kernel_instantiations():
     """Every (A, B) the planner can return for L = 1..32 must have a scan_segment<A, B> case."""
     src = open(os.path.join(ROOT, "discover_tfbs_b200", "csrc", "scan_hits.cu")).read()
-    cases = {(int(a), int(b)) for a, b in re.findall(r"TFBS_CASE\((\d+), (\d+)\)", src)}
+    cases = {(int(a), int(b), int(n)) for a, b, n in re.findall(r"TFBS_CASE\((\d+), (\d+), (\d+)\)", src)}
+    narrow_max = int(re.search(r"#define TFBS_NARROW_MAX_GROUPS (\d+)",
+                               open(os.path.join(ROOT, "discover_tfbs_b200", "csrc", "common.cuh")).read()).group(1))
     for L in range(1, 33):
         a, b = _lib.hits_group_plan(L)
-        assert 4 * a + 3 * b >= L and 32 * a + 8 * b <= 192 and (a, b) in cases, (L, a, b)
+        assert 4 * a + 3 * b >= L and 32 * a + 8 * b <= 192 and (a, b, 0) in cases, (L, a, b)
+        if a + b <= narrow_max:  # such blocks may be scanned in narrow form (64 motifs, 8-bit fields)
+            assert (a, b, 1) in cases, (L, a, b)
         # optimal: no admissible grouping with fewer loads
         assert all(not (4 * x + 3 * y >= L and 32 * x + 8 * y <= 192 and 1 <= x + y < a + b)
                    for x in range(7) for y in range(12))
@@ -209,3 +213,27 @@ T  [11  1  1  1 24  0 ]
         thr = pssm.threshold_fpr(lo, fpr, precision=2000)
         achieved = (brute >= thr).mean()
         assert achieved <= fpr * 1.05 + 1e-3 and achieved >= fpr * 0.3 - 1e-3, (fpr, achieved)
+
+
+def test_hits_block_plan_covers_every_motif_once():
+    """Block cutting (host logic of the hits-table builder): narrow blocks only up to the given group
+    limit and only while more than 32 motifs are left; every motif lands in exactly one block."""
+    rng = np.random.default_rng(5)
+    for M in (1, 31, 32, 33, 64, 65, 97, 800):
+        lens = rng.integers(1, 33, size=M)
+        for limit in (0, 3, 5, 6, 9):
+            blocks = _lib.hits_block_plan(lens, limit)
+            assert sum(b[3] for b in blocks) == M
+            srt = np.sort(lens)[::-1]
+            i = 0
+            for a, b, narrow, count in blocks:
+                assert (a, b) == _lib.hits_group_plan(int(srt[i]))  # sized for the longest motif of the block
+                assert count == min(M - i, 64 if narrow else 32)
+                assert bool(narrow) == (a + b <= limit and M - i > 32)
+                i += count
+    assert _lib.hits_block_plan([8] * 100, 5) == [(2, 0, 1, 64), (2, 0, 1, 36)]
+    assert _lib.hits_block_plan([30] * 40, 6) == [(5, 4, 0, 32), (5, 4, 0, 8)]
+    assert _lib.hits_block_plan([30] * 40, 9) == [(5, 4, 1, 40)]
+    assert _lib.hits_block_plan([8] * 100, 0) == [(2, 0, 0, 32)] * 3 + [(2, 0, 0, 4)]
+    assert _lib.hits_block_plan([24] * 100, 99) == [(6, 0, 1, 64), (6, 0, 1, 36)]
+    assert _lib.hits_block_plan([25] * 100, 6)[0] == (5, 2, 0, 32)
