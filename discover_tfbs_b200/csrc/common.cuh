@@ -120,9 +120,10 @@ int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
 // One block of the hits-mode plan: A 4-column + B 3-column groups, narrow (64 motifs, 8-bit fields)
 // or wide (32 motifs, 16-bit fields), motifs [first, first + count) of the length-sorted order.
-struct tfbs_hits_block { int A, B, narrow, first, count; };
+struct tfbs_hits_block { int A, B, narrow /* 0 wide, 1 narrow, 2 sticky narrow */, first, count; };
 #define TFBS_BLOCK_SLOTS 64          // motif slots per hits-mode block (32 used by a wide block)
 #define TFBS_NARROW_MAX_GROUPS 9     // narrow blocks: 8-bit fields leave (128 - 2G) / (G - 1) quantisation steps
+#define TFBS_STICKY_MIN_GROUPS 5     // sticky narrow blocks (flag bits masked out of every add) from 5 groups on
 int tfbs_encode_range(tfbs_ctx *ctx, const void *ascii_dev, int64_t valid, tfbs_seq *s, int64_t base,
                       int64_t cover, cudaStream_t stream);
 

@@ -28,8 +28,13 @@
 //     shared-memory traffic per motif — the resource this kernel is bound by.  Only
 //     (128 - 2G) / (G - 1) quantisation steps fit without carries, so the filter is coarser (1.1x the
 //     candidates at G = 3, 2.4x at G = 5, 78x at G = 9; profiles/field8_simulation.py) and the exact
-//     verifier, which keeps the hit set bit-exact, has more to do.  Narrow or wide is therefore
-//     chosen per block and per threshold vector by a cost model (tfbs_build_hits_tables).
+//     verifier, which keeps the hit set bit-exact, has more to do.
+//   * STICKY narrow blocks (5 or more groups): the flag bits are masked out before every add and OR-ed
+//     back (acc = ((acc & 0x7F7F7F7F) + v) | (acc & 0x80808080), two more ALU ops per load, still
+//     under the issue budget of a load-bound loop), so fields can never carry and all 126 steps are
+//     usable whatever G is: the 8-bit filter is then almost as sharp as the 16-bit one.
+//     Wide, narrow or sticky is chosen per block and per threshold vector by a cost model
+//     (tfbs_build_hits_tables).
 //   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
 //     block-major order, so a CTA re-loads its table (up to 192 KB) only when the block changes.
 #include <algorithm>
@@ -68,7 +73,7 @@ struct HitsParams {
     int32_t n_blocks;
     const uint32_t *qlut;        // per block [A][256][32] then [B][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
-    const int32_t *blk_AB;       // [n_blocks] (narrow << 16) | (A << 8) | B: 4- and 3-column groups of the block
+    const int32_t *blk_AB;       // [n_blocks] (mode << 16) | (A << 8) | B: 4- and 3-column groups of the block
     const uint32_t *kinit;       // [n_blocks][32] initial field values per lane (0x7FFF - Dq or 0x7F - Dq each)
     const int32_t *blk_motif;    // [n_blocks][64] original motif index or -1 (slot = lane + 32 * half)
     const int32_t *lens;         // [M]
@@ -300,10 +305,11 @@ __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32
 // (NARROW) motifs of the resident block.  A, B = 4-column and 3-column groups of the block (compile
 // time, so the 32-entry accumulator ring and all LUT offsets are static).  Group g < A covers columns 4g..4g+3, group
 // A + j covers columns 4A+3j..4A+3j+2.
-template <int A, int B, bool NARROW>
+template <int A, int B, int MODE>
 __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s_words, uint32_t lut_lane_addr,
                                              uint32_t kinit)
 {
+    constexpr bool NARROW = MODE != 0, STICKY = MODE == 2;
     constexpr uint32_t PM = NARROW ? kPoisonNarrow : kPoison;
     uint32_t acc[kRing];
 #pragma unroll
@@ -329,6 +335,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                     const uint32_t v = lds32(addr4 + g * 32768);
                     const int slot = (j - 4 * g + 2 * kRing) % kRing;
                     if (g == 0) acc[slot] = kinit + v;
+                    else if (STICKY) acc[slot] = ((acc[slot] & ~PM) + v) | (acc[slot] & PM);
                     else acc[slot] += v;
                 }
             }
@@ -339,6 +346,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                     const uint32_t v = lds32(addr3 + g * 8192);
                     const int slot = (j - 4 * A - 3 * g + 2 * kRing) % kRing;
                     if (A == 0 && g == 0) acc[slot] = kinit + v;
+                    else if (STICKY) acc[slot] = ((acc[slot] & ~PM) + v) | (acc[slot] & PM);
                     else acc[slot] += v;
                 }
             }
@@ -461,13 +469,16 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         const uint32_t lut_lane_addr = lut_addr + (uint32_t)lane * 4u;
         switch (AB) {
 #define TFBS_CASE(a, b, n) \
-    case ((n << 16) | (a << 8) | b): scan_segment<a, b, n != 0>(C, S.words, lut_lane_addr, kinit); break;
+    case ((n << 16) | (a << 8) | b): scan_segment<a, b, n>(C, S.words, lut_lane_addr, kinit); break;
             // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32 ...
             TFBS_CASE(1, 0, 0) TFBS_CASE(2, 0, 0) TFBS_CASE(3, 0, 0) TFBS_CASE(4, 0, 0) TFBS_CASE(5, 0, 0)
             TFBS_CASE(6, 0, 0) TFBS_CASE(5, 2, 0) TFBS_CASE(5, 3, 0) TFBS_CASE(5, 4, 0)
             // ... and the narrow form of those with at most TFBS_NARROW_MAX_GROUPS groups
             TFBS_CASE(1, 0, 1) TFBS_CASE(2, 0, 1) TFBS_CASE(3, 0, 1) TFBS_CASE(4, 0, 1) TFBS_CASE(5, 0, 1)
             TFBS_CASE(6, 0, 1) TFBS_CASE(5, 2, 1) TFBS_CASE(5, 3, 1) TFBS_CASE(5, 4, 1)
+            // ... and the sticky narrow form (flag bits kept by masking, 126 quantisation steps) of
+            // those with at least TFBS_STICKY_MIN_GROUPS groups
+            TFBS_CASE(5, 0, 2) TFBS_CASE(6, 0, 2) TFBS_CASE(5, 2, 2) TFBS_CASE(5, 3, 2) TFBS_CASE(5, 4, 2)
 #undef TFBS_CASE
             default:  // no instantiation for this grouping: report it instead of silently skipping
                 if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)(AB & 0xFFFF)));
@@ -593,25 +604,30 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 }
 
 // ---- block plan + filter tables (host) ------------------------------------------------------------
-// Cost model of the narrow/wide choice, in warp-wide shared-memory loads per window start (measured on
-// B200 at 100 Mb x 800 PWMs, profiles/r01/SUMMARY.md): a candidate handed to the exact verifier costs
-// about as much as 48 loads; a narrow block saves the loads of the second of the two wide blocks it
-// replaces, and its 8-bit fields inflate the candidate count by about kInflation[G].
-constexpr double kCandidateCost = 48.0;
-constexpr double kInflation[TFBS_NARROW_MAX_GROUPS + 1] = {1.0, 1.02, 1.05, 1.15, 1.45, 2.4, 5.2, 11.0, 30.0, 78.0};
+// Cost model of the block form, in warp-wide shared-memory loads per window start, fitted to B200
+// measurements at 100 Mb x 800 PWMs and hit rates 1e-6 .. 1e-2 (profiles/r01/SUMMARY.md): one load
+// costs 4.1 ps per window; a candidate handed to the exact verifier costs 0.15 / 0.27 / 0.40 ns in a
+// wide / narrow / sticky block (the denser the loop, the less slack hides the cold path); a load of
+// the sticky form costs 1.3 plain loads (two more ALU ops each).  A narrow block of G groups replaces
+// two wide blocks of G and G2 groups.
+constexpr double kCandidateCost[3] = {37.0, 66.0, 98.0};
+constexpr double kStickyLoad = 1.30;
+enum { kWide = 0, kNarrow = 1, kSticky = 2 };
 
-// Narrow-block policy from the environment: -1 = cost model (default), 0 = never, g >= 1 = always
-// when the block has at most g groups (A/B measurements and tests).
-static int narrow_override()
+// Block form forced from the environment (A/B measurements and tests); -1 = cost model (default).
+//   TFBS_HITS_NARROW=<g>  plain narrow blocks wherever the block has at most g groups (0 = never)
+//   TFBS_HITS_STICKY=<g>  sticky narrow blocks wherever the block has at least g groups (>= 5)
+static int env_int(const char *name)
 {
-    const char *env = getenv("TFBS_HITS_NARROW");
+    const char *env = getenv(name);
     if (!env || env[0] < '0' || env[0] > '9') return -1;
-    return std::min(atoi(env), TFBS_NARROW_MAX_GROUPS);
+    return atoi(env);
 }
 
 // Cut `M` motifs (lengths in descending order) into blocks.  At each step the block is sized for its
 // longest motif; if that needs at most TFBS_NARROW_MAX_GROUPS groups and more than 32 motifs are left,
-// accept(first, count, A, B) decides whether the next (up to) 64 motifs form one narrow block.
+// accept(first, count, A, B) decides whether the next (up to) 64 motifs form one narrow block
+// (returns kNarrow or kSticky) or a wide one (kWide, the first 32 of them).
 // emit(block) is called for every block before the next one is considered.
 template <class Accept, class Emit>
 static void cut_blocks(const int32_t *lens_desc, int M, Accept accept, Emit emit)
@@ -620,8 +636,8 @@ static void cut_blocks(const int32_t *lens_desc, int M, Accept accept, Emit emit
         tfbs_hits_block K;
         tfbs_hits_group_plan(lens_desc[i], &K.A, &K.B);
         K.first = i;
-        K.narrow = 0;
-        if (K.A + K.B <= TFBS_NARROW_MAX_GROUPS && M - i > 32 && accept(i, std::min(M - i, 64), K.A, K.B)) K.narrow = 1;
+        K.narrow = kWide;
+        if (K.A + K.B <= TFBS_NARROW_MAX_GROUPS && M - i > 32) K.narrow = accept(i, std::min(M - i, 64), K.A, K.B);
         K.count = std::min(M - i, K.narrow ? 64 : 32);
         emit(K);
         i += K.count;
@@ -631,11 +647,12 @@ static void cut_blocks(const int32_t *lens_desc, int M, Accept accept, Emit emit
 // Fill the filter table and the initial field values of one block.  `lut` (A * 8192 + B * 2048 words)
 // and kinit (32 words) are overwritten.  Everything rounds in the direction that keeps {candidates} a
 // superset of {hits}.  Returns the expected number of candidates per window start (all fields of the
-// block, uniform i.i.d. bases) for a narrow block, 0 for a wide one (not needed by the cost model).
+// block, uniform i.i.d. bases) for a narrow or sticky block, 0 for a wide one (not needed by the model).
 static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *motifs, int count, int A, int B,
-                         bool narrow, uint32_t *lut, uint32_t *kinit)
+                         int mode, uint32_t *lut, uint32_t *kinit)
 {
     const int G = A + B;
+    const bool narrow = mode != kWide;
     const int FB = narrow ? 8 : 16;                   // field width
     const int fmax = (1 << (FB - 1)) - 1;             // 0x7F / 0x7FFF: largest value with the flag bit clear
     std::fill(lut, lut + (size_t)A * 8192 + (size_t)B * 2048, 0u);
@@ -676,9 +693,11 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
             }
             // Quantisation steps for the deficit budget.  No carry out of a field needs
             //   (fmax - Dq) + Gm * capq <= 2 * fmax + 1   with  Dq >= dq_max, capq = dq_max + 2:
-            // wide fields take the block-wide bound, narrow ones the bound of their own Gm.
+            // wide fields take the block-wide bound, narrow ones the bound of their own Gm.  Sticky
+            // fields cannot carry at all (flag bits are masked out of every add): entries <= 127.
             int dq_max;
-            if (!narrow) dq_max = 0x7FFF / G - 3;
+            if (mode == kWide) dq_max = 0x7FFF / G - 3;
+            else if (mode == kSticky) dq_max = 125;
             else dq_max = Gm <= 1 ? 100 : std::min(100, (128 - 2 * Gm) / (Gm - 1));
             const int capq = dq_max + 2;
             if (std::isnan(t)) reachable = false;
@@ -744,20 +763,39 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         return TFBS_OK;
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
-    const int force = narrow_override();
+    const int force_narrow = env_int("TFBS_HITS_NARROW"), force_sticky = env_int("TFBS_HITS_STICKY");
     int64_t words = 0;   // table words of the blocks emitted so far
     int nb = 0;
     const int32_t *order = pw->order.data();
-    // the narrow form of a block is built in place; a rejected one is overwritten by the wide form below
-    auto accept = [&](int first, int count, int A, int B) -> bool {
-        if (force == 0) return false;
-        const double cand = fill_block(pw, thr, order + first, count, A, B, true, qlut.data() + words, kinit.data() + (size_t)nb * 32);
+    // The candidate forms of a block are built in place (the chosen one last); a wide block is built
+    // by emit below.
+    auto accept = [&](int first, int count, int A, int B) -> int {
         const int G = A + B;
-        if (force > 0) return G <= force;
-        // loads saved per window = the groups of the second wide block this narrow block absorbs
+        uint32_t *lut = qlut.data() + words, *ki = kinit.data() + (size_t)nb * 32;
+        if (force_narrow >= 0 || force_sticky >= 0) {
+            int mode = kWide;
+            if (force_sticky >= 0 && G >= std::max(force_sticky, TFBS_STICKY_MIN_GROUPS)) mode = kSticky;
+            else if (force_narrow >= 0 && G <= force_narrow) mode = kNarrow;
+            if (mode != kWide) fill_block(pw, thr, order + first, count, A, B, mode, lut, ki);
+            return mode;
+        }
+        // groups of the second of the two wide blocks a narrow block replaces
         int A2 = 0, B2 = 1;
         tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
-        return kCandidateCost * cand * (1.0 - 1.0 / kInflation[G]) < (double)(A2 + B2);
+        const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
+        // the sticky filter (126 steps) is nearly as sharp as the 16-bit one: it also estimates the
+        // candidates of the wide form
+        const double c_sticky = fill_block(pw, thr, order + first, count, A, B, kSticky, lut, ki);
+        const double c_narrow = fill_block(pw, thr, order + first, count, A, B, kNarrow, lut, ki);
+        const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.2;
+        const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
+        const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
+        if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) return kNarrow;  // tables are in place
+        if (cost_sticky <= cost_wide) {
+            fill_block(pw, thr, order + first, count, A, B, kSticky, lut, ki);
+            return kSticky;
+        }
+        return kWide;
     };
     pw->blk_A.clear();
     pw->blk_B.clear();
@@ -767,8 +805,8 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     pw->blk_motif.assign((size_t)pw->n_blocks_max * TFBS_BLOCK_SLOTS, -1);
     std::vector<int32_t> blk_AB;
     cut_blocks(pw->lens_desc.data(), M, accept, [&](const tfbs_hits_block &K) {
-        if (!K.narrow)
-            fill_block(pw, thr, order + K.first, K.count, K.A, K.B, false, qlut.data() + words, kinit.data() + (size_t)nb * 32);
+        if (K.narrow == kWide)
+            fill_block(pw, thr, order + K.first, K.count, K.A, K.B, kWide, qlut.data() + words, kinit.data() + (size_t)nb * 32);
         for (int l = 0; l < K.count; l++) pw->blk_motif[(size_t)nb * TFBS_BLOCK_SLOTS + l] = order[K.first + l];
         pw->blk_A.push_back(K.A);
         pw->blk_B.push_back(K.B);
@@ -1013,7 +1051,7 @@ extern "C" int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_
         if (L < 1 || L > TFBS_MAX_MOTIF_LEN) return TFBS_ERR_INVALID;
     std::stable_sort(d.begin(), d.end(), [](int a, int b) { return a > b; });
     int nb = 0;
-    cut_blocks(d.data(), M, [&](int, int, int A, int B) { return A + B <= narrow_max_groups; },
+    cut_blocks(d.data(), M, [&](int, int, int A, int B) { return A + B <= narrow_max_groups ? kNarrow : kWide; },
                [&](const tfbs_hits_block &K) {
                    out[4 * nb + 0] = K.A;
                    out[4 * nb + 1] = K.B;

@@ -21,16 +21,18 @@ n = 100_000_000
 dev = ctx.synth_ascii(39, 0, n, gc=0.41)
 enc = ctx.encode_device(dev.ptr, n)
 units = sum(n - int(L) + 1 for L in lens)
-for narrow in ("", "6", "9", "0"):  # cost model (default); narrow blocks forced up to 6 / 9 groups; wide only
+MODES = {"auto": {}, "narrow": {"TFBS_HITS_NARROW": "9"}, "sticky>=5": {"TFBS_HITS_NARROW": "4", "TFBS_HITS_STICKY": "5"},
+         "wide": {"TFBS_HITS_NARROW": "0"}}  # cost model (default) and the three forced block forms
+for narrow, env in MODES.items():
     os.environ.pop("TFBS_HITS_NARROW", None)
-    if narrow:
-        os.environ["TFBS_HITS_NARROW"] = narrow
+    os.environ.pop("TFBS_HITS_STICKY", None)
+    os.environ.update(env)
     lib2 = ctx.upload_pwms(logodds, lens)
     ms = []
     for i in range(4):
         ctx.flush_l2()
         hits = ctx.scan_hits(enc, lib2, thr, cap=1 << 25, to_host=False)
         ms.append(ctx.last_kernel_ms())
-    print(f"scan_hits narrow={narrow}: {min(ms):.2f} ms (all {[round(m,2) for m in ms]}), {units / min(ms) / 1e6:.1f} G units/s, "
+    print(f"scan_hits {narrow}: {min(ms):.2f} ms (all {[round(m,2) for m in ms]}), {units / min(ms) / 1e6:.1f} G units/s, "
           f"hits {hits}, candidates {ctx.last_scan_candidates()}")
     lib2.close()

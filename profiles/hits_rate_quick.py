@@ -9,10 +9,14 @@ thrs = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hits_ra
 n = 100_000_000
 dev = ctx.synth_ascii(39, 0, n, gc=0.41)
 enc = ctx.encode_device(dev.ptr, n)
-for narrow in ("", "9", "0"):  # cost model (default); narrow forced for every block; wide blocks only
+MODES = {"auto": {}, "narrow": {"TFBS_HITS_NARROW": "9"}, "sticky>=5": {"TFBS_HITS_NARROW": "4", "TFBS_HITS_STICKY": "5"},
+         "wide": {"TFBS_HITS_NARROW": "0"}}  # cost model (default) and the three forced block forms
+for narrow, env in MODES.items():
+    if len(sys.argv) > 1 and narrow not in sys.argv[1:]:
+        continue
     os.environ.pop("TFBS_HITS_NARROW", None)
-    if narrow:
-        os.environ["TFBS_HITS_NARROW"] = narrow
+    os.environ.pop("TFBS_HITS_STICKY", None)
+    os.environ.update(env)
     lib = ctx.upload_pwms(logodds, lens)
     for rate in ("0.01", "0.001", "0.0001", "1e-05", "1e-06"):
         thr = thrs[rate]
@@ -21,6 +25,6 @@ for narrow in ("", "9", "0"):  # cost model (default); narrow forced for every b
             h = ctx.scan_hits(enc, lib, thr, cap=1 << 28, to_host=False)
             ms.append(ctx.last_kernel_ms())
         plan = lib.hits_blocks()
-        print(f"narrow<={narrow or "auto"} rate {rate}: {min(ms):.2f} ms, hits {h}, candidates {ctx.last_scan_candidates()}, "
-              f"blocks {len(plan)} ({sum(b[2] for b in plan)} narrow: groups {sorted(set(b[0] + b[1] for b in plan if b[2]))})", flush=True)
+        print(f"{narrow} rate {rate}: {min(ms):.2f} ms, hits {h}, candidates {ctx.last_scan_candidates()}, "
+              f"blocks {len(plan)} (narrow groups {sorted(b[0] + b[1] for b in plan if b[2] == 1)}, sticky groups {sorted(b[0] + b[1] for b in plan if b[2] == 2)})", flush=True)
     lib.close()

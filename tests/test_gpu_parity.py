@@ -691,10 +691,13 @@ def test_hits_narrow_blocks_equal_wide_blocks_and_oracle(ctx, kind, monkeypatch)
         pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
     enc = ctx.encode(seq)
     results = {}
-    for narrow in ("9", "0", None):
-        if narrow is None:
-            monkeypatch.delenv("TFBS_HITS_NARROW", raising=False)
-        else:
+    for narrow in ("9", "0", "sticky", None):
+        monkeypatch.delenv("TFBS_HITS_NARROW", raising=False)
+        monkeypatch.delenv("TFBS_HITS_STICKY", raising=False)
+        if narrow == "sticky":  # sticky narrow form from 5 groups on, plain narrow below
+            monkeypatch.setenv("TFBS_HITS_NARROW", "4")
+            monkeypatch.setenv("TFBS_HITS_STICKY", "5")
+        elif narrow is not None:
             monkeypatch.setenv("TFBS_HITS_NARROW", narrow)
         lib = ctx.upload_pwms(logodds, lens)
         assert lib.hits_blocks() == []
@@ -705,7 +708,7 @@ def test_hits_narrow_blocks_equal_wide_blocks_and_oracle(ctx, kind, monkeypatch)
     hits, cand_narrow, blocks_narrow = results["9"]
     wide, cand_wide, blocks_wide = results["0"]
     auto, cand_auto, blocks_auto = results[None]
-    assert blocks_narrow == _lib.hits_block_plan(lens, 9) and sum(b[2] for b in blocks_narrow) == 2
+    assert blocks_narrow == _lib.hits_block_plan(lens, 9) and [b[2] for b in blocks_narrow] == [1, 1, 0]
     assert blocks_wide == _lib.hits_block_plan(lens, 0) and len(blocks_wide) == (M + 31) // 32
     assert sum(b[3] for b in blocks_auto) == M
     assert hits.size == cnt and cnt > 0
@@ -714,11 +717,13 @@ def test_hits_narrow_blocks_equal_wide_blocks_and_oracle(ctx, kind, monkeypatch)
     assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
     assert np.array_equal(hits["score"], score)
     assert np.array_equal(hits, wide) and np.array_equal(hits, auto)
+    sticky, cand_sticky, blocks_sticky = results["sticky"]
+    assert [b[2] for b in blocks_sticky] == [2, 2, 0] and np.array_equal(hits, sticky)
     if kind == "flood":
         # everything is a candidate: the cost model must not pick the coarser filter
         assert not any(b[2] for b in blocks_auto)
     else:  # (inline verification of a full queue is not counted, so only compare below flood level)
-        assert cand_narrow >= cand_auto >= cand_wide >= cnt
+        assert cand_narrow >= cand_sticky >= cand_wide >= cnt and cand_narrow >= cand_auto >= cand_wide
 
 
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
@@ -738,7 +743,7 @@ def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypat
     h3 = ctx.scan_hits(enc, lib, sparse, sort=True)  # back to the first thresholds: same plan, same hits
     assert lib.hits_blocks() == plan_sparse and np.array_equal(h1, h3)
     assert any(b[2] for b in plan_sparse)
-    assert sum(b[2] for b in plan_dense) < sum(b[2] for b in plan_sparse)
+    assert sum(1 for b in plan_dense if b[2]) < sum(1 for b in plan_sparse if b[2])
     for a, b, narrow, count in plan_sparse:
         assert count <= (64 if narrow else 32)
     with np.errstate(invalid="ignore"):

@@ -176,11 +176,15 @@ def test_hits_group_plan_is_covered_by_kernel_instantiations():
     cases = {(int(a), int(b), int(n)) for a, b, n in re.findall(r"TFBS_CASE\((\d+), (\d+), (\d+)\)", src)}
     narrow_max = int(re.search(r"#define TFBS_NARROW_MAX_GROUPS (\d+)",
                                open(os.path.join(ROOT, "discover_tfbs_b200", "csrc", "common.cuh")).read()).group(1))
+    sticky_min = int(re.search(r"#define TFBS_STICKY_MIN_GROUPS (\d+)",
+                               open(os.path.join(ROOT, "discover_tfbs_b200", "csrc", "common.cuh")).read()).group(1))
     for L in range(1, 33):
         a, b = _lib.hits_group_plan(L)
         assert 4 * a + 3 * b >= L and 32 * a + 8 * b <= 192 and (a, b, 0) in cases, (L, a, b)
         if a + b <= narrow_max:  # such blocks may be scanned in narrow form (64 motifs, 8-bit fields)
             assert (a, b, 1) in cases, (L, a, b)
+        if a + b >= sticky_min:  # ... and these in the sticky narrow form
+            assert (a, b, 2) in cases, (L, a, b)
         # optimal: no admissible grouping with fewer loads
         assert all(not (4 * x + 3 * y >= L and 32 * x + 8 * y <= 192 and 1 <= x + y < a + b)
                    for x in range(7) for y in range(12))
