@@ -381,7 +381,7 @@ def run_ours(args):
         # hits kernel: one LDS.32 per (lane, base, column group).  Motifs are sorted by descending
         # length and cut into blocks (tfbs_hits_block_plan in csrc/scan_hits.cu): a block of longest
         # motif L uses A 4-column + B 3-column groups (minimal A + B under 192 KB of tables) and holds
-        # 32 motifs (16-bit filter fields) or 64 motifs (8-bit fields; at most 6 groups, chosen per block
+        # 32 motifs (16-bit filter fields) or 64 motifs (8-bit fields, plain or sticky; chosen per block
         # from the thresholds by the cost model in tfbs_build_hits_tables)
         blocks = lib.hits_blocks()
         lookups = float(n_scan) * 32.0 * float(sum(a + b for a, b, _, _ in blocks))
@@ -413,8 +413,9 @@ def run_ours(args):
                          "lut_bytes_per_launch": lookups * 4.0, "achieved_gbs": lookups * 4.0 / k_ms / 1e6,
                          "peak_gbs": smem_peak / 1e9, "frac": lookups * 4.0 / k_ms / 1e6 / (smem_peak / 1e9),
                          "peak_def": "148 SM x 128 B/clk x sampled SM clock",
-                         "blocks": {"wide_32_motifs": sum(1 for b in blocks if not b[2]),
-                                    "narrow_64_motifs": sum(1 for b in blocks if b[2])}},
+                         "blocks": {"wide_32_motifs": sum(1 for b in blocks if b[2] == 0),
+                                    "narrow_64_motifs": sum(1 for b in blocks if b[2] == 1),
+                                    "sticky_narrow_64_motifs": sum(1 for b in blocks if b[2] == 2)}},
             },
             "kernel_ms": {"encode": float(np.mean(enc_ms)), "scan_hits": k_ms,
                           **({"shape_tracks_4": float(np.mean(shape_ms))} if shape_ms else {})},

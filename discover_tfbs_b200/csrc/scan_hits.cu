@@ -63,7 +63,7 @@ constexpr int kMaxG = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 constexpr uint32_t kPoison = 0x80008000u;        // flag bits of the two 16-bit fields (wide blocks)
 constexpr uint32_t kPoisonNarrow = 0x80808080u;  // flag bits of the four 8-bit fields (narrow blocks)
 constexpr int kLutBudget = 192 * 1024;    // shared memory for one block table (6 x 32 KB)
-constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + kWarps * 4 + 2 * TFBS_BLOCK_SLOTS * 4 + 32;
+constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + 2 * TFBS_BLOCK_SLOTS * 4 + 32;
 
 struct HitsParams {
     const uint32_t *packed;
@@ -91,7 +91,6 @@ struct Smem {
     uint32_t *words;     // [kTileWords]
     uint32_t *mask;      // [kTileMask]
     uint32_t *queue;     // [kWarps][kQueueCap]
-    uint32_t *qcount;    // [kWarps]
     int32_t *motif;      // [64]
     int32_t *len;        // [64]
     uint64_t *bar;       // mbarrier
@@ -196,7 +195,6 @@ __device__ __forceinline__ void store_hit(tfbs_hit *hits, unsigned long long slo
 
 struct PushCtx {
     uint32_t *queue;   // this warp's queue
-    uint32_t *qcount;  // this warp's counter
     int seg_begin, seg_end;
     int lane;
     const VerifyCtx *V;
@@ -207,10 +205,12 @@ struct PushCtx {
 
 // Warp-synchronous verification of the queued candidates, 32 at a time; hits are compacted with
 // ballot/popc and one atomic per batch.
-__device__ __noinline__ void drain_queue(const PushCtx &C)
+// `qn` = entries pushed since the last drain (warp-uniform register; entries beyond kQueueCap were
+// verified inline by push_group).
+__device__ __noinline__ void drain_queue(const PushCtx &C, uint32_t qn)
 {
     __syncwarp();
-    const uint32_t cnt = min(*C.qcount, (uint32_t)kQueueCap);
+    const uint32_t cnt = min(qn, (uint32_t)kQueueCap);
     for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t i = base + C.lane;
         bool hit = false;
@@ -232,10 +232,7 @@ __device__ __noinline__ void drain_queue(const PushCtx &C)
         }
     }
     __syncwarp();
-    if (C.lane == 0) {
-        if (cnt) atomicAdd(C.hit_count + 1, (unsigned long long)cnt);  // statistics: candidates verified
-        *C.qcount = 0;
-    }
+    if (C.lane == 0 && cnt) atomicAdd(C.hit_count + 1, (unsigned long long)cnt);  // statistics: candidates verified
     __syncwarp();
 }
 
@@ -248,22 +245,21 @@ __device__ __noinline__ void drain_queue(const PushCtx &C)
 // no lane-by-lane serialisation when hits are dense.
 template <int NF>
 __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                           int p_first)
+                                           int p_first, uint32_t &qn)
 {
-    constexpr int FB = 32 / NF;  // field width
-    // bit NF * k + f of `mine`: this lane has a candidate at start p_first + k in field f
-    uint32_t mine = 0;
+    constexpr uint32_t PM = NF == 4 ? kPoisonNarrow : kPoison;
+    // bit 8b + k of `mine`: this lane has a candidate at start p_first + k in the field whose flag is
+    // bit 8b + 7 of the accumulator (b = 3: slot `lane` forward; narrow b = 2 / 1 / 0: slot `lane`
+    // reverse, slot `lane + 32` forward / reverse; wide b = 1: slot `lane` reverse)
+    uint32_t mine = ((~a0 & PM) >> 7) | ((~a1 & PM) >> 6) | ((~a2 & PM) >> 5) | ((~a3 & PM) >> 4);
     {
-        const uint32_t a[4] = {a0, a1, a2, a3};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int p = p_first + k;
-            if (p >= C.seg_begin && p < C.seg_end) {  // ring lead-in / overshoot of the last turn
-                const uint32_t cand = ~a[k];
-#pragma unroll
-                for (int f = 0; f < NF; f++) mine |= ((cand >> (31 - FB * f)) & 1u) << (NF * k + f);
-            }
-        }
+        // starts outside [seg_begin, seg_end): the ring lead-in (never a candidate, masked for good
+        // measure) and the overshoot of the last turn (windows of the next warp's segment)
+        const int lo = C.seg_begin - p_first, hi = C.seg_end - p_first;
+        uint32_t kmask = 0xFu;
+        if (lo > 0) kmask &= 0xFu << min(lo, 4);
+        if (hi < 4) kmask &= (1u << max(hi, 0)) - 1u;
+        mine &= kmask * 0x01010101u;
     }
     uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mine);
     const uint32_t lt = (1u << C.lane) - 1u;
@@ -272,15 +268,12 @@ __device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32
         any &= any - 1u;
         const bool c = (mine >> bit) & 1u;
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, c);
-        uint32_t base = 0;
-        if (C.lane == 0) {
-            base = *C.qcount;
-            *C.qcount = base + (uint32_t)__popc(b);
-        }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const uint32_t base = qn;
+        qn += (uint32_t)__popc(b);
         if (c) {
-            const int p = p_first + bit / NF, f = bit % NF, strand = f & 1;
-            const int ml = C.lane + 32 * (f >> 1);  // motif slot of the block
+            const int p = p_first + (bit & 7), byte = bit >> 3;
+            const int strand = NF == 4 ? (~byte & 1) : (byte == 1);
+            const int ml = C.lane + (NF == 4 && byte < 2 ? 32 : 0);  // motif slot of the block
             const uint32_t slot = base + (uint32_t)__popc(b & lt);
             if (slot < (uint32_t)kQueueCap) {
                 C.queue[slot] = (uint32_t)p | ((uint32_t)ml << 16) | ((uint32_t)strand << 31);
@@ -314,6 +307,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
     uint32_t acc[kRing];
 #pragma unroll
     for (int i = 0; i < kRing; i++) acc[i] = PM;
+    uint32_t qn = 0;  // candidates queued by this warp since its last drain (warp-uniform)
     const uint32_t *wptr = s_words + (C.seg_begin >> 4);
     uint32_t wlo = wptr[0], whi = wptr[1];
     int wk = 2;
@@ -360,7 +354,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                 for (int k = 0; k < kCheck; k++) fin[k] = acc[(j - (kCheck - 1 - k) - kTail + 2 * kRing) % kRing];
                 const uint32_t all = fin[0] & fin[1] & fin[2] & fin[3];
                 if (__any_sync(0xFFFFFFFFu, (~all & PM) != 0u))
-                    push_group<NARROW ? 4 : 2>(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail);
+                    push_group<NARROW ? 4 : 2>(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail, qn);
             }
             if (jj == 15) {
                 wlo = whi;
@@ -368,8 +362,12 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
             }
         }
         // all lanes are converged again here: verify queued candidates before the queue can fill up
-        if (*C.qcount >= (uint32_t)kQueueCap / 2) drain_queue(C);
+        if (qn >= (uint32_t)kQueueCap / 2) {
+            drain_queue(C, qn);
+            qn = 0;
+        }
     }
+    drain_queue(C, qn);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -391,8 +389,6 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
     p += kTileMask * 4;
     S.queue = reinterpret_cast<uint32_t *>(p);
     p += kWarps * kQueueCap * 4;
-    S.qcount = reinterpret_cast<uint32_t *>(p);
-    p += kWarps * 4;
     S.motif = reinterpret_cast<int32_t *>(p);
     p += TFBS_BLOCK_SLOTS * 4;
     S.len = reinterpret_cast<int32_t *>(p);
@@ -405,7 +401,6 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(S.bar, 1);
-    if (tid < kWarps) S.qcount[tid] = 0;
     __syncthreads();
 
     const uint32_t total_items = (uint32_t)(P.n_tiles * P.n_blocks);
@@ -458,7 +453,6 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         V.tile_start = tile_start;
         PushCtx C;
         C.queue = S.queue + warp * kQueueCap;
-        C.qcount = S.qcount + warp;
         C.seg_begin = warp * kSeg;
         C.seg_end = C.seg_begin + kSeg;
         C.lane = lane;
@@ -484,7 +478,6 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
                 if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)(AB & 0xFFFF)));
                 break;
         }
-        drain_queue(C);
         __syncthreads();  // tile buffers and S.item are reused by the next item
     }
 }
@@ -606,12 +599,11 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 // ---- block plan + filter tables (host) ------------------------------------------------------------
 // Cost model of the block form, in warp-wide shared-memory loads per window start, fitted to B200
 // measurements at 100 Mb x 800 PWMs and hit rates 1e-6 .. 1e-2 (profiles/r01/SUMMARY.md): one load
-// costs 4.1 ps per window; a candidate handed to the exact verifier costs 0.15 / 0.27 / 0.40 ns in a
-// wide / narrow / sticky block (the denser the loop, the less slack hides the cold path); a load of
-// the sticky form costs 1.3 plain loads (two more ALU ops each).  A narrow block of G groups replaces
-// two wide blocks of G and G2 groups.
-constexpr double kCandidateCost[3] = {37.0, 66.0, 98.0};
-constexpr double kStickyLoad = 1.30;
+// costs 4.1 ps per window; a candidate handed to the exact verifier costs 0.16 / 0.22 / 0.20 ns in a
+// wide / narrow / sticky block; a load of the sticky form costs 1.33 plain loads (two more ALU ops
+// each).  A narrow block of G groups replaces two wide blocks of G and G2 groups.
+constexpr double kCandidateCost[3] = {39.0, 54.0, 50.0};
+constexpr double kStickyLoad = 1.33;
 enum { kWide = 0, kNarrow = 1, kSticky = 2 };
 
 // Block form forced from the environment (A/B measurements and tests); -1 = cost model (default).
