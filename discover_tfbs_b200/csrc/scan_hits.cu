@@ -29,10 +29,12 @@
 //     (128 - 2G) / (G - 1) quantisation steps fit without carries, so the filter is coarser (1.1x the
 //     candidates at G = 3, 2.4x at G = 5, 78x at G = 9; profiles/field8_simulation.py) and the exact
 //     verifier, which keeps the hit set bit-exact, has more to do.
-//   * STICKY narrow blocks (5 or more groups): the flag bits are masked out before every add and OR-ed
-//     back (acc = ((acc & 0x7F7F7F7F) + v) | (acc & 0x80808080), two more ALU ops per load, still
-//     under the issue budget of a load-bound loop), so fields can never carry and all 126 steps are
-//     usable whatever G is: the 8-bit filter is then almost as sharp as the 16-bit one.
+//   * STICKY narrow blocks (5 or more groups): flag bits, once set, are OR-ed back after every add
+//     (acc = (acc + v) | (acc & 0x80808080), one more ALU op per load), so a dead field may wrap
+//     without looking alive again.  A wrapping field carries +1 into the field above it, at most
+//     (2 + 127 G + 4) / 256 <= 4 times per window; a field with a neighbour below therefore starts
+//     that many steps lower, which keeps {candidates} a superset of {hits}, and >= 121 quantisation
+//     steps are usable whatever G is: the 8-bit filter is then almost as sharp as the 16-bit one.
 //     Wide, narrow or sticky is chosen per block and per threshold vector by a cost model
 //     (tfbs_build_hits_tables).
 //   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
@@ -329,7 +331,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                     const uint32_t v = lds32(addr4 + g * 32768);
                     const int slot = (j - 4 * g + 2 * kRing) % kRing;
                     if (g == 0) acc[slot] = kinit + v;
-                    else if (STICKY) acc[slot] = ((acc[slot] & ~PM) + v) | (acc[slot] & PM);
+                    else if (STICKY) acc[slot] = (acc[slot] + v) | (acc[slot] & PM);
                     else acc[slot] += v;
                 }
             }
@@ -340,7 +342,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                     const uint32_t v = lds32(addr3 + g * 8192);
                     const int slot = (j - 4 * A - 3 * g + 2 * kRing) % kRing;
                     if (A == 0 && g == 0) acc[slot] = kinit + v;
-                    else if (STICKY) acc[slot] = ((acc[slot] & ~PM) + v) | (acc[slot] & PM);
+                    else if (STICKY) acc[slot] = (acc[slot] + v) | (acc[slot] & PM);
                     else acc[slot] += v;
                 }
             }
@@ -600,10 +602,10 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 // Cost model of the block form, in warp-wide shared-memory loads per window start, fitted to B200
 // measurements at 100 Mb x 800 PWMs and hit rates 1e-6 .. 1e-2 (profiles/r01/SUMMARY.md): one load
 // costs 4.1 ps per window; a candidate handed to the exact verifier costs 0.16 / 0.22 / 0.20 ns in a
-// wide / narrow / sticky block; a load of the sticky form costs 1.33 plain loads (two more ALU ops
-// each).  A narrow block of G groups replaces two wide blocks of G and G2 groups.
+// wide / narrow / sticky block; a load of the sticky form costs kStickyLoad plain loads (one more ALU
+// op each).  A narrow block of G groups replaces two wide blocks of G and G2 groups.
 constexpr double kCandidateCost[3] = {39.0, 54.0, 50.0};
-constexpr double kStickyLoad = 1.33;
+constexpr double kStickyLoad = 1.18;
 enum { kWide = 0, kNarrow = 1, kSticky = 2 };
 
 // Block form forced from the environment (A/B measurements and tests); -1 = cost model (default).
@@ -686,10 +688,23 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
             // Quantisation steps for the deficit budget.  No carry out of a field needs
             //   (fmax - Dq) + Gm * capq <= 2 * fmax + 1   with  Dq >= dq_max, capq = dq_max + 2:
             // wide fields take the block-wide bound, narrow ones the bound of their own Gm.  Sticky
-            // fields cannot carry at all (flag bits are masked out of every add): entries <= 127.
+            // fields may wrap (their flag is sticky): entries <= 127, and `slack` steps of the field
+            // absorb the carries a wrapping neighbour sends in.
+            int slack = 0;
+            if (mode == kSticky) {
+                // the field one byte below: the reverse strand of the same motif, or (below the reverse
+                // field of slot l < 32) the forward strand of slot l + 32; the lowest field has none.
+                // It starts at most at 2 (127 - Dq - slack with Dq >= 125 - slack; a threshold of -inf
+                // starts higher but adds zeros), adds Gl entries <= 127 and receives <= 4 carries itself.
+                int Gl = 0;
+                if (s == 0) Gl = Gm;
+                else if (half == 0 && l + 32 < count)
+                    for (int g = 0; g < G && gcol[g] < pw->lens[motifs[l + 32]]; g++) Gl++;
+                slack = Gl ? (2 + Gl * 127 + 4) / 256 : 0;
+            }
             int dq_max;
             if (mode == kWide) dq_max = 0x7FFF / G - 3;
-            else if (mode == kSticky) dq_max = 125;
+            else if (mode == kSticky) dq_max = 125 - slack;
             else dq_max = Gm <= 1 ? 100 : std::min(100, (128 - 2 * Gm) / (Gm - 1));
             const int capq = dq_max + 2;
             if (std::isnan(t)) reachable = false;
@@ -710,8 +725,9 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
                 Dq = (int)std::min(dqv, (double)(dq_max + 1));
                 Dq = std::max(Dq, dq_max);  // D * scale == dq_max up to rounding; keeps the no-carry bound
             }
-            kinit[lane] = (kinit[lane] & ~((uint32_t)(2 * fmax + 1) << shift)) | ((uint32_t)(fmax - Dq) << shift);
-            // pass[v]: probability that the quantised deficits of the groups so far sum to v <= Dq
+            kinit[lane] = (kinit[lane] & ~((uint32_t)(2 * fmax + 1) << shift)) | ((uint32_t)(fmax - Dq - slack) << shift);
+            const int Dp = Dq + slack;  // what the field lets pass when no carry comes in
+            // pass[v]: probability that the quantised deficits of the groups so far sum to v <= Dp
             double pass[128], next[128];
             if (narrow) {
                 std::fill(pass, pass + 128, 0.0);
@@ -730,18 +746,18 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
                         q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
                     }
                     lut[(size_t)goff[g] + (size_t)x * 32 + lane] |= (uint32_t)q << shift;
-                    if (narrow && q <= Dq) hist[q] += 1.0 / E;
+                    if (narrow && q <= Dp) hist[q] += 1.0 / E;
                 }
                 if (narrow) {
-                    std::fill(next, next + Dq + 1, 0.0);
-                    for (int v = 0; v <= Dq; v++)
+                    std::fill(next, next + Dp + 1, 0.0);
+                    for (int v = 0; v <= Dp; v++)
                         if (pass[v] > 0.0)
-                            for (int q = 0; v + q <= Dq; q++) next[v + q] += pass[v] * hist[q];
-                    std::copy(next, next + Dq + 1, pass);
+                            for (int q = 0; v + q <= Dp; q++) next[v + q] += pass[v] * hist[q];
+                    std::copy(next, next + Dp + 1, pass);
                 }
             }
             if (narrow)
-                for (int v = 0; v <= Dq; v++) expected += pass[v];
+                for (int v = 0; v <= Dp; v++) expected += pass[v];
         }
     }
     return narrow ? expected : 0.0;
@@ -775,11 +791,11 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         int A2 = 0, B2 = 1;
         tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
         const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
-        // the sticky filter (126 steps) is nearly as sharp as the 16-bit one: it also estimates the
-        // candidates of the wide form
+        // the sticky filter (>= 121 steps) also estimates the candidates of the wide form: measured,
+        // it passes about 1.5x as many
         const double c_sticky = fill_block(pw, thr, order + first, count, A, B, kSticky, lut, ki);
         const double c_narrow = fill_block(pw, thr, order + first, count, A, B, kNarrow, lut, ki);
-        const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.2;
+        const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.5;
         const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
         const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
         if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) return kNarrow;  // tables are in place
