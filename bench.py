@@ -346,7 +346,7 @@ def run_ours(args):
     t_resident = float(np.sum(step_ms)) / 1e3
 
     # ---- end to end --------------------------------------------------------------------------------
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         step_e2e()
     barrier()
     e2e_ms = []
@@ -402,9 +402,10 @@ def run_ours(args):
                 "kernel": "scan_hits_kernel", "bound": "hbm", "achieved": algo_bytes / k_ms / 1e6, "peak": peak,
                 "unit": "GB/s", "frac": algo_bytes / k_ms / 1e6 / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, from the
-                # committed ncu --set full capture profiles/r01/ncu_full_final_100Mb_raw.csv (part of the
-                # 297 MB of hits is still in L2 when the kernel ends)
-                "traffic": 76.19e6 + 116.30e6 if (args.motifs == 800 and per_gpu == 100_000_000) else None,
+                # committed ncu --set full capture profiles/r01/ncu_full_hits_narrow_100Mb_raw.csv (part of
+                # the 297 MB of hits is still in L2 when the kernel ends)
+                "traffic": 62.62e6 + 106.75e6 if (args.motifs == 800 and per_gpu == 100_000_000
+                                                  and abs(args.rate - 1e-4) < 1e-12) else None,
                 "peak_source": peak_src,
                 "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes,
                 "note": "hits mode at 800 motifs is bounded by shared-memory LUT bandwidth, not HBM "
