@@ -241,27 +241,28 @@ __device__ __noinline__ void drain_queue(const PushCtx &C, uint32_t qn)
 // Cold path, entered by the WHOLE warp when any lane of a check group has a candidate field (its flag
 // bit clear).  NF = fields per accumulator word: 2 (wide: bit 31 forward, bit 15 reverse) or 4 (narrow:
 // bits 31 / 23 = motif slot `lane` forward / reverse, bits 15 / 7 = motif slot `lane + 32`).
-// a0..a3 are the finalised accumulators of window starts p_first .. p_first+3 (unused slots: all flag
+// a[0..7] are the finalised accumulators of window starts p_first .. p_first+7 (unused slots: all flag
 // bits set).  One warp-wide OR tells which (start, field) pairs have candidates at all (usually one); each of those is compacted into the warp's queue with
 // ballot/popc — the queue is warp-private and every access is warp-synchronous, so no atomics and
 // no lane-by-lane serialisation when hits are dense.
 template <int NF>
-__device__ __forceinline__ void push_group(const PushCtx &C, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                           int p_first, uint32_t &qn)
+__device__ __forceinline__ void push_group(const PushCtx &C, const uint32_t (&a)[8], int p_first, uint32_t &qn)
 {
     constexpr uint32_t PM = NF == 4 ? kPoisonNarrow : kPoison;
     // bit 8b + k of `mine`: this lane has a candidate at start p_first + k in the field whose flag is
     // bit 8b + 7 of the accumulator (b = 3: slot `lane` forward; narrow b = 2 / 1 / 0: slot `lane`
     // reverse, slot `lane + 32` forward / reverse; wide b = 1: slot `lane` reverse)
-    uint32_t mine = ((~a0 & PM) >> 7) | ((~a1 & PM) >> 6) | ((~a2 & PM) >> 5) | ((~a3 & PM) >> 4);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) mine |= (~a[k] & PM) >> (7 - k);  // unused slots hold PM: no bits
     {
         // starts outside [seg_begin, seg_end): the ring lead-in (never a candidate, masked for good
         // measure) and the overshoot of the last turn (windows of the next warp's segment)
         const int lo = C.seg_begin - p_first, hi = C.seg_end - p_first;
-        uint32_t kmask = 0xFu;
-        if (lo > 0) kmask &= 0xFu << min(lo, 4);
-        if (hi < 4) kmask &= (1u << max(hi, 0)) - 1u;
-        mine &= kmask * 0x01010101u;
+        uint32_t kmask = 0xFFu;
+        if (lo > 0) kmask &= 0xFFu << min(lo, 8);
+        if (hi < 8) kmask &= (1u << max(hi, 0)) - 1u;
+        mine &= (kmask & 0xFFu) * 0x01010101u;
     }
     uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mine);
     const uint32_t lt = (1u << C.lane) - 1u;
@@ -315,7 +316,7 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
     int wk = 2;
     constexpr int kTail = B > 0 ? 4 * A + 3 * (B - 1) : 4 * (A - 1);  // column offset of the last group
     constexpr int kChunks = (kSeg + kTail + kRing - 1) / kRing;
-    constexpr int kCheck = (kRing - kTail >= 4) ? 4 : ((kRing - kTail >= 2) ? 2 : 1);
+    constexpr int kCheck = (kRing - kTail >= 8) ? 8 : ((kRing - kTail >= 4) ? 4 : ((kRing - kTail >= 2) ? 2 : 1));
     const uint32_t lut3_lane_addr = lut_lane_addr + A * 32768;
     for (int c = 0; c < kChunks; c++) {
         const int q0 = C.seg_begin + c * kRing;
@@ -346,17 +347,17 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
                     else acc[slot] += v;
                 }
             }
-            // Candidate test, amortised over kCheck consecutive steps: bit 15 of a field stays SET
+            // Candidate test, amortised over kCheck (up to 8) consecutive steps: the flag bit of a field stays SET
             // in the AND of the finalised accumulators unless one of them cleared it.  (A finalised
             // slot is re-opened 32 - kTail steps later, which bounds kCheck.)  The vote keeps the
             // branch warp-uniform, so the cold path can compact candidates cooperatively.
             if ((j % kCheck) == kCheck - 1) {
-                uint32_t fin[4] = {PM, PM, PM, PM};
+                uint32_t fin[8] = {PM, PM, PM, PM, PM, PM, PM, PM};
 #pragma unroll
                 for (int k = 0; k < kCheck; k++) fin[k] = acc[(j - (kCheck - 1 - k) - kTail + 2 * kRing) % kRing];
-                const uint32_t all = fin[0] & fin[1] & fin[2] & fin[3];
+                const uint32_t all = (fin[0] & fin[1] & fin[2] & fin[3]) & (fin[4] & fin[5] & fin[6] & fin[7]);
                 if (__any_sync(0xFFFFFFFFu, (~all & PM) != 0u))
-                    push_group<NARROW ? 4 : 2>(C, fin[0], fin[1], fin[2], fin[3], q0 + j - (kCheck - 1) - kTail, qn);
+                    push_group<NARROW ? 4 : 2>(C, fin, q0 + j - (kCheck - 1) - kTail, qn);
             }
             if (jj == 15) {
                 wlo = whi;
