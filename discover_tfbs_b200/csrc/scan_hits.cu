@@ -4,8 +4,9 @@
 // SURVEY.md A.1) for a whole motif library in one pass, and generalises the reference's
 // exact-match BLASTn candidate stage (utils.py:340-398, process_blast.sh:32).
 //
-// Design (one warp lane = one motif, so shared-memory LUT reads are bank-conflict free):
-//   * motifs are sorted by length and grouped 32 to a block.  The columns of a block are cut into
+// Design (one warp lane = one motif — two in narrow blocks — so shared-memory LUT reads are
+// bank-conflict free):
+//   * motifs are sorted by length and grouped 32 to a (wide) block.  The columns of a block are cut into
 //     A groups of 4 columns followed by B groups of 3 (A, B chosen per block to minimise A + B under
 //     the shared-memory budget: a 4-mer group costs 32 KB, a 3-mer group 8 KB).  The block table
 //     lives in shared memory as T[g][x][lane] (x = 8- or 6-bit k-mer code, 4 B per entry): the 32
@@ -18,7 +19,8 @@
 //     {score >= threshold}.
 //   * the warp walks its segment base by base (the k-mer code is warp-uniform, sliced from the
 //     2-bit packed words staged in shared memory by TMA); A + B loads feed A + B of the 32 ring
-//     accumulators held in registers; the accumulator that just received its last group is tested.
+//     accumulators held in registers; finalised accumulators are tested up to 8 at a time (their AND
+//     keeps a flag bit set unless one of them cleared it), with a warp vote.
 //   * candidates (rare) go to a per-warp shared-memory queue and are verified 32 at a time:
 //     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
 //     float, compared with >= — so hit sets and scores are bit-exact.  Hits are compacted with
@@ -88,8 +90,8 @@ struct HitsParams {
 };
 
 struct Smem {
-    // LUT region first (8 KB aligned at run time), the rest follows
-    uint32_t *lut;       // [G][64][32]
+    // small buffers first, then the block table on the next 32 KB boundary of the shared window
+    uint32_t *lut;       // [A][256][32] then [B][64][32]
     uint32_t *words;     // [kTileWords]
     uint32_t *mask;      // [kTileMask]
     uint32_t *queue;     // [kWarps][kQueueCap]
