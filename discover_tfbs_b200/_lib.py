@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_debug_hits_block_plan": (C.c_int, [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
+    "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None
@@ -119,6 +120,19 @@ def hits_block_plan(lens, narrow_max_groups: int = 9):
     _check(load().tfbs_debug_hits_block_plan(a.ctypes.data_as(C.POINTER(_i32)), int(a.size), int(narrow_max_groups),
                                              out.ctypes.data_as(C.POINTER(_i32)), C.byref(nb)))
     return [tuple(int(v) for v in row) for row in out[: nb.value]]
+
+
+def hits_filter_host(logodds, lens, thr, form: int, codes) -> np.ndarray:
+    """Host run of the hits kernel's candidate filter (test hook, no GPU): uint8[n][M][2], 1 where
+    window start p of motif m passes on strand s.  form 0 wide, 1 narrow, 2 narrow + sticky blocks."""
+    lo = np.ascontiguousarray(logodds, dtype=np.float64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    th = np.ascontiguousarray(thr, dtype=np.float32)
+    cd = np.ascontiguousarray(codes, dtype=np.uint8)
+    M, Lmax = int(lo.shape[0]), int(lo.shape[1])
+    out = np.zeros((cd.size, M, 2), dtype=np.uint8)
+    _check(load().tfbs_debug_hits_filter(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), int(form), _ptr(cd), int(cd.size), _ptr(out)))
+    return out
 
 
 def device_count() -> int:

@@ -118,6 +118,17 @@ struct tfbs_shapes {
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
+// Exact scoring matrices of motif m: F = log-odds as given, R = reverse complement (columns reversed,
+// bases complemented), both [L][4] in a [TFBS_MAX_MOTIF_LEN][4] slab.
+static inline void tfbs_fill_exact(const double *logodds, int Lmax, int m, int L, double *F, double *R)
+{
+    for (int j = 0; j < L; j++)
+        for (int b = 0; b < 4; b++) {
+            F[j * 4 + b] = logodds[((size_t)m * Lmax + j) * 4 + b];
+            R[j * 4 + b] = logodds[((size_t)m * Lmax + (L - 1 - j)) * 4 + (3 - b)];
+        }
+}
+
 // One block of the hits-mode plan: A 4-column + B 3-column groups, narrow (64 motifs, 8-bit fields)
 // or wide (32 motifs, 16-bit fields), motifs [first, first + count) of the length-sorted order.
 struct tfbs_hits_block { int A, B, narrow /* 0 wide, 1 narrow, 2 sticky narrow */, first, count; };

@@ -234,11 +234,7 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
         Gmax = std::max(Gmax, G);
         double *F = &exact[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4];
         double *R = &exact[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4];
-        for (int j = 0; j < L; j++)
-            for (int b = 0; b < 4; b++) {
-                F[j * 4 + b] = logodds[((size_t)m * Lmax + j) * 4 + b];
-                R[j * 4 + b] = logodds[((size_t)m * Lmax + (L - 1 - j)) * 4 + (3 - b)];
-            }
+        tfbs_fill_exact(logodds, Lmax, m, L, F, R);
         // dense mode: fp32 k-mer tables, k = 4 (256 entries per group) for L <= 24, else k = 3
         const int K = L <= 24 ? 4 : 3, Gd = (L + K - 1) / K, E = 1 << (2 * K);
         lut_off[m] = (int32_t)lut.size();

@@ -1049,6 +1049,74 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
 }
 
 
+// Test hook (host only, no CUDA): run the candidate FILTER of the hits kernel on the host, with the
+// kernel's own tables (fill_block) and its 32-bit field arithmetic, so the CPU test-suite can check
+// that {candidates} is a superset of {hits} for every block form — in particular that fields never
+// carry (wide, narrow) and that the carry slack of sticky fields is sufficient.
+//   form 0: wide blocks only; 1: narrow wherever more than 32 motifs are left; 2: as 1, but sticky
+//   from TFBS_STICKY_MIN_GROUPS groups on.
+//   codes: n bases as 2-bit codes, one per byte (bases past the end count as 0, as in the padded device buffer)
+//   cand:  uint8[n][M][2], set to 1 where the filter passes window start p of motif m on strand s
+extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                      const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand)
+{
+    if (!logodds || !lens || !thr || !codes || !cand || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1 ||
+        form < 0 || form > 2)
+        return TFBS_ERR_INVALID;
+    tfbs_pwms pw;  // host fields only
+    pw.M = M;
+    pw.Lmax = Lmax;
+    pw.lens.assign(lens, lens + M);
+    pw.exact_host.assign((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
+    for (int m = 0; m < M; m++) {
+        if (lens[m] < 1 || lens[m] > Lmax) return TFBS_ERR_INVALID;
+        tfbs_fill_exact(logodds, Lmax, m, lens[m], &pw.exact_host[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4],
+                        &pw.exact_host[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4]);
+    }
+    pw.order.resize(M);
+    for (int m = 0; m < M; m++) pw.order[m] = m;
+    std::stable_sort(pw.order.begin(), pw.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    pw.lens_desc.resize(M);
+    for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
+    memset(cand, 0, (size_t)n * M * 2);
+    std::vector<uint32_t> lut, kinit(32);
+    auto base = [&](int64_t i) -> uint32_t { return i < n ? (codes[i] & 3u) : 0u; };
+    cut_blocks(
+        pw.lens_desc.data(), M,
+        [&](int, int, int A, int B) { return form == 0 ? kWide : (form == 2 && A + B >= TFBS_STICKY_MIN_GROUPS ? kSticky : kNarrow); },
+        [&](const tfbs_hits_block &K) {
+            const int G = K.A + K.B;
+            const int32_t *motifs = pw.order.data() + K.first;
+            lut.assign((size_t)K.A * 8192 + (size_t)K.B * 2048, 0u);
+            fill_block(&pw, thr, motifs, K.count, K.A, K.B, K.narrow, lut.data(), kinit.data());
+            const uint32_t PM = K.narrow ? kPoisonNarrow : kPoison;
+            for (int64_t p = 0; p < n; p++)
+                for (int lane = 0; lane < 32; lane++) {
+                    uint32_t acc = 0;
+                    for (int g = 0; g < G; g++) {
+                        const int k = g < K.A ? 4 : 3;
+                        const int col = g < K.A ? 4 * g : 4 * K.A + 3 * (g - K.A);
+                        const size_t off = g < K.A ? (size_t)g * 8192 : (size_t)K.A * 8192 + (size_t)(g - K.A) * 2048;
+                        uint32_t x = 0;
+                        for (int j = 0; j < k; j++) x |= base(p + col + j) << (2 * j);
+                        const uint32_t v = lut[off + (size_t)x * 32 + lane];
+                        if (g == 0) acc = kinit[lane] + v;                         // the kernel's three
+                        else if (K.narrow == kSticky) acc = (acc + v) | (acc & PM);  // accumulate forms
+                        else acc += v;
+                    }
+                    const int nf = K.narrow ? 4 : 2;
+                    for (int f = 0; f < nf; f++) {
+                        const int flag = 31 - (32 / nf) * f;
+                        if ((acc >> flag) & 1u) continue;
+                        const int slot = lane + 32 * (K.narrow ? (f >> 1) : 0);
+                        if (slot >= K.count) continue;
+                        cand[((size_t)p * M + motifs[slot]) * 2 + (f & 1)] = 1;
+                    }
+                }
+        });
+    return TFBS_OK;
+}
+
 // Test hook (host only): the blocks a library of the given motif lengths (any order) is cut into when
 // every block of at most `narrow_max_groups` column groups is taken in narrow form (the scan itself
 // decides per block from the thresholds, see tfbs_pwms_hits_blocks).

@@ -220,6 +220,14 @@ int tfbs_debug_hits_group_plan(int32_t L, int32_t *A, int32_t *B);
 int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_max_groups, int32_t *out,
                                int32_t *n_blocks);
 
+/* The candidate FILTER of the hits kernel run on the host with the kernel's own tables and 32-bit
+ * field arithmetic (no CUDA): form 0 = wide blocks, 1 = narrow, 2 = narrow + sticky.  codes = n bases
+ * as 2-bit codes, one per byte; cand = uint8[n][M][2], 1 where window start p of motif m passes on
+ * strand s.  Lets the CPU suite check that the filter never loses a hit (Biopython search semantics,
+ * SURVEY.md A.1) in any block form. */
+int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                           const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand);
+
 #ifdef __cplusplus
 }
 #endif

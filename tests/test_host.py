@@ -241,3 +241,43 @@ def test_hits_block_plan_covers_every_motif_once():
     assert _lib.hits_block_plan([8] * 100, 0) == [(2, 0, 0, 32)] * 3 + [(2, 0, 0, 4)]
     assert _lib.hits_block_plan([24] * 100, 99) == [(6, 0, 1, 64), (6, 0, 1, 36)]
     assert _lib.hits_block_plan([25] * 100, 6)[0] == (5, 2, 0, 32)
+
+
+@pytest.mark.parametrize("seed,lmin,lmax,rate,minus_inf", [(1, 3, 32, 3e-3, False), (2, 17, 32, 1e-2, False),
+                                                          (3, 1, 12, 1e-2, True), (4, 20, 30, 3e-4, True)])
+def test_hits_filter_never_loses_a_hit_in_any_block_form(seed, lmin, lmax, rate, minus_inf):
+    """The hits kernel's candidate filter (its own tables and 32-bit field arithmetic, run on the
+    host by tfbs_debug_hits_filter) must pass every window the oracle scores >= threshold, in wide,
+    narrow and sticky blocks: fields must not carry into their neighbours (wide, narrow) and the
+    carry slack of sticky fields must hold."""
+    from oracle import pssm_oracle as po
+    from discover_tfbs_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    M, n = 100, 6000
+    logodds, lens = synth.pwm_library(700 + seed, M, lmin=lmin, lmax=lmax, alpha=float(rng.choice([0.1, 0.3, 1.0])))
+    if minus_inf:
+        logodds = np.where(rng.random(logodds.shape) < 0.03, -np.inf, logodds)
+    thr = synth.thresholds_for_rate(np.where(np.isinf(logodds), -20.0, logodds), lens, rate=rate, sample=5000, seed=seed)
+    thr[::17] = -np.inf   # everything passes
+    thr[5::17] = np.inf   # nothing can
+    thr[9::17] = np.nan
+    codes = rng.integers(0, 4, size=n).astype(np.uint8)
+    codes[1000:1300] = 0  # a poly-A stretch: extreme deficits in every group at once
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr)
+    assert cnt > 1000
+    passed = {}
+    for form in (0, 1, 2):
+        cand = _lib.hits_filter_host(logodds, lens, thr, form, codes)
+        assert cand[pos, mot, strand].all(), (form, int((cand[pos, mot, strand] == 0).sum()))
+        inside = np.arange(n)[:, None] + lens[None, :] <= n  # windows that end inside the sequence
+        passed[form] = int(cand[inside].sum())
+        assert not cand[:, 5::17].any() and not cand[:, 9::17].any()  # +inf / NaN thresholds: poisoned fields
+    # the wide filter is sharp; the 8-bit forms pass more, the sticky one less than the plain one
+    finite = np.isfinite(thr)
+    n_hits_finite = int(np.isin(mot, np.flatnonzero(finite)).sum())
+    always = int(sum(2 * (n - int(L) + 1) for L, t in zip(lens, thr) if t == -np.inf))
+    assert passed[0] - always <= 1.25 * n_hits_finite + 50
+    assert passed[1] >= passed[2] >= passed[0] >= cnt
