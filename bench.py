@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--genome-mb", type=float, default=100.0, help="Mb scanned per GPU")
     ap.add_argument("--motifs", type=int, default=800)
     ap.add_argument("--rate", type=float, default=1e-4, help="expected hit rate per position per strand")
+    ap.add_argument("--chunks", type=int, default=8, help="chunks of the pipelined end-to-end pass")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel roofline section")
     ap.add_argument("--with-shape", action="store_true",
                     help="config C5 flavour: every step also computes 4 DNA-shape tracks of the chunk")
@@ -315,8 +316,8 @@ def run_ours(args):
 
     def step_e2e():
         # public end-to-end call: pinned host ASCII -> (H2D | encode + scan | hits D2H) pipelined
-        # over 8 chunks on three streams -> hits in pinned host memory
-        return ctx.scan_hits_host(pinned_in.array, enc, lib, thr, hits_out[:cap], chunks=8)
+        # over args.chunks chunks on three streams -> hits in pinned host memory
+        return ctx.scan_hits_host(pinned_in.array, enc, lib, thr, hits_out[:cap], chunks=args.chunks)
 
     # ---- resident (value) ------------------------------------------------------------------------
     sampler = ClockSampler(local)
