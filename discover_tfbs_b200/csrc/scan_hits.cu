@@ -240,6 +240,22 @@ __device__ __noinline__ void drain_queue(const PushCtx &C, uint32_t qn)
     __syncwarp();
 }
 
+// Queue full (flood thresholds): verify one candidate right here, divergently.  Out of line on
+// purpose: the call sits in every candidate-test site of the unrolled scan loop, and inlining the
+// verifier there made each instantiation several times larger than its hot loop.
+__device__ __noinline__ void verify_now(const PushCtx &C, int p, int ml, int strand)
+{
+    int m;
+    float sc;
+    if (verify(*C.V, p, ml, strand, &m, &sc)) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long hb = 0;
+        if (g.thread_rank() == 0) hb = atomicAdd(C.hit_count, (unsigned long long)g.size());
+        hb = g.shfl(hb, 0);
+        store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, sc);
+    }
+}
+
 // Cold path, entered by the WHOLE warp when any lane of a check group has a candidate field (its flag
 // bit clear).  NF = fields per accumulator word: 2 (wide: bit 31 forward, bit 15 reverse) or 4 (narrow:
 // bits 31 / 23 = motif slot `lane` forward / reverse, bits 15 / 7 = motif slot `lane + 32`).
@@ -283,16 +299,7 @@ __device__ __forceinline__ void push_group(const PushCtx &C, const uint32_t (&a)
             if (slot < (uint32_t)kQueueCap) {
                 C.queue[slot] = (uint32_t)p | ((uint32_t)ml << 16) | ((uint32_t)strand << 31);
             } else {
-                // queue full (flood thresholds): verify right here, divergently
-                int m;
-                float sc;
-                if (verify(*C.V, p, ml, strand, &m, &sc)) {
-                    cg::coalesced_group g = cg::coalesced_threads();
-                    unsigned long long hb = 0;
-                    if (g.thread_rank() == 0) hb = atomicAdd(C.hit_count, (unsigned long long)g.size());
-                    hb = g.shfl(hb, 0);
-                    store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, sc);
-                }
+                verify_now(C, p, ml, strand);  // queue full (flood thresholds)
             }
         }
         __syncwarp();
@@ -405,7 +412,10 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
     S.lut = reinterpret_cast<uint32_t *>(smem_raw + (lut_addr - raw));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) mbar_init(S.bar, 1);
+    if (tid == 0) {
+        mbar_init(S.bar, 1);
+        *S.item = atomicAdd(P.work_counter, 1u);
+    }
     __syncthreads();
 
     const uint32_t total_items = (uint32_t)(P.n_tiles * P.n_blocks);
@@ -414,9 +424,7 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
     uint32_t kinit = kPoison;
     int AB = 1;
     for (;;) {
-        if (tid == 0) *S.item = atomicAdd(P.work_counter, 1u);
-        __syncthreads();
-        const uint32_t item = *S.item;
+        const uint32_t item = *S.item;  // fetched while the previous item was scanned
         if (item >= total_items) break;
         const int b = (int)(item / (uint32_t)P.n_tiles);
         const int64_t tile = P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles);
@@ -446,7 +454,10 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         }
         mbar_wait(S.bar, phase);
         phase ^= 1u;
-        __syncthreads();  // S.motif / S.len visible
+        __syncthreads();  // S.motif / S.len visible; everybody has read S.item
+        // ask for the next item now: the round trip of the atomic hides behind the scan
+        uint32_t next_item = 0;
+        if (tid == 0) next_item = atomicAdd(P.work_counter, 1u);
 
         VerifyCtx V;
         V.s_words = S.words;
@@ -483,7 +494,8 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
                 if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)(AB & 0xFFFF)));
                 break;
         }
-        __syncthreads();  // tile buffers and S.item are reused by the next item
+        if (tid == 0) *S.item = next_item;
+        __syncthreads();  // tile buffers are reused by the next item; S.item holds it
     }
 }
 
@@ -883,7 +895,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
     P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 24);
-    TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFFFFF0ll, "tfbs_scan_hits: too many work items");
+    TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFF0000ll, "tfbs_scan_hits: too many work items");  // + one prefetch per CTA
     TFBS_REQUIRE((P.n_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits: sequence padding too small");
 
     size_t smem = 0;
