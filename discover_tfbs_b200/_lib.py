@@ -64,7 +64,7 @@ _PROTOTYPES = {
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_debug_hits_block_plan": (C.c_int, [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
-    "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
+    "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
 }
 
 _lib = None
@@ -122,17 +122,25 @@ def hits_block_plan(lens, narrow_max_groups: int = 9):
     return [tuple(int(v) for v in row) for row in out[: nb.value]]
 
 
-def hits_filter_host(logodds, lens, thr, form: int, codes) -> np.ndarray:
+def hits_filter_host(logodds, lens, thr, form: int, codes, with_plan: bool = False):
     """Host run of the hits kernel's candidate filter (test hook, no GPU): uint8[n][M][2], 1 where
-    window start p of motif m passes on strand s.  form 0 wide, 1 narrow, 2 narrow + sticky blocks."""
+    window start p of motif m passes on strand s.  form 0 wide, 1 narrow, 2 narrow + sticky blocks,
+    3 the plan a scan would choose.  with_plan: also return [(A, B, form, n_motifs), ...] and the
+    candidates per window start the table builder expects of every narrow / sticky block."""
     lo = np.ascontiguousarray(logodds, dtype=np.float64)
     ln = np.ascontiguousarray(lens, dtype=np.int32)
     th = np.ascontiguousarray(thr, dtype=np.float32)
     cd = np.ascontiguousarray(codes, dtype=np.uint8)
     M, Lmax = int(lo.shape[0]), int(lo.shape[1])
     out = np.zeros((cd.size, M, 2), dtype=np.uint8)
-    _check(load().tfbs_debug_hits_filter(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), int(form), _ptr(cd), int(cd.size), _ptr(out)))
-    return out
+    plan = np.zeros((M, 4), dtype=np.int32)
+    expected = np.zeros(M, dtype=np.float64)
+    nb = _i32(0)
+    _check(load().tfbs_debug_hits_filter(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), int(form), _ptr(cd), int(cd.size),
+                                         _ptr(out), _ptr(plan), _ptr(expected), C.byref(nb)))
+    if not with_plan:
+        return out
+    return out, [tuple(int(v) for v in row) for row in plan[: nb.value]], expected[: nb.value].copy()
 
 
 def device_count() -> int:

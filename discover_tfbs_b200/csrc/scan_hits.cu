@@ -778,6 +778,47 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
     return narrow ? expected : 0.0;
 }
 
+// Form of the block made of motifs order[first, first + count) (count > 32): forced from the
+// environment, else the cheapest by the cost model.  The candidate forms are built in place in
+// lut / kinit; on return they hold the tables of the chosen form unless that is kWide (the caller
+// builds the wide table of the first 32 motifs).  *expected = candidates per window start the chosen
+// narrow / sticky form is expected to pass (0 for kWide).
+static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int count, int A, int B, uint32_t *lut,
+                       uint32_t *kinit, double *expected)
+{
+    const int G = A + B;
+    const int32_t *motifs = pw->order.data() + first;
+    const int force_narrow = env_int("TFBS_HITS_NARROW"), force_sticky = env_int("TFBS_HITS_STICKY");
+    *expected = 0.0;
+    if (force_narrow >= 0 || force_sticky >= 0) {
+        int mode = kWide;
+        if (force_sticky >= 0 && G >= std::max(force_sticky, TFBS_STICKY_MIN_GROUPS)) mode = kSticky;
+        else if (force_narrow >= 0 && G <= force_narrow) mode = kNarrow;
+        if (mode != kWide) *expected = fill_block(pw, thr, motifs, count, A, B, mode, lut, kinit);
+        return mode;
+    }
+    // groups of the second of the two wide blocks a narrow block replaces
+    int A2 = 0, B2 = 1;
+    tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
+    const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
+    // the sticky filter (>= 121 steps) also estimates the candidates of the wide form: measured,
+    // it passes about 1.5x as many
+    const double c_sticky = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
+    const double c_narrow = fill_block(pw, thr, motifs, count, A, B, kNarrow, lut, kinit);
+    const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.5;
+    const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
+    const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
+    if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) {  // tables are in place
+        *expected = c_narrow;
+        return kNarrow;
+    }
+    if (cost_sticky <= cost_wide) {
+        *expected = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
+        return kSticky;
+    }
+    return kWide;
+}
+
 // Plan the blocks and quantise their tables for a threshold vector; cached per threshold vector.
 int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
 {
@@ -786,39 +827,13 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         return TFBS_OK;
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
-    const int force_narrow = env_int("TFBS_HITS_NARROW"), force_sticky = env_int("TFBS_HITS_STICKY");
     int64_t words = 0;   // table words of the blocks emitted so far
     int nb = 0;
     const int32_t *order = pw->order.data();
-    // The candidate forms of a block are built in place (the chosen one last); a wide block is built
-    // by emit below.
+    // a narrow / sticky block is built in place by choose_form, a wide one by emit below
     auto accept = [&](int first, int count, int A, int B) -> int {
-        const int G = A + B;
-        uint32_t *lut = qlut.data() + words, *ki = kinit.data() + (size_t)nb * 32;
-        if (force_narrow >= 0 || force_sticky >= 0) {
-            int mode = kWide;
-            if (force_sticky >= 0 && G >= std::max(force_sticky, TFBS_STICKY_MIN_GROUPS)) mode = kSticky;
-            else if (force_narrow >= 0 && G <= force_narrow) mode = kNarrow;
-            if (mode != kWide) fill_block(pw, thr, order + first, count, A, B, mode, lut, ki);
-            return mode;
-        }
-        // groups of the second of the two wide blocks a narrow block replaces
-        int A2 = 0, B2 = 1;
-        tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
-        const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
-        // the sticky filter (>= 121 steps) also estimates the candidates of the wide form: measured,
-        // it passes about 1.5x as many
-        const double c_sticky = fill_block(pw, thr, order + first, count, A, B, kSticky, lut, ki);
-        const double c_narrow = fill_block(pw, thr, order + first, count, A, B, kNarrow, lut, ki);
-        const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.5;
-        const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
-        const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
-        if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) return kNarrow;  // tables are in place
-        if (cost_sticky <= cost_wide) {
-            fill_block(pw, thr, order + first, count, A, B, kSticky, lut, ki);
-            return kSticky;
-        }
-        return kWide;
+        double expected;
+        return choose_form(pw, thr, first, count, A, B, qlut.data() + words, kinit.data() + (size_t)nb * 32, &expected);
     };
     pw->blk_A.clear();
     pw->blk_B.clear();
@@ -1066,14 +1081,17 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
 // that {candidates} is a superset of {hits} for every block form — in particular that fields never
 // carry (wide, narrow) and that the carry slack of sticky fields is sufficient.
 //   form 0: wide blocks only; 1: narrow wherever more than 32 motifs are left; 2: as 1, but sticky
-//   from TFBS_STICKY_MIN_GROUPS groups on.
+//   from TFBS_STICKY_MIN_GROUPS groups on; 3: what a scan would use (cost model / environment).
+//   plan (optional): int32[blocks][4] = {A, B, form, motifs}, n_blocks; expected (optional):
+//   double[blocks] = candidates per window start the builder expects of a narrow / sticky block.
 //   codes: n bases as 2-bit codes, one per byte (bases past the end count as 0, as in the padded device buffer)
 //   cand:  uint8[n][M][2], set to 1 where the filter passes window start p of motif m on strand s
 extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
-                                      const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand)
+                                      const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand,
+                                      int32_t *plan, double *expected, int32_t *n_blocks)
 {
     if (!logodds || !lens || !thr || !codes || !cand || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1 ||
-        form < 0 || form > 2)
+        form < 0 || form > 3)
         return TFBS_ERR_INVALID;
     tfbs_pwms pw;  // host fields only
     pw.M = M;
@@ -1091,16 +1109,29 @@ extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens
     pw.lens_desc.resize(M);
     for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
     memset(cand, 0, (size_t)n * M * 2);
-    std::vector<uint32_t> lut, kinit(32);
+    std::vector<uint32_t> lut((size_t)6 * 8192 + (size_t)kMaxG * 2048), kinit(32);
     auto base = [&](int64_t i) -> uint32_t { return i < n ? (codes[i] & 3u) : 0u; };
+    int nb = 0;
+    double exp_block = 0.0;
     cut_blocks(
         pw.lens_desc.data(), M,
-        [&](int, int, int A, int B) { return form == 0 ? kWide : (form == 2 && A + B >= TFBS_STICKY_MIN_GROUPS ? kSticky : kNarrow); },
+        [&](int first, int count, int A, int B) {
+            exp_block = 0.0;
+            if (form == 3) return choose_form(&pw, thr, first, count, A, B, lut.data(), kinit.data(), &exp_block);
+            return form == 0 ? (int)kWide : (form == 2 && A + B >= TFBS_STICKY_MIN_GROUPS ? (int)kSticky : (int)kNarrow);
+        },
         [&](const tfbs_hits_block &K) {
             const int G = K.A + K.B;
             const int32_t *motifs = pw.order.data() + K.first;
-            lut.assign((size_t)K.A * 8192 + (size_t)K.B * 2048, 0u);
-            fill_block(&pw, thr, motifs, K.count, K.A, K.B, K.narrow, lut.data(), kinit.data());
+            const double e = fill_block(&pw, thr, motifs, K.count, K.A, K.B, K.narrow, lut.data(), kinit.data());
+            if (plan) {
+                plan[4 * nb + 0] = K.A;
+                plan[4 * nb + 1] = K.B;
+                plan[4 * nb + 2] = K.narrow;
+                plan[4 * nb + 3] = K.count;
+            }
+            if (expected) expected[nb] = K.narrow == kWide ? 0.0 : e;
+            nb++;
             const uint32_t PM = K.narrow ? kPoisonNarrow : kPoison;
             for (int64_t p = 0; p < n; p++)
                 for (int lane = 0; lane < 32; lane++) {
@@ -1126,6 +1157,7 @@ extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens
                     }
                 }
         });
+    if (n_blocks) *n_blocks = nb;
     return TFBS_OK;
 }
 

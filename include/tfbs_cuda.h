@@ -221,12 +221,16 @@ int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_ma
                                int32_t *n_blocks);
 
 /* The candidate FILTER of the hits kernel run on the host with the kernel's own tables and 32-bit
- * field arithmetic (no CUDA): form 0 = wide blocks, 1 = narrow, 2 = narrow + sticky.  codes = n bases
- * as 2-bit codes, one per byte; cand = uint8[n][M][2], 1 where window start p of motif m passes on
- * strand s.  Lets the CPU suite check that the filter never loses a hit (Biopython search semantics,
- * SURVEY.md A.1) in any block form. */
+ * field arithmetic (no CUDA): form 0 = wide blocks, 1 = narrow, 2 = narrow + sticky, 3 = the plan a
+ * scan would use (cost model).  codes = n bases as 2-bit codes, one per byte; cand = uint8[n][M][2],
+ * 1 where window start p of motif m passes on strand s.  Optional outputs: plan = int32[blocks][4]
+ * {A, B, form, motifs} (room for M blocks), expected = double[blocks] candidates per window start the
+ * table builder predicts for a narrow / sticky block, n_blocks.  Lets the CPU suite check that the
+ * filter never loses a hit (Biopython search semantics) in any block form and that
+ * the cost model's prediction matches what the filter passes. */
 int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
-                           const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand);
+                           const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand,
+                           int32_t *plan, double *expected, int32_t *n_blocks);
 
 #ifdef __cplusplus
 }

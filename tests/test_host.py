@@ -281,3 +281,47 @@ def test_hits_filter_never_loses_a_hit_in_any_block_form(seed, lmin, lmax, rate,
     always = int(sum(2 * (n - int(L) + 1) for L, t in zip(lens, thr) if t == -np.inf))
     assert passed[0] - always <= 1.25 * n_hits_finite + 50
     assert passed[1] >= passed[2] >= passed[0] >= cnt
+
+
+def test_hits_cost_model_plan_and_candidate_prediction(monkeypatch):
+    """The table builder predicts the candidates a narrow / sticky block passes (exact convolution of
+    the quantised deficits under uniform bases) and picks the block form from it.  Run on the host:
+    the prediction must match what the filter really passes on a uniform random sequence, flood
+    thresholds must keep every block wide, sparse thresholds must use the two-motifs-per-lane forms."""
+    from discover_tfbs_b200 import synth
+
+    monkeypatch.delenv("TFBS_HITS_NARROW", raising=False)
+    monkeypatch.delenv("TFBS_HITS_STICKY", raising=False)
+    rng = np.random.default_rng(11)
+    M, n = 200, 30_000
+    logodds, lens = synth.pwm_library(711, M, lmin=6, lmax=30)
+    codes = rng.integers(0, 4, size=n).astype(np.uint8)
+    order = np.argsort(-lens, kind="stable")
+
+    sparse = synth.thresholds_for_rate(logodds, lens, rate=1e-3, gc=0.5, sample=20_000)
+    cand, plan, expected = _lib.hits_filter_host(logodds, lens, sparse, 3, codes, with_plan=True)
+    assert sum(b[3] for b in plan) == M and any(b[2] for b in plan)
+    first = 0
+    checked = 0
+    for (a, b, form, count), exp in zip(plan, expected):
+        motifs = order[first:first + count]
+        first += count
+        if form == 0:
+            assert exp == 0.0
+            continue
+        observed = cand[:, motifs].sum() / n
+        assert abs(observed - exp) <= 0.25 * exp + 0.01, (a, b, form, observed, exp)
+        checked += 1
+    assert checked >= 1
+
+    flood = np.full(M, -1e30, dtype=np.float32)
+    _, plan_flood, _ = _lib.hits_filter_host(logodds, lens, flood, 3, codes[:64], with_plan=True)
+    assert all(form == 0 for _, _, form, _ in plan_flood) and len(plan_flood) == (M + 31) // 32
+
+    strict = synth.thresholds_for_rate(logodds, lens, rate=2e-5, gc=0.5, sample=50_000)
+    _, plan_strict, _ = _lib.hits_filter_host(logodds, lens, strict, 3, codes[:64], with_plan=True)
+    assert sum(1 for b in plan_strict if b[2]) >= sum(1 for b in plan if b[2])
+
+    monkeypatch.setenv("TFBS_HITS_NARROW", "0")  # the environment override reaches the same code path
+    _, plan_off, _ = _lib.hits_filter_host(logodds, lens, sparse, 3, codes[:64], with_plan=True)
+    assert all(form == 0 for _, _, form, _ in plan_off)
