@@ -167,41 +167,121 @@ def read_jaspar(path_or_text, pseudocounts=0.5, background=None):
     return motifs
 
 
-def score_distribution(logodds, background=None, precision=1000):
-    """Discretised exact score distribution of a PSSM under an i.i.d. background — the dynamic
-    programme behind Biopython's `pssm.distribution(precision=10**3)` (Bio/motifs/thresholds.py):
-    scores are binned into `precision` steps between the minimum and maximum attainable score.
-    Returns (scores float64[precision+1], probability mass float64[precision+1])."""
+def read_meme(path_or_text, pseudocounts=0.5, background=None):
+    """Parse MEME "minimal" motif files (the format `Bio.motifs.parse(handle, "minimal")` reads):
+
+        MOTIF MA0004.1 Arnt
+        letter-probability matrix: alength= 4 w= 6 nsites= 20 E= 0
+          0.200000  0.800000  0.000000  0.000000
+          ...
+
+    Probabilities are turned back into counts with `nsites` (20 when absent), then treated like
+    read_jaspar: normalize(pseudocounts), log_odds(background).  Returns [(name, logodds[L][4])]."""
+    import os
+    import re
+
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    motifs = []
+    lines = text.splitlines()
+    i = 0
+    name = None
+    while i < len(lines):
+        line = lines[i].strip()
+        if line.startswith("MOTIF"):
+            name = line[5:].strip()
+        elif line.startswith("letter-probability matrix") and name is not None:
+            w = re.search(r"w=\s*(\d+)", line)
+            ns = re.search(r"nsites=\s*([0-9.eE+-]+)", line)
+            alen = re.search(r"alength=\s*(\d+)", line)
+            if alen and int(alen.group(1)) != 4:
+                raise ValueError(f"motif {name}: alength {alen.group(1)} is not a DNA alphabet")
+            nsites = float(ns.group(1)) if ns else 20.0
+            rows = []
+            i += 1
+            while i < len(lines) and (w is None or len(rows) < int(w.group(1))):
+                parts = lines[i].split()
+                if len(parts) != 4:
+                    if rows or lines[i].strip():
+                        break
+                    i += 1
+                    continue
+                rows.append([float(x) for x in parts])
+                i += 1
+            if not rows or (w is not None and len(rows) != int(w.group(1))):
+                raise ValueError(f"motif {name}: expected {w.group(1) if w else 'some'} matrix rows, found {len(rows)}")
+            counts = np.asarray(rows, dtype=np.float64) * nsites
+            motifs.append((name, log_odds(normalize(counts, pseudocounts), background)))
+            name = None
+            continue
+        i += 1
+    return motifs
+
+
+def score_distribution(logodds, background=None, precision=1000, under="background"):
+    """Discretised exact score distribution of a PSSM — the dynamic programme behind Biopython's
+    `pssm.distribution(precision=10**3)` (Bio/motifs/thresholds.py): scores are binned into
+    `precision` steps between the minimum and maximum attainable score.  under="background": windows
+    drawn from the i.i.d. background; under="motif": windows drawn from the motif itself
+    (p = background * 2**logodds per column).
+    Returns (scores, probability mass), float64[precision + 1 + L] each."""
     m = np.asarray(logodds, dtype=np.float64)
     bg = np.full(4, 0.25) if background is None else np.array([float(background[b]) for b in LETTERS])
     bg = bg / bg.sum()
+    if under not in ("background", "motif"):
+        raise ValueError("under must be 'background' or 'motif'")
     finite = np.where(np.isfinite(m), m, np.nan)
     lo = float(np.nansum(np.nanmin(finite, axis=1)))
     hi = float(np.nansum(np.nanmax(finite, axis=1)))
     step = (hi - lo) / precision if hi > lo else 1.0
-    dist = np.zeros(precision + 1)
+    nbins = precision + 1 + m.shape[0]  # per-column rounding can push the top score a few bins up
+    dist = np.zeros(nbins)
     dist[0] = 1.0
-    offset = 0.0  # score represented by bin 0 so far
     for j in range(m.shape[0]):
         colmin = float(np.nanmin(finite[j]))
-        new = np.zeros(precision + 1)
+        new = np.zeros(nbins)
         for b in range(4):
             if not np.isfinite(m[j, b]):
                 continue  # -inf: the window can never reach any finite threshold
             shift = int(round((m[j, b] - colmin) / step))
+            weight = bg[b] if under == "background" else bg[b] * 2.0 ** m[j, b]
             if shift == 0:
-                new += dist * bg[b]
+                new += dist * weight
             else:
-                new[shift:] += dist[:-shift] * bg[b]
+                new[shift:] += dist[:-shift] * weight
         dist = new
-        offset += colmin
-    return lo + step * np.arange(precision + 1), dist
+    return lo + step * np.arange(nbins), dist
 
 
 def threshold_fpr(logodds, fpr, background=None, precision=1000):
     """Smallest score threshold whose false-positive rate under the background is <= fpr
     (Biopython: `pssm.distribution().threshold_fpr(fpr)`)."""
     scores, mass = score_distribution(logodds, background, precision)
-    tail = np.cumsum(mass[::-1])[::-1]  # P(score >= scores[i])
+    tail = np.cumsum(mass[::-1])[::-1]  # P(binned score >= scores[i])
     ok = np.flatnonzero(tail <= fpr)
-    return float(scores[ok[0]]) if ok.size else float(scores[-1] + (scores[1] - scores[0]))
+    # a window's binned score is within half a step per column of its real score: err on the safe side
+    margin = 0.5 * (scores[1] - scores[0]) * np.asarray(logodds).shape[0]
+    return float(scores[ok[0]] + margin) if ok.size else float(scores[-1] + (scores[1] - scores[0]))
+
+
+def threshold_fnr(logodds, fnr, background=None, precision=1000):
+    """Largest score threshold that still keeps the false-NEGATIVE rate <= fnr, i.e. at most a
+    fraction fnr of windows drawn from the motif itself score below it
+    (Biopython: `pssm.distribution().threshold_fnr(fnr)`)."""
+    scores, mass = score_distribution(logodds, background, precision, under="motif")
+    mass = mass / mass.sum()
+    below = np.cumsum(mass) - mass  # P(binned score < scores[i]) under the motif
+    ok = np.flatnonzero(below <= fnr)
+    margin = 0.5 * (scores[1] - scores[0]) * np.asarray(logodds).shape[0]  # binning error, safe side
+    return float(scores[ok[-1]] - margin)
+
+
+def threshold_balanced(logodds, rate_proportion=1.0, background=None, precision=1000):
+    """Threshold where false-negative rate ~= rate_proportion * false-positive rate
+    (Biopython: `pssm.distribution().threshold_balanced(rate_proportion)`)."""
+    scores, bg_mass = score_distribution(logodds, background, precision)
+    _, mo_mass = score_distribution(logodds, background, precision, under="motif")
+    mo_mass = mo_mass / mo_mass.sum()
+    fpr = np.cumsum(bg_mass[::-1])[::-1]          # P_bg(score >= s_i)
+    fnr = np.cumsum(mo_mass) - mo_mass            # P_motif(score < s_i)
+    i = int(np.argmin(np.abs(fnr - rate_proportion * fpr)))
+    return float(scores[i])

@@ -325,3 +325,53 @@ def test_hits_cost_model_plan_and_candidate_prediction(monkeypatch):
     monkeypatch.setenv("TFBS_HITS_NARROW", "0")  # the environment override reaches the same code path
     _, plan_off, _ = _lib.hits_filter_host(logodds, lens, sparse, 3, codes[:64], with_plan=True)
     assert all(form == 0 for _, _, form, _ in plan_off)
+
+
+def test_read_meme_and_motif_side_thresholds():
+    from discover_tfbs_b200 import pssm
+
+    text = """MEME version 4
+
+ALPHABET= ACGT
+
+MOTIF MA0004.1 Arnt
+letter-probability matrix: alength= 4 w= 6 nsites= 20 E= 0
+ 0.200000  0.800000  0.000000  0.000000
+ 0.950000  0.000000  0.050000  0.000000
+ 0.000000  1.000000  0.000000  0.000000
+ 0.000000  0.000000  1.000000  0.000000
+ 0.000000  0.000000  0.000000  1.000000
+ 0.000000  0.000000  1.000000  0.000000
+URL http://jaspar.genereg.net/matrix/MA0004.1
+
+MOTIF second
+letter-probability matrix: alength= 4 w= 2
+ 0.25 0.25 0.25 0.25
+ 0.10 0.20 0.30 0.40
+"""
+    motifs = pssm.read_meme(text, pseudocounts=0.5)
+    assert [n for n, _ in motifs] == ["MA0004.1 Arnt", "second"]
+    jaspar = pssm.read_jaspar(">x\nA [ 4 19 0 0 0 0 ]\nC [16 0 20 0 0 0 ]\nG [ 0 1 0 20 0 20 ]\nT [ 0 0 0 0 20 0 ]\n")
+    assert np.allclose(motifs[0][1], jaspar[0][1])  # same counts, same log-odds
+    assert motifs[1][1].shape == (2, 4)
+    lo = motifs[0][1]
+    # motif-side distribution against brute force over all 4^6 windows weighted by the motif itself
+    idx = np.indices((4,) * 6).reshape(6, -1)
+    brute = lo[np.arange(6)[:, None], idx].sum(axis=0)
+    p_motif = np.prod(0.25 * 2.0 ** lo[np.arange(6)[:, None], idx], axis=0)
+    assert abs(p_motif.sum() - 1.0) < 1e-9
+    for fnr in (0.01, 0.1, 0.3):
+        thr = pssm.threshold_fnr(lo, fnr, precision=4000)
+        missed = p_motif[brute < thr - 1e-9].sum()
+        assert missed <= fnr + 2e-3, (fnr, missed)
+        assert p_motif[brute < thr + 0.05].sum() >= fnr * 0.5 - 2e-3  # ... and not needlessly low
+    bal = pssm.threshold_balanced(lo, 1.0, precision=4000)
+    def gap_at(t):
+        return abs(p_motif[brute < t].sum() - (brute >= t).mean())
+
+    # scores are discrete and the DP bins them (6 columns x half a step of 0.01): as balanced as an
+    # attainable threshold can be, within the binning error
+    best = min(gap_at(t) for t in np.unique(brute))
+    assert min(gap_at(bal + d) for d in (-0.05, 0.0, 0.05)) <= best + 0.01
+    with pytest.raises(ValueError):
+        pssm.read_meme("MOTIF p\nletter-probability matrix: alength= 20 w= 1\n" + " ".join(["0.05"] * 20) + "\n")
