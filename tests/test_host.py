@@ -375,3 +375,43 @@ letter-probability matrix: alength= 4 w= 2
     assert min(gap_at(bal + d) for d in (-0.05, 0.0, 0.05)) <= best + 0.01
     with pytest.raises(ValueError):
         pssm.read_meme("MOTIF p\nletter-probability matrix: alength= 20 w= 1\n" + " ".join(["0.05"] * 20) + "\n")
+
+
+def test_scan_genome_cli_wiring(tmp_path, monkeypatch):
+    """scan_genome.py = motif file -> matrices + thresholds -> candidates.scan_candidates -> BED6 +
+    FASTA.  The scan itself is the GPU path (tested in test_gpu_parity); here it is replaced by a
+    recorder so that file parsing, threshold selection and the writers are checked without a GPU."""
+    from discover_tfbs_b200 import candidates, pssm, scan_genome
+
+    fa = tmp_path / "g.fa"
+    fa.write_text(">chr1 test\nACGTACGTAC\nGTCACGTGAA\n>chr2\nTTTTCACGTG\n")
+    jaspar = tmp_path / "m.jaspar"
+    jaspar.write_text(">MA0004.1 Arnt\nA [ 4 19 0 0 0 0 ]\nC [16 0 20 0 0 0 ]\nG [ 0 1 0 20 0 20 ]\nT [ 0 0 0 0 20 0 ]\n")
+    words = tmp_path / "w.txt"
+    words.write_text("# curated\nCACGTG\nCANNTG extra\n")
+    seen = {}
+
+    def fake_scan(records, matrices, thresholds, names=None, ctx=None, cap=0):
+        seen.update(records=records, matrices=matrices, thresholds=np.asarray(thresholds), names=names)
+        return [{"chrom": "chr1", "start": 13, "end": 19, "strand": "+", "motif": 0, "name": names[0],
+                 "score": 9.5, "sequence": "CACGTG"},
+                {"chrom": "chr2", "start": 4, "end": 10, "strand": "-", "motif": 0, "name": names[0],
+                 "score": 9.5, "sequence": "CACGTG"}]
+
+    monkeypatch.setattr(candidates, "scan_candidates", fake_scan)
+    out = str(tmp_path / "out")
+    assert scan_genome.main([str(fa), str(jaspar), out, "--fpr", "0.01"]) == 0
+    assert seen["records"] == {"chr1": "ACGTACGTACGTCACGTGAA", "chr2": "TTTTCACGTG"}
+    assert seen["names"] == ["MA0004.1 Arnt"] and seen["matrices"][0].shape == (6, 4)
+    assert np.isclose(seen["thresholds"][0], pssm.threshold_fpr(seen["matrices"][0], 0.01), atol=1e-6)
+    assert open(out + ".bed").read().splitlines() == ["chr1\t13\t19\tMA0004.1 Arnt\t9.5\t+", "chr2\t4\t10\tMA0004.1 Arnt\t9.5\t-"]
+    assert open(out + ".fasta").read() == ">chr1:13-19(+)\nCACGTG\n>chr2:4-10(-)\nCACGTG\n"
+
+    assert scan_genome.main([str(fa), str(words), out, "--exact"]) == 0
+    assert seen["names"] == ["CACGTG", "CANNTG"] and list(seen["thresholds"]) == [0.0, 0.0]
+    m = seen["matrices"][1]
+    assert np.array_equal(np.isfinite(m).sum(axis=1), [1, 1, 4, 4, 1, 1])
+
+    assert scan_genome.main([str(fa), str(jaspar), out, "--threshold", "7.5", "--gc", "0.4"]) == 0
+    assert list(seen["thresholds"]) == [7.5]
+    assert np.isclose(seen["matrices"][0][0, 1], np.log2((16.5 / 22) / 0.2))
