@@ -621,6 +621,8 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 // op each).  A narrow block of G groups replaces two wide blocks of G and G2 groups.
 constexpr double kCandidateCost[3] = {39.0, 54.0, 50.0};
 constexpr double kStickyLoad = 1.18;
+constexpr int kSaturatingSteps[] = {48, 64};  // step counts tried for saturating plain 8-bit fields (32, 96 and
+                                              // 124 were almost never the best on the 800-PWM library)
 enum { kWide = 0, kNarrow = 1, kSticky = 2 };
 
 // Block form forced from the environment (A/B measurements and tests); -1 = cost model (default).
@@ -700,11 +702,6 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
                 best += mx;
                 if (!std::isfinite(mx)) reachable = false;  // a column group of -inf only
             }
-            // Quantisation steps for the deficit budget.  No carry out of a field needs
-            //   (fmax - Dq) + Gm * capq <= 2 * fmax + 1   with  Dq >= dq_max, capq = dq_max + 2:
-            // wide fields take the block-wide bound, narrow ones the bound of their own Gm.  Sticky
-            // fields may wrap (their flag is sticky): entries <= 127, and `slack` steps of the field
-            // absorb the carries a wrapping neighbour sends in.
             int slack = 0;
             if (mode == kSticky) {
                 // the field one byte below: the reverse strand of the same motif, or (below the reverse
@@ -717,62 +714,103 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
                     for (int g = 0; g < G && gcol[g] < pw->lens[motifs[l + 32]]; g++) Gl++;
                 slack = Gl ? (2 + Gl * 127 + 4) / 256 : 0;
             }
-            int dq_max;
-            if (mode == kWide) dq_max = 0x7FFF / G - 3;
-            else if (mode == kSticky) dq_max = 125 - slack;
-            else dq_max = Gm <= 1 ? 100 : std::min(100, (128 - 2 * Gm) / (Gm - 1));
-            const int capq = dq_max + 2;
             if (std::isnan(t)) reachable = false;
             // D: how much a hit may lose against the best possible score (plus slack for the
             // float rounding of the oracle's comparison and double summation order)
             double D = reachable ? (best - (double)t) : -1.0;
             if (reachable && std::isfinite(D)) D += std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(best) * 1e-12 + 1e-9;
             if (!reachable || D < 0.0) continue;  // field stays poisoned: never a candidate
-            double scale;
-            int Dq;
-            if (std::isinf(D)) {
-                scale = 0.0;  // threshold -inf: everything is a candidate
-                Dq = 1;
-            } else {
-                scale = (double)dq_max / std::max(D, 1e-300);
-                if (!std::isfinite(scale)) scale = 1e300;
-                const double dqv = std::floor(D * scale) + 1.0;
-                Dq = (int)std::min(dqv, (double)(dq_max + 1));
-                Dq = std::max(Dq, dq_max);  // D * scale == dq_max up to rounding; keeps the no-carry bound
-            }
-            kinit[lane] = (kinit[lane] & ~((uint32_t)(2 * fmax + 1) << shift)) | ((uint32_t)(fmax - Dq - slack) << shift);
-            const int Dp = Dq + slack;  // what the field lets pass when no carry comes in
-            // pass[v]: probability that the quantised deficits of the groups so far sum to v <= Dp
-            double pass[128], next[128];
-            if (narrow) {
-                std::fill(pass, pass + 128, 0.0);
-                pass[0] = 1.0;
-            }
-            for (int g = 0; g < Gm; g++) {
-                const int E = 1 << (2 * gk[g]);
-                double hist[128];
-                if (narrow) std::fill(hist, hist + 128, 0.0);
-                for (int x = 0; x < E; x++) {
-                    const double d = gmax[g] - ent[(size_t)g * 256 + x];  // >= 0, +inf for -inf entries
-                    int q;
-                    if (scale == 0.0) q = 0;
-                    else {
-                        const double v = std::floor(d * scale);
-                        q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
-                    }
-                    lut[(size_t)goff[g] + (size_t)x * 32 + lane] |= (uint32_t)q << shift;
-                    if (narrow && q <= Dp) hist[q] += 1.0 / E;
+
+            // Quantise the field with dq_max steps for the budget D and entries capped at capq; with
+            // `commit` the table and the initial value are written.  Returns the probability that a
+            // window of uniform random bases passes (narrow forms only).
+            auto quantise = [&](int dq_max, int capq, bool commit) -> double {
+                double scale;
+                int Dq;
+                if (std::isinf(D)) {
+                    scale = 0.0;  // threshold -inf: everything is a candidate
+                    Dq = 1;
+                } else {
+                    scale = (double)dq_max / std::max(D, 1e-300);
+                    if (!std::isfinite(scale)) scale = 1e300;
+                    const double dqv = std::floor(D * scale) + 1.0;
+                    Dq = (int)std::min(dqv, (double)(dq_max + 1));
+                    Dq = std::max(Dq, dq_max);  // D * scale == dq_max up to rounding; keeps the no-carry bound
                 }
+                if (commit)
+                    kinit[lane] = (kinit[lane] & ~((uint32_t)(2 * fmax + 1) << shift)) | ((uint32_t)(fmax - Dq - slack) << shift);
+                const int Dp = Dq + slack;  // what the field lets pass when no carry comes in
+                // pass[v]: probability that the quantised deficits of the groups so far sum to v <= Dp
+                double pass[128], next[128];
                 if (narrow) {
-                    std::fill(next, next + Dp + 1, 0.0);
-                    for (int v = 0; v <= Dp; v++)
-                        if (pass[v] > 0.0)
-                            for (int q = 0; v + q <= Dp; q++) next[v + q] += pass[v] * hist[q];
-                    std::copy(next, next + Dp + 1, pass);
+                    std::fill(pass, pass + 128, 0.0);
+                    pass[0] = 1.0;
                 }
+                for (int g = 0; g < Gm; g++) {
+                    const int E = 1 << (2 * gk[g]);
+                    double hist[128];
+                    int qmax = 0;  // largest quantised deficit of the group that can still pass
+                    if (narrow) std::fill(hist, hist + 128, 0.0);
+                    for (int x = 0; x < E; x++) {
+                        const double d = gmax[g] - ent[(size_t)g * 256 + x];  // >= 0, +inf for -inf entries
+                        int q;
+                        if (scale == 0.0) q = 0;
+                        else {
+                            const double v = std::floor(d * scale);
+                            q = (v >= (double)capq || std::isnan(v)) ? capq : (int)v;
+                        }
+                        if (commit) lut[(size_t)goff[g] + (size_t)x * 32 + lane] |= (uint32_t)q << shift;
+                        if (narrow && q <= Dp) {
+                            hist[q] += 1.0 / E;
+                            qmax = std::max(qmax, q);
+                        }
+                    }
+                    if (narrow) {
+                        std::fill(next, next + Dp + 1, 0.0);
+                        for (int v = 0; v <= Dp; v++)
+                            if (pass[v] > 0.0)
+                                for (int q = 0; q <= qmax && v + q <= Dp; q++) next[v + q] += pass[v] * hist[q];
+                        std::copy(next, next + Dp + 1, pass);
+                    }
+                }
+                double p = 0.0;
+                if (narrow)
+                    for (int v = 0; v <= Dp; v++) p += pass[v];
+                return p;
+            };
+
+            // Steps and entry cap.  No carry out of a field needs
+            //   (fmax - Dq - slack) + Gm * capq <= 2 * fmax + 1   with   Dq >= dq_max.
+            if (mode == kWide) {
+                const int dq_max = 0x7FFF / G - 3;  // block-wide bound; an entry above the budget kills alone
+                quantise(dq_max, dq_max + 2, true);
+            } else if (mode == kSticky) {
+                // sticky fields may wrap (their flag is kept by the OR): entries <= 127, and `slack` steps
+                // of the field absorb the carries a wrapping neighbour sends in
+                expected += quantise(125 - slack, 127, true);
+            } else {
+                // Plain 8-bit fields must not wrap.  Either every entry above the budget kills alone
+                // (capq = dq_max + 2, which leaves only (128 - 2 Gm) / (Gm - 1) steps), or the steps are
+                // finer and entries SATURATE at capq <= (128 + dq_max) / Gm — a window then needs several
+                // bad groups to be rejected.  Both keep {candidates} a superset of {hits}; the one that
+                // passes fewer random windows (exact, by the convolution above) is taken.
+                int best_dq = Gm <= 1 ? 100 : std::min(100, (128 - 2 * Gm) / (Gm - 1));
+                int best_cap = best_dq + 2;
+                if (Gm >= 3 && std::isfinite(D)) {
+                    double best_p = quantise(best_dq, best_cap, false);
+                    for (int dq : kSaturatingSteps) {
+                        const int cap = (128 + dq) / Gm;
+                        if (dq <= best_dq || cap < 2 || cap >= dq + 2) continue;
+                        const double p = quantise(dq, cap, false);
+                        if (p < best_p) {
+                            best_p = p;
+                            best_dq = dq;
+                            best_cap = cap;
+                        }
+                    }
+                }
+                expected += quantise(best_dq, best_cap, true);
             }
-            if (narrow)
-                for (int v = 0; v <= Dp; v++) expected += pass[v];
         }
     }
     return narrow ? expected : 0.0;
