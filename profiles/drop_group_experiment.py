@@ -1,9 +1,8 @@
 """Historical (r01): timed the hits kernel with the last column group of long-motif blocks dropped from the
 filter (TFBS_HITS_DROP_MIN_G).  The switch was a net loss and has been removed from the kernel, so this script
 no longer changes anything; results in profiles/r01/drop_group_experiment.txt."""
-import os, sys, subprocess, json
+import os, sys
 sys.path.insert(0, '/root/repo')
-import numpy as np
 from discover_tfbs_b200 import _lib, synth
 ctx = _lib.Context(0)
 n = 100_000_000

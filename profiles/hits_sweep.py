@@ -2,7 +2,6 @@
 """Sensitivity of the hits kernel: hit-rate sweep (thresholds) and genome-size sweep, 800 PWMs."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from discover_tfbs_b200 import _lib, synth
 ctx = _lib.Context(0)
 logodds, lens = synth.pwm_library(39, 800, 6, 30)

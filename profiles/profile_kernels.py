@@ -9,7 +9,6 @@ import argparse
 import os
 import sys
 
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from discover_tfbs_b200 import _lib, dnashape, synth  # noqa: E402
