@@ -52,6 +52,7 @@ _PROTOTYPES = {
     "tfbs_pwm_upload": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _pp]),
     "tfbs_pwms_destroy": (C.c_int, [_vp]),
     "tfbs_scan_dense": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "tfbs_scan_best": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "tfbs_scan_hits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(_i64)]),
     "tfbs_scan_hits_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, C.POINTER(_i64)]),
     "tfbs_shapes_upload": (C.c_int, [_vp, _vp, _vp, _i32, _pp]),
@@ -61,6 +62,7 @@ _PROTOTYPES = {
     "tfbs_track_sites": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "tfbs_similarity_sums": (C.c_int, [_vp] + [_vp] * 6 + [_i64] + [_vp] * 6 + [_i64, _vp]),
     "tfbs_debug_swar4": (C.c_int, [_u32, C.POINTER(_u32), C.POINTER(_u32)]),
+    "tfbs_debug_dense_tables": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _vp, _i64]),
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_debug_hits_block_plan": (C.c_int, [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
@@ -107,6 +109,20 @@ def hits_group_plan(L: int):
     a, b = _i32(0), _i32(0)
     _check(load().tfbs_debug_hits_group_plan(int(L), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def dense_tables(pssm):
+    """(K, G, e, neg_thr, entries int32[G][4**K][2]): the dense kernel's fixed-point k-mer tables of one
+    motif (log-odds [L][4]); a window score is float32(sum of its G entries) * 2**-e, or -inf when
+    the sum is below neg_thr.  Host-only test hook."""
+    m = np.ascontiguousarray(pssm, dtype=np.float64)
+    L = int(m.shape[0])
+    k, g, e, neg = _i32(0), _i32(0), _i32(0), _i32(0)
+    lib = load()
+    _check(lib.tfbs_debug_dense_tables(_ptr(m), L, C.byref(k), C.byref(g), C.byref(e), C.byref(neg), None, 0))
+    ent = np.zeros((g.value, 4 ** k.value, 2), dtype=np.int32)
+    _check(lib.tfbs_debug_dense_tables(_ptr(m), L, C.byref(k), C.byref(g), C.byref(e), C.byref(neg), _ptr(ent), ent.size))
+    return k.value, g.value, e.value, neg.value, ent
 
 
 def hits_block_plan(lens, narrow_max_groups: int = 9):
@@ -296,6 +312,16 @@ class Context:
         rev = np.empty((pwms.M, seq.n), dtype=np.float32)
         _check(self._lib.tfbs_scan_dense(self._h, seq._h, pwms._h, _ptr(fwd), _ptr(rev)))
         return fwd, rev
+
+    def scan_best(self, seq: "EncodedSeq", pwms: "MotifLibrary", rec_start, rec_len, with_pos: bool = False):
+        """Per-record best window: float32[S][M][2] (fwd, rev; NaN = no valid window), reduced on the
+        device; with_pos also returns int32[S][M][2] offsets of the first best window (-1 = none)."""
+        rs = np.ascontiguousarray(rec_start, dtype=np.int64)
+        rl = np.ascontiguousarray(rec_len, dtype=np.int64)
+        best = np.empty((rs.size, pwms.M, 2), dtype=np.float32)
+        pos = np.empty((rs.size, pwms.M, 2), dtype=np.int32) if with_pos else None
+        _check(self._lib.tfbs_scan_best(self._h, seq._h, pwms._h, _ptr(rs), _ptr(rl), rs.size, _ptr(best), _ptr(pos)))
+        return (best, pos) if with_pos else best
 
     def scan_hits(self, seq: "EncodedSeq", pwms: "MotifLibrary", thresholds, cap: int = 1 << 20,
                   sort: bool = True, to_host: bool = True, out: np.ndarray = None,

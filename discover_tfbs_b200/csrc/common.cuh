@@ -81,9 +81,12 @@ struct tfbs_pwms {
     std::vector<double> logodds;     // host copy [M][Lmax][4]
     // exact matrices for re-scoring: double[M][2][TFBS_MAX_MOTIF_LEN][4] (strand 0 fwd, 1 revcomp)
     double *exact = nullptr;
-    // dense mode: fp32 k-mer LUTs (k = 4 for L <= 24, else 3): per motif G groups of 4^k float2 (fwd, rev)
-    float2 *lut = nullptr;
-    int32_t *lut_off = nullptr;      // [M] offset in float2 units
+    // dense mode: fixed-point k-mer LUTs (k = 4 for L <= 24, else 3): per motif G groups of 4^k int2
+    // (fwd, rev) = rint(group sum * 2^e), per-motif scale 2^-e and -inf detection bound
+    int2 *lut = nullptr;
+    float *dense_scale = nullptr;    // [M]
+    int32_t *dense_neg = nullptr;    // [M]
+    int32_t *lut_off = nullptr;      // [M] offset in int2 units
     int32_t *glen = nullptr;         // [M] packed (K << 16) | (G << 8) | L
     int64_t lut_entries = 0;
     size_t dense_lut_bytes = 0;      // shared memory the dense kernel needs for its largest table
@@ -118,6 +121,8 @@ struct tfbs_shapes {
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
+void tfbs_dense_quantise(const double *F, const double *R, int L, int *K_out, int *G_out, int *e_out,
+                         int32_t *neg_thr, std::vector<int2> &lut);
 // Exact scoring matrices of motif m: F = log-odds as given, R = reverse complement (columns reversed,
 // bases complemented), both [L][4] in a [TFBS_MAX_MOTIF_LEN][4] slab.
 static inline void tfbs_fill_exact(const double *logodds, int Lmax, int m, int L, double *F, double *R)

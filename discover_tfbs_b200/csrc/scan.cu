@@ -4,12 +4,18 @@
 // Bio/motifs/_pwm.c) — the scoring the north star names — and generalises the
 // reference's exact-match BLASTn candidate stage (utils.py:340-398, process_blast.sh:32).
 //
-// Arithmetic: the motif matrix and its reverse complement are folded on the host into 3-mer
-// look-up tables (64 entries per group of 3 columns, each entry the double sum of its <=3
-// log-odds values rounded once to fp32, fwd and rev packed as float2) so a window of length L
-// costs ceil(L/3) shared-memory loads for both strands.  The 6-bit LUT index is sliced straight
-// out of the 2-bit packed sequence held in registers.
-//   dense mode (this file): fp32 accumulation, scores written for every (motif, start, strand).
+// Arithmetic: the motif matrix and its reverse complement are folded on the host into k-mer
+// look-up tables (k = 4 for L <= 24, else 3; each entry the double sum of its <= k log-odds values,
+// fwd and rev packed in 8 bytes) so a window of length L costs ceil(L/k) shared-memory loads for
+// both strands.  The LUT index is sliced straight out of the 2-bit packed sequence held in registers.
+//   dense mode (this file): FIXED-POINT int32 accumulation.  Biopython's _pwm.c sums in double and
+//     casts once to float; summing fp32-rounded group entries in fp32 drifts past the 1e-4 contract
+//     on sharp long motifs (|score| ~ 600: ulp 6e-5 per add).  Every motif therefore gets its own
+//     power-of-two scale 2^e, as large as keeps any window sum inside int32; entries are
+//     rint(sum * 2^e), integer adds are exact and order-independent, and the epilogue is one
+//     int->float conversion (round to nearest, like the oracle's cast) and one exact multiply by
+//     2^-e.  Error before the final rounding <= G/2 * 2^-e (1.9e-6 at |score| < 1000).  -inf entries
+//     are a sentinel below every finite window sum (see tfbs_dense_quantise).
 //   hits mode (scan_hits.cu): packed fixed-point filter + exact double re-scoring of candidates.
 #include <algorithm>
 #include <cmath>
@@ -28,7 +34,9 @@ struct ScanParams {
     const uint32_t *packed;
     const uint32_t *mask;
     int64_t pitch;  // row pitch of the dense outputs (multiple of kTile)
-    const float2 *lut;
+    const int2 *lut;
+    const float *dscale;    // [M] 2^-e of the motif's fixed-point entries
+    const int32_t *dneg;    // [M] window sums below this mean -inf (INT32_MIN: motif has no -inf entry)
     const int32_t *lut_off;
     const int32_t *glen;
     int32_t M;
@@ -43,8 +51,8 @@ struct ScanParams {
 // profiles/r01/ncu_full_v1_raw.csv) and leave room for 256-entry groups: L = 20 costs 5 loads per
 // window instead of 7.  The table is 32 KB aligned so a lookup address is
 // base | (kmer << 7) | ((lane & 15) << 3)  (one shift + one LOP3), the group offset is an
-// immediate (K, G are template parameters) and both strands are accumulated with one packed
-// add.rn.f32x2.  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 4
+// immediate (K, G are template parameters) and the two strands are accumulated in int32 (ptxas fuses
+// the adds of two groups into one IADD3).  The CTA streams over its sub-tiles of 8192 window starts: every thread scores 4
 // consecutive starts from a 48-base register window and writes 16 B per strand (streaming stores,
 // 512 contiguous bytes per warp).
 __device__ __forceinline__ uint64_t lds64(uint32_t addr)
@@ -52,12 +60,6 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr)
     uint64_t v;
     asm("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
 }
 
 template <int K, int G>
@@ -70,7 +72,9 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
     const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
     float *row_f = P.out_fwd + (size_t)m * P.pitch;
     float *row_r = P.out_rev + (size_t)m * P.pitch;
-    const uint64_t qnan2 = 0x7FC000007FC00000ull;
+    const float scale = __ldg(P.dscale + m);
+    const int32_t neg_thr = __ldg(P.dneg + m);
+    const float qnan = __uint_as_float(0x7FC00000u), ninf = __uint_as_float(0xFF800000u);
 
     // raw words are prefetched three tiles ahead (one round of the 32 resident warps is shorter
     // than an HBM round trip; ncu showed long-scoreboard stalls at smaller distances).  3 packed words (96 bases from a 16-base boundary) and 2 mask words cover the
@@ -100,7 +104,7 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
             inv_lo = __funnelshift_r(cur.m0, cur.m1, msh);
             inv_hi = cur.m1 >> msh;
         }
-        uint64_t acc[kPosPerThread];
+        int32_t accf[kPosPerThread], accr[kPosPerThread];
 #pragma unroll
         for (int g = 0; g < G; g++) {
 #pragma unroll
@@ -108,7 +112,8 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
                 // bits [7, 7+2K) of t = k-mer code at base p0 + p + K*g
                 const uint32_t t = (2 * p >= 7) ? (w0 >> (2 * p - 7)) : (w0 << (7 - 2 * p));
                 const uint64_t v = lds64(((t & kIndexMask) | lut_lane_addr) + g * kGroupBytes);
-                acc[p] = g == 0 ? v : add_f32x2(acc[p], v);
+                accf[p] = g == 0 ? (int32_t)(uint32_t)v : accf[p] + (int32_t)(uint32_t)v;
+                accr[p] = g == 0 ? (int32_t)(v >> 32) : accr[p] + (int32_t)(v >> 32);
             }
             if (g + 1 < G) {
                 w0 = __funnelshift_r(w0, w1, 2 * K);
@@ -120,9 +125,10 @@ __device__ __forceinline__ void dense_tiles(const ScanParams &P, int m, int L, u
 #pragma unroll
         for (int p = 0; p < kPosPerThread; p++) {
             const bool bad = (__funnelshift_r(inv_lo, inv_hi, p) & lmask) != 0u;
-            const uint64_t a = bad ? qnan2 : acc[p];
-            af[p] = __uint_as_float((uint32_t)a);
-            ar[p] = __uint_as_float((uint32_t)(a >> 32));
+            const float f = accf[p] < neg_thr ? ninf : __int2float_rn(accf[p]) * scale;
+            const float r = accr[p] < neg_thr ? ninf : __int2float_rn(accr[p]) * scale;
+            af[p] = bad ? qnan : f;
+            ar[p] = bad ? qnan : r;
         }
         // one fully contiguous 512 B store per warp and strand (a stride-32 B pattern writes half
         // sectors: twice the L1->XBAR sector traffic and store wavefronts, ncu r01)
@@ -160,7 +166,7 @@ scan_dense_kernel(const ScanParams P)
     // base | (kmer << 7) | ((lane & 15) << 3)
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(dense_smem_raw);
     const uint32_t pad = ((raw + 32767u) & ~32767u) - raw;
-    float2 *s_lut = reinterpret_cast<float2 *>(dense_smem_raw + pad);  // [G][4^K][16]
+    int2 *s_lut = reinterpret_cast<int2 *>(dense_smem_raw + pad);  // [G][4^K][16]
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lut_lane_addr = raw + pad + (uint32_t)(lane & 15) * 8u;
 
@@ -169,7 +175,7 @@ scan_dense_kernel(const ScanParams P)
         const int K = gl >> 16, G = (gl >> 8) & 255, L = gl & 255;
         __syncthreads();  // everyone is done with the previous motif's table
         {
-            const float2 *src = P.lut + __ldg(P.lut_off + m);
+            const int2 *src = P.lut + __ldg(P.lut_off + m);
             const int total = G << (2 * K + 4);  // G * 4^K entries x 16 copies
             for (int i = tid; i < total; i += kScanThreads) s_lut[i] = __ldg(src + (i >> 4));
         }
@@ -191,6 +197,8 @@ void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_
     P.mask = seq->mask;
     P.pitch = pitch;
     P.lut = pw->lut;
+    P.dscale = pw->dense_scale;
+    P.dneg = pw->dense_neg;
     P.lut_off = pw->lut_off;
     P.glen = pw->glen;
     P.M = pw->M;
@@ -199,7 +207,86 @@ void fill_params(ScanParams &P, const tfbs_seq *seq, const tfbs_pwms *pw, int64_
 
 }  // namespace
 
+// Fixed-point k-mer tables of one motif for the dense kernel.  F / R: exact fwd / reverse-complement
+// matrices [L][4].  k = 4 for L <= 24, else 3; entry (g, x) = sum of the <= k log-odds values of
+// columns k*g.. selected by the k-mer x (first base in the low bits), in double.  The scale 2^e is the
+// largest power of two (e <= 30) for which every window sum of rounded entries stays inside int32:
+//   no -inf entry :  sum_g max_x |q| <= 2^31 - 1
+//   with -inf     :  -inf groups become NEG = -(2 Rq + 1), Rq = sum_g max_x |q| over finite entries, so
+//                    a window with a -inf group sums to <= NEG + Rq < -Rq <= any finite window sum and
+//                    G * |NEG| + Rq must fit: the kernel reports -inf when the sum is < *neg_thr = -Rq.
+// Appends G * 4^k int2 (fwd, rev) to `lut`.
+void tfbs_dense_quantise(const double *F, const double *R, int L, int *K_out, int *G_out, int *e_out,
+                         int32_t *neg_thr, std::vector<int2> &lut)
+{
+    const int K = L <= 24 ? 4 : 3, G = (L + K - 1) / K, E = 1 << (2 * K);
+    std::vector<double> sf((size_t)G * E), sr((size_t)G * E);
+    bool has_inf = false;
+    double Rsum = 0.0;  // sum over groups of the largest finite |entry|
+    for (int g = 0; g < G; g++) {
+        double gmax = 0.0;
+        for (int x = 0; x < E; x++) {
+            double a = 0.0, b = 0.0;
+            for (int j = 0; j < K && K * g + j < L; j++) {
+                const int base = (x >> (2 * j)) & 3;
+                a += F[(K * g + j) * 4 + base];
+                b += R[(K * g + j) * 4 + base];
+            }
+            sf[(size_t)g * E + x] = a;
+            sr[(size_t)g * E + x] = b;
+            if (std::isinf(a)) has_inf = true; else gmax = std::max(gmax, std::fabs(a));
+            if (std::isinf(b)) has_inf = true; else gmax = std::max(gmax, std::fabs(b));
+        }
+        Rsum += gmax;
+    }
+    // rounding adds at most 1/2 per group to a window sum
+    const double room = has_inf ? (2147483647.0 - G) / (2.0 * G + 1.0) - G : 2147483647.0 - G;
+    int e = 30;
+    while (e > -60 && std::ldexp(Rsum, e) > room) e--;
+    int64_t Rq = 0;
+    std::vector<int64_t> qf((size_t)G * E), qr((size_t)G * E);
+    for (int g = 0; g < G; g++) {
+        int64_t gmax = 0;
+        for (int x = 0; x < E; x++) {
+            const double a = sf[(size_t)g * E + x], b = sr[(size_t)g * E + x];
+            const int64_t ia = std::isinf(a) ? INT64_MIN : (int64_t)std::llrint(std::ldexp(a, e));
+            const int64_t ib = std::isinf(b) ? INT64_MIN : (int64_t)std::llrint(std::ldexp(b, e));
+            qf[(size_t)g * E + x] = ia;
+            qr[(size_t)g * E + x] = ib;
+            if (ia != INT64_MIN) gmax = std::max<int64_t>(gmax, ia < 0 ? -ia : ia);
+            if (ib != INT64_MIN) gmax = std::max<int64_t>(gmax, ib < 0 ? -ib : ib);
+        }
+        Rq += gmax;
+    }
+    const int64_t NEG = -(2 * Rq + 1);
+    for (size_t i = 0; i < qf.size(); i++)
+        lut.push_back(make_int2((int)(qf[i] == INT64_MIN ? NEG : qf[i]), (int)(qr[i] == INT64_MIN ? NEG : qr[i])));
+    *K_out = K;
+    *G_out = G;
+    *e_out = e;
+    *neg_thr = has_inf ? (int32_t)(-Rq) : INT32_MIN;
+}
+
 extern "C" {
+
+int tfbs_debug_dense_tables(const double *logodds, int32_t L, int32_t *K, int32_t *G, int32_t *scale_exp,
+                            int32_t *neg_thr, int32_t *entries, int64_t cap)
+{
+    TFBS_REQUIRE(logodds && K && G && scale_exp && neg_thr && L >= 1 && L <= TFBS_MAX_MOTIF_LEN,
+                 "tfbs_debug_dense_tables: bad argument");
+    double F[TFBS_MAX_MOTIF_LEN * 4], R[TFBS_MAX_MOTIF_LEN * 4];
+    tfbs_fill_exact(logodds, L, 0, L, F, R);
+    std::vector<int2> lut;
+    int k = 0, g = 0, e = 0;
+    tfbs_dense_quantise(F, R, L, &k, &g, &e, neg_thr, lut);
+    *K = k; *G = g; *scale_exp = e;
+    if (entries) {
+        TFBS_REQUIRE(cap >= (int64_t)lut.size() * 2, "tfbs_debug_dense_tables: entries holds %lld < %lld",
+                     (long long)cap, (long long)lut.size() * 2);
+        for (size_t i = 0; i < lut.size(); i++) { entries[2 * i] = lut[i].x; entries[2 * i + 1] = lut[i].y; }
+    }
+    return TFBS_OK;
+}
 
 int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, int32_t M,
                     int32_t Lmax, tfbs_pwms **out)
@@ -225,8 +312,9 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->logodds.assign(logodds, logodds + (size_t)M * Lmax * 4);
 
     std::vector<double> exact((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
-    std::vector<int32_t> lut_off(M), glen(M);
-    std::vector<float2> lut;
+    std::vector<int32_t> lut_off(M), glen(M), dneg(M);
+    std::vector<float> dscale(M);
+    std::vector<int2> lut;
     int Gmax = 0;
     size_t dense_lut_bytes = 0;  // largest per-motif table once expanded to 16 lane copies
     for (int m = 0; m < M; m++) {
@@ -235,21 +323,13 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
         double *F = &exact[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4];
         double *R = &exact[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4];
         tfbs_fill_exact(logodds, Lmax, m, L, F, R);
-        // dense mode: fp32 k-mer tables, k = 4 (256 entries per group) for L <= 24, else k = 3
-        const int K = L <= 24 ? 4 : 3, Gd = (L + K - 1) / K, E = 1 << (2 * K);
+        // dense mode: fixed-point k-mer tables, k = 4 (256 entries per group) for L <= 24, else k = 3
+        int K = 0, Gd = 0, e = 0;
         lut_off[m] = (int32_t)lut.size();
+        tfbs_dense_quantise(F, R, L, &K, &Gd, &e, &dneg[m], lut);
+        dscale[m] = std::ldexp(1.0f, -e);
         glen[m] = (K << 16) | (Gd << 8) | L;
-        dense_lut_bytes = std::max(dense_lut_bytes, (size_t)Gd * E * 16 * sizeof(float2));
-        for (int g = 0; g < Gd; g++)
-            for (int x = 0; x < E; x++) {
-                double sf = 0.0, sr = 0.0;
-                for (int j = 0; j < K && K * g + j < L; j++) {
-                    const int b = (x >> (2 * j)) & 3;
-                    sf += F[(K * g + j) * 4 + b];
-                    sr += R[(K * g + j) * 4 + b];
-                }
-                lut.push_back(make_float2((float)sf, (float)sr));
-            }
+        dense_lut_bytes = std::max(dense_lut_bytes, (size_t)Gd * (1 << (2 * K)) * 16 * sizeof(int2));
     }
     p->dense_lut_bytes = dense_lut_bytes;
     p->Gmax = Gmax;
@@ -277,7 +357,9 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->hq_lut_words = words;
 
     cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&p->lut, lut.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->lut, lut.size() * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->dense_scale, M * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&p->dense_neg, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->lut_off, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->glen, M * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&p->hq_lut_dev, (size_t)p->hq_lut_words * 4);
@@ -288,7 +370,9 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     if (e == cudaSuccess) e = cudaMalloc(&p->lens_dev, (size_t)M * 4);
     if (e == cudaSuccess) e = cudaMemcpy(p->lens_dev, lens, (size_t)M * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->exact, exact.data(), exact.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(p->lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->lut, lut.data(), lut.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->dense_scale, dscale.data(), M * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->dense_neg, dneg.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->lut_off, lut_off.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->glen, glen.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -306,6 +390,8 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (p->ctx) cudaSetDevice(p->ctx->device);
     if (p->exact) cudaFree(p->exact);
     if (p->lut) cudaFree(p->lut);
+    if (p->dense_scale) cudaFree(p->dense_scale);
+    if (p->dense_neg) cudaFree(p->dense_neg);
     if (p->lut_off) cudaFree(p->lut_off);
     if (p->glen) cudaFree(p->glen);
     if (p->hq_lut_dev) cudaFree(p->hq_lut_dev);

@@ -3,10 +3,33 @@
 The reference obtains MGW / ProT / Roll / HelT / EP out of process from the Bioconductor
 package DNAshapeR (get_DNA_shapes.R:23-25, create_bkg_seqs.py:365-366) and then parses its
 text output (build_features.py:193-198, 215-241).  Here the pentamer lookup runs on the GPU
-straight from the 2-bit encoded sequence.  The real 1024-entry query tables are not
-redistributable with this repository (and R is absent from the image), so `synthetic_tables`
-provides seeded tables in realistic ranges; `load_tables` accepts the real ones.
+straight from the 2-bit encoded sequence.
+
+PENTAMER TABLES.  The real 1024-entry query tables are not redistributable with this repository (and
+R is absent from the build image), so every product entry point REQUIRES tables: pass `tables=` /
+`kinds=`, or point the environment variable TFBS_SHAPE_TABLES at a table file; without either the
+call raises (`resolve_tables`).  `synthetic_tables` (seeded values in realistic ranges) exists for
+tests, bench.py and examples only and must be requested with `synthetic=True`.
+
+Where the real tables come from — DNAshapeR itself, through the text format this module already
+reads (no access to DNAshapeR internals needed):
+    1. `write_pentamer_fasta("pentamers.fa")` writes the 1024 pentamers as 5-bp records;
+    2. in R: `library(DNAshapeR); getShape("pentamers.fa")` (get_DNA_shapes.R:23-25 does exactly
+       this per FASTA file) writes pentamers.fa.{MGW,HelT,ProT,Roll,EP};
+    3. `tables_from_shape_files("pentamers.fa")` reads them back: a 5-bp record has exactly one
+       pentamer, so token 2 of a per-nucleotide track is its table value and tokens 1 / 2 of a per-step
+       track are Y1 / Y2 (SURVEY.md A.2);
+    4. `save_tables("dnashape_tables.tsv", tables, kinds)`, then `export TFBS_SHAPE_TABLES=...`.
+
+Table file format (`save_tables` / `load_tables`): tab-separated text, one header line
+`pentamer<TAB>col...`, one line per pentamer (ACGT, upper case).  A per-nucleotide shape X has one
+column `X`; a per-step shape Y has two, `Y_1` (value for the step before the centre) and `Y_2` (step
+after it).  Either all 1024 pentamers, or only one of each reverse-complement pair (512): the other
+is filled in by symmetry (per-nucleotide: same value; per-step: Y1(P) = Y2(revcomp P)).
 """
+import os
+import warnings
+
 import numpy as np
 
 from . import _lib
@@ -55,22 +78,121 @@ def synthetic_tables(shapes=SHAPES, seed: int = 39):
     return tables, kinds
 
 
-def load_tables(mapping: dict, shapes=SHAPES):
-    """Build the table array from {shape: {pentamer str: value or (y1, y2)}} (real tables)."""
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+PENTAMERS = ["".join("ACGT"[(i >> (2 * (4 - k))) & 3] for k in range(5)) for i in range(1024)]
+
+
+def resolve_tables(tables=None, kinds=None, shapes=SHAPES, synthetic: bool = False):
+    """The (tables, kinds) a product entry point uses: the arguments if given; else the file named by
+    $TFBS_SHAPE_TABLES; else — only when the caller explicitly passes synthetic=True (tests, bench,
+    examples) — the seeded stand-in tables.  Anything else raises: shape values are never fabricated
+    silently."""
+    if tables is not None:
+        if kinds is None:
+            kinds = np.array([KIND[s] for s in shapes], dtype=np.int32)
+        return tables, kinds
+    path = os.environ.get("TFBS_SHAPE_TABLES")
+    if path:
+        return load_tables(path, shapes)
+    if synthetic:
+        warnings.warn("using SYNTHETIC pentamer tables: shape values are not DNAshapeR's", stacklevel=3)
+        return synthetic_tables(shapes)
+    raise ValueError(
+        "no DNA-shape pentamer tables: pass tables=/kinds= (dnashape.load_tables(path)) or set "
+        "TFBS_SHAPE_TABLES to a table file; see discover_tfbs_b200/dnashape.py for how to export the real "
+        "tables from DNAshapeR.  (synthetic=True selects seeded stand-in tables for tests only.)")
+
+
+def write_pentamer_fasta(path: str) -> str:
+    """The 1024 pentamers as 5-bp FASTA records (input for DNAshapeR::getShape, see module docstring)."""
+    with open(path, "w") as fh:
+        for p in PENTAMERS:
+            fh.write(f">{p}\n{p}\n")
+    return path
+
+
+def tables_from_shape_files(fasta_path: str, shapes=SHAPES):
+    """Read `<fasta_path>.<shape>` files DNAshapeR wrote for the pentamer FASTA -> (tables, kinds)."""
+    from .utils import parse_fasta
+
+    mapping = {}
+    for name in shapes:
+        rows = {}
+        for pent, body in parse_fasta(f"{fasta_path}.{name}"):
+            tok = body.strip().split(",")
+            rows[pent] = float(tok[2]) if KIND[name] == _lib.PER_NUCLEOTIDE else (float(tok[1]), float(tok[2]))
+        mapping[name] = rows
+    return load_tables(mapping, shapes)
+
+
+def save_tables(path: str, tables, kinds, shapes=SHAPES) -> str:
+    """Write the table file format described in the module docstring (all 1024 pentamers)."""
+    cols = []
+    for t, name in enumerate(shapes):
+        cols += [name] if kinds[t] == _lib.PER_NUCLEOTIDE else [f"{name}_1", f"{name}_2"]
+    with open(path, "w") as fh:
+        fh.write("pentamer\t" + "\t".join(cols) + "\n")
+        for i, p in enumerate(PENTAMERS):
+            vals = []
+            for t in range(len(shapes)):
+                vals += [tables[t][0][i]] if kinds[t] == _lib.PER_NUCLEOTIDE else [tables[t][0][i], tables[t][1][i]]
+            fh.write(p + "\t" + "\t".join(repr(float(np.float32(v))) for v in vals) + "\n")
+    return path
+
+
+def _read_table_file(path: str, shapes):
+    with open(path) as fh:
+        header = fh.readline().rstrip("\n").split("\t")
+        if not header or header[0] != "pentamer":
+            raise ValueError(f"{path}: first column of a shape table file must be 'pentamer'")
+        col = {name: i for i, name in enumerate(header)}
+        mapping = {name: {} for name in shapes}
+        for line in fh:
+            f = line.rstrip("\n").split("\t")
+            if len(f) < 2:
+                continue
+            for name in shapes:
+                if KIND[name] == _lib.PER_NUCLEOTIDE:
+                    if name not in col:
+                        raise ValueError(f"{path}: no column '{name}'")
+                    mapping[name][f[0]] = float(f[col[name]])
+                else:
+                    if f"{name}_1" not in col or f"{name}_2" not in col:
+                        raise ValueError(f"{path}: no columns '{name}_1' / '{name}_2'")
+                    mapping[name][f[0]] = (float(f[col[f"{name}_1"]]), float(f[col[f"{name}_2"]]))
+    return mapping
+
+
+def load_tables(source, shapes=SHAPES):
+    """Real tables -> (float32[T][2][1024], kinds).  `source` is a table file path (format in the module
+    docstring) or a mapping {shape: {pentamer str: value or (y1, y2)}}.  Pentamers missing from the
+    input are filled from their reverse complement; anything still missing raises."""
+    mapping = _read_table_file(source, shapes) if isinstance(source, (str, os.PathLike)) else source
     tables = np.full((len(shapes), 2, 1024), np.nan, dtype=np.float32)
     kinds = np.array([KIND[s] for s in shapes], dtype=np.int32)
-    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    rc = _revcomp_index(np.arange(1024))
     for t, name in enumerate(shapes):
         for pent, val in mapping[name].items():
+            if len(pent) != 5:
+                raise ValueError(f"'{pent}' is not a pentamer")
             i = 0
             for ch in pent.upper():
-                i = i * 4 + code[ch]
+                i = i * 4 + _CODE[ch]
             if kinds[t] == _lib.PER_NUCLEOTIDE:
                 tables[t, 0, i] = tables[t, 1, i] = float(val)
             else:
                 tables[t, 0, i], tables[t, 1, i] = float(val[0]), float(val[1])
+        # reverse-complement symmetry fills the other half of a 512-row table
+        miss = np.isnan(tables[t, 0])
+        if kinds[t] == _lib.PER_NUCLEOTIDE:
+            tables[t, 0, miss] = tables[t, 0, rc[miss]]
+            tables[t, 1] = tables[t, 0]
+        else:
+            tables[t, 0, miss] = tables[t, 1, rc[miss]]
+            miss2 = np.isnan(tables[t, 1])
+            tables[t, 1, miss2] = tables[t, 0, rc[miss2]]
     if np.isnan(tables).any():
-        raise ValueError("shape table is missing pentamers")
+        raise ValueError("shape table is missing pentamers (and their reverse complements)")
     return tables, kinds
 
 
@@ -88,17 +210,16 @@ def format_tokens(track: np.ndarray, n_tokens: int) -> list:
     return ["NA" if v != v else "%.2f" % v for v in np.asarray(track[:n_tokens], dtype=np.float64)]
 
 
-def getDNAShape(fasta_path: str, shape: str, ctx=None, tables=None, kinds=None, shapes=SHAPES):
+def getDNAShape(fasta_path: str, shape: str, ctx=None, tables=None, kinds=None, shapes=SHAPES, synthetic=False):
     """DNAshapeR::getDNAShape(filename, shapeType) (create_bkg_seqs.py:365-366): writes
     `<fasta_path>.<shape>` with one '>name' line per record followed by comma-separated values
-    wrapped at 20 per line, NA at the undefined ends."""
+    wrapped at 20 per line, NA at the undefined ends.  Tables: see `resolve_tables` (raises without)."""
     from .utils import parse_fasta
 
+    tables, kinds = resolve_tables(tables, kinds, shapes, synthetic)  # raises before any GPU work
     own = ctx is None
     ctx = _lib.Context(0) if own else ctx
     try:
-        if tables is None:
-            tables, kinds = synthetic_tables(shapes)
         t = list(shapes).index(shape)
         tab = ctx.upload_shapes(tables[t: t + 1], kinds[t: t + 1])
         names, recs = zip(*parse_fasta(fasta_path))

@@ -79,7 +79,9 @@ class GenomeShapeSource:
     instead of the reference's {shape: {chrom: [tokens]}} dict."""
 
     def __init__(self, genome_fasta=None, records=None, tables=None, kinds=None,
-                 shapes=dnashape.SHAPES, trailing_empty=True, ctx=None):
+                 shapes=dnashape.SHAPES, trailing_empty=True, ctx=None, synthetic=False):
+        # pentamer tables are required (argument or $TFBS_SHAPE_TABLES); never fabricated silently
+        tables, kinds = dnashape.resolve_tables(tables, kinds, shapes, synthetic)
         self.ctx = ctx or default_context()
         if records is None:
             records = dict(parse_fasta(genome_fasta))
@@ -88,8 +90,6 @@ class GenomeShapeSource:
         self.start = dict(zip(self.names, starts.tolist()))
         self.length = dict(zip(self.names, lens.tolist()))
         self.enc = self.ctx.encode(buf)
-        if tables is None:
-            tables, kinds = dnashape.synthetic_tables(shapes)
         self.shapes = tuple(shapes)
         self.kinds = np.asarray(kinds, dtype=np.int32)
         self.tables = self.ctx.upload_shapes(tables, kinds)
@@ -221,7 +221,12 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
         tf_data["GC_content"] = np.zeros(0)
 
     if similarity_features:
-        if len(seqs) and similarity.acgt_only(seqs) and similarity.acgt_only(true_seqs):
+        if len(seqs):
+            if not (similarity.acgt_only(seqs) and similarity.acgt_only(true_seqs)):
+                # no host fallback: the all-pairs kernel works on 2-bit k-mers (the reference raises
+                # KeyError on lower case as well, utils.py:104)
+                raise ValueError("MinHash/PAS/PPS need upper-case ACGT sequences; pass "
+                                 "similarity_features=False to skip these columns")
             # all-pairs kernel (tfbs_similarity_sums); k-mer / hash preparation is vectorised host code
             if minhash:
                 print(strftime("%x %X | Calculating MinHash similarity score"))
@@ -232,35 +237,20 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
             tf_data["PAS"] = pas
             tf_data["PPS"] = pps
         else:
-            # IUPAC / lower-case input: keep the reference's exact string semantics on the host
             if minhash:
-                print(strftime("%x %X | Calculating MinHash similarity score"))
-                tf_data["MinHash"] = [similarity.minhash_similarity(s, true_seqs) for s in seqs]
-            print(strftime("%x %X | Calculating Poisson similarity scores"))
-            pbs = [similarity.pac_similarity(s, true_seqs) for s in seqs]
-            tf_data["PAS"] = [p["PAS"] for p in pbs]
-            tf_data["PPS"] = [p["PPS"] for p in pbs]
+                tf_data["MinHash"] = np.zeros(0)
+            tf_data["PAS"] = np.zeros(0)
+            tf_data["PPS"] = np.zeros(0)
 
     if pwms is not None and enc is not None:
         print(strftime("%x %X | Scoring position weight matrices on both strands"))
         lib = ctx.upload_pwms(list(pwms))
-        fwd, rev = ctx.scan_dense(enc, lib)
+        # reduced on the device (tfbs_scan_best): S x M x 2 floats cross PCIe, not the dense [M][n] arrays
+        best = ctx.scan_best(enc, lib, starts, lens)
         names = pwm_names or [f"PWM{i + 1}" for i in range(lib.M)]
         for m, name in enumerate(names):
-            L = int(lib.lens[m])
-            best_f = np.full(len(seqs), np.nan)
-            best_r = np.full(len(seqs), np.nan)
-            with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
-                __import__("warnings").simplefilter("ignore", RuntimeWarning)  # all-NaN rows stay NaN
-                for ln in np.unique(lens):
-                    if ln < L:
-                        continue
-                    rows = np.flatnonzero(lens == ln)
-                    idx = starts[rows][:, None] + np.arange(int(ln) - L + 1)[None, :]
-                    best_f[rows] = np.nanmax(fwd[m][idx], axis=1)
-                    best_r[rows] = np.nanmax(rev[m][idx], axis=1)
-            tf_data[f"{name}_fwd_max"] = best_f
-            tf_data[f"{name}_rev_max"] = best_r
+            tf_data[f"{name}_fwd_max"] = best[:, m, 0].astype(np.float64)
+            tf_data[f"{name}_rev_max"] = best[:, m, 1].astype(np.float64)
         lib.close()
 
     if genome_wide_shape_data:
@@ -280,18 +270,18 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
     return tf_data
 
 
-def background_shape_table(bkg_fasta: str, tables=None, kinds=None, shapes=dnashape.SHAPES, ctx=None):
+def background_shape_table(bkg_fasta: str, tables=None, kinds=None, shapes=dnashape.SHAPES, ctx=None,
+                           synthetic=False):
     """GPU equivalent of the driver glue at build_features.py:215-241: DNA-shape columns of the
     2+2-padded background records (MGW/ProT/EP trimmed [2:-2], Roll/HelT trimmed [1:-1], NA ->
     0.0), returned as the `shapes_data_df` the driver merges on 'location' (:243-251)."""
+    tables, kinds = dnashape.resolve_tables(tables, kinds, shapes, synthetic)
     ctx = ctx or default_context()
     names, recs = [], []
     for name, seq in parse_fasta(bkg_fasta):
         names.append(name)
         recs.append(seq)
     buf, starts, lens = join_records(recs)
-    if tables is None:
-        tables, kinds = dnashape.synthetic_tables(shapes)
     tab = ctx.upload_shapes(tables, kinds)
     enc = ctx.encode(buf)
     width = int(lens.max()) - 3 if len(recs) else 1

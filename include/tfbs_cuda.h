@@ -125,11 +125,23 @@ int tfbs_pwms_destroy(tfbs_pwms *p);
 /* Dense mode: fwd[m][i], rev[m][i] = float32 score of motif m at start i on the + strand and of
  * its reverse-complement matrix at the same window (so rev[m][i] == fwd score of
  * revcomp(seq) at n-L-i); NaN where the window touches an invalid byte or runs past n.
- * Output layout [M][n] row-major, fp32 accumulation of double-precomputed k-mer partial sums
- * (|error| <= 1e-4 vs the double-accumulating oracle is asserted in tests).
+ * Output layout [M][n] row-major.  Scores are accumulated exactly in per-motif scaled int32 fixed
+ * point over double-precomputed k-mer partial sums and converted once to float, so they differ from
+ * the double-accumulating oracle by at most one float rounding step of the score
+ * (|error| <= 1e-4 for |score| < 1024, asserted in tests on adversarial sharp long motifs).
  * Host pointers may be NULL: results then stay in the context's device scratch (bench `value`). */
 int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, float *fwd_host,
                     float *rev_host);
+/* Per-record best window (the PWM columns of the feature matrix; north_star item (3), joined like the
+ * reference's per-site columns at utils.py:1134-1170): for S records [rec_start, rec_start + rec_len)
+ * of the encoded buffer, best[s][m][0 fwd / 1 rev] = max over the record's windows of the score
+ * calculate() gives (windows touching an invalid byte are skipped, numpy.nanmax semantics; NaN when
+ * the record has no valid window or is shorter than the motif).  pos[s][m][strand] (may be NULL) =
+ * offset of the first best window inside the record, -1 when none.  Every window is summed left to
+ * right in double and the maximum is cast to float once, so values are bit-exact with
+ * max(oracle calculate()).  Only S*M*2 floats cross PCIe instead of the [M][n] dense arrays. */
+int tfbs_scan_best(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const int64_t *rec_start,
+                   const int64_t *rec_len, int64_t S, float *best_host, int32_t *pos_host);
 /* Hits mode: every (motif, start, strand) with (float)score >= thr[motif].  A packed
  * fixed-point filter with a rigorous upper bound selects candidates; each candidate is then
  * re-scored left to right in double and cast to float, so hit sets and scores are bit-exact
@@ -210,6 +222,14 @@ int tfbs_similarity_sums(tfbs_ctx *ctx, const uint32_t *c_words, const uint16_t 
  * The encode kernel converts 4 ASCII bytes per 32-bit word with integer bit tricks; this runs
  * the same inline function on the host so the CPU test-suite can check it exhaustively. */
 int tfbs_debug_swar4(uint32_t four_ascii_bytes, uint32_t *codes8, uint32_t *valid4);
+/* The dense kernel's fixed-point k-mer tables of ONE motif (logodds double[L][4], ACGT): k-mer width
+ * K, groups G, scale exponent e (entries = rint(group sum * 2^e)), the bound below which a window sum
+ * means -inf (INT32_MIN when the motif has no -inf entry), and optionally the entries themselves as
+ * int32[G][4^K][2] (fwd, rev; `cap` = int32 slots `entries` holds).  A window score is
+ * (float)(sum over groups) * 2^-e: lets the CPU suite replay the kernel's arithmetic on adversarial
+ * matrices against the double-accumulating oracle (Biopython _pwm.c semantics). */
+int tfbs_debug_dense_tables(const double *logodds, int32_t L, int32_t *K, int32_t *G, int32_t *scale_exp,
+                            int32_t *neg_thr, int32_t *entries, int64_t cap);
 /* Column grouping of the hits kernel for a motif block of maximum length L: A groups of 4 columns
  * + B groups of 3 (the kernel is instantiated for every pair this can return for L = 1..32). */
 int tfbs_debug_hits_group_plan(int32_t L, int32_t *A, int32_t *B);

@@ -30,10 +30,14 @@ def lib():
         L.oracle_base_counts.restype = None
         L.oracle_pwm_calculate.argtypes = [vp, i64, vp, i32, vp]
         L.oracle_pwm_calculate.restype = None
+        L.oracle_pwm_calculate_mt.argtypes = [vp, i64, vp, i32, vp, i32]
+        L.oracle_pwm_calculate_mt.restype = None
         L.oracle_pwm_revcomp.argtypes = [vp, i32, vp]
         L.oracle_pwm_revcomp.restype = None
         L.oracle_pwm_search.argtypes = [vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64]
         L.oracle_pwm_search.restype = i64
+        L.oracle_pwm_search_mt.argtypes = [vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, i32]
+        L.oracle_pwm_search_mt.restype = i64
         L.oracle_pwm_scan_count.argtypes = [vp, i64, vp, vp, i32, i32, vp, i32, vp, vp]
         L.oracle_pwm_scan_count.restype = i64
         L.oracle_shape_tracks.argtypes = [vp, i64, vp, vp, i32, vp]

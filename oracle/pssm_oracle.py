@@ -56,16 +56,20 @@ def reverse_complement(pssm) -> np.ndarray:
     return np.ascontiguousarray(pssm[::-1, ::-1])
 
 
-def calculate(seq, pssm) -> np.ndarray:
+def calculate(seq, pssm, threads=None) -> np.ndarray:
     """PositionSpecificScoringMatrix.calculate via the C loop: float32[n-m+1] (always an array;
-    Biopython returns the bare scalar when n == m)."""
+    Biopython returns the bare scalar when n == m).  threads: None -> the plain loop; an int splits
+    the window starts over that many OpenMP threads (0 = all cores), same output."""
     s = clib.as_bytes(seq)
     m = np.ascontiguousarray(pssm, dtype=np.float64)
     n, L = s.size, m.shape[0]
     if n < L:
         raise ValueError("sequence shorter than motif")
     out = np.empty(n - L + 1, dtype=np.float32)
-    clib.lib().oracle_pwm_calculate(clib.ptr(s), n, clib.ptr(m), L, clib.ptr(out))
+    if threads is None:
+        clib.lib().oracle_pwm_calculate(clib.ptr(s), n, clib.ptr(m), L, clib.ptr(out))
+    else:
+        clib.lib().oracle_pwm_calculate_mt(clib.ptr(s), n, clib.ptr(m), L, clib.ptr(out), int(threads) or host_threads())
     return out
 
 
@@ -110,10 +114,22 @@ def search(seq, pssm, threshold=0.0, both=True):
     return hits
 
 
-def search_library(seq, matrices, lens, thr, cap=None):
+def host_threads() -> int:
+    """Host cores this process may run on (not OMP_NUM_THREADS: torchrun exports that as 1)."""
+    import os
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
+
+
+def search_library(seq, matrices, lens, thr, cap=None, threads=None):
     """Both-strand thresholded scan of one sequence with a motif library via the C loop.
     matrices float64[M][Lmax][4]; returns structured arrays (pos, motif, strand, score)
-    in (motif, pos, strand) order."""
+    in (motif, pos, strand) order.  threads: None -> the single-threaded loop; an int runs the
+    OpenMP form with that many threads (0 = all cores), same output."""
+    if threads is not None:
+        return _search_library_mt(seq, matrices, lens, thr, int(threads) or host_threads())
     s = clib.as_bytes(seq)
     mats = np.ascontiguousarray(matrices, dtype=np.float64)
     lens = np.ascontiguousarray(lens, dtype=np.int32)
@@ -132,6 +148,28 @@ def search_library(seq, matrices, lens, thr, cap=None):
                               clib.ptr(score), cap)
     k = min(cnt, cap)
     return pos[:k], mot[:k], strand[:k], score[:k], cnt
+
+
+def _search_library_mt(seq, matrices, lens, thr, threads):
+    s = clib.as_bytes(seq)
+    mats = np.ascontiguousarray(matrices, dtype=np.float64)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    thr = np.ascontiguousarray(thr, dtype=np.float32)
+    M, Lmax = mats.shape[0], mats.shape[1]
+    L = clib.lib()
+    cap = 1 << 22  # two passes (count, fill) when the hits fit; one more call with the exact size otherwise
+    while True:
+        pos = np.empty(cap, dtype=np.int64)
+        mot = np.empty(cap, dtype=np.int32)
+        strand = np.empty(cap, dtype=np.int32)
+        score = np.empty(cap, dtype=np.float32)
+        cnt = L.oracle_pwm_search_mt(clib.ptr(s), s.size, clib.ptr(mats), clib.ptr(lens), M, Lmax, clib.ptr(thr),
+                                     clib.ptr(pos), clib.ptr(mot), clib.ptr(strand), clib.ptr(score), cap, threads)
+        if cnt <= cap:
+            break
+        cap = int(cnt)
+    pos, mot, strand, score = pos[:cnt].copy(), mot[:cnt].copy(), strand[:cnt].copy(), score[:cnt].copy()
+    return pos, mot, strand, score, int(cnt)
 
 
 def scan_count(seq, matrices, lens, thr, threads=0):

@@ -1,11 +1,165 @@
-"""BASELINE.json full-size configurations checked through size-independent properties (the CPU
-oracle would need hours there): cross-kernel consistency, shard invariance, idempotence."""
+"""BASELINE.json configurations at their stated sizes.
+
+Compared with the CPU ORACLE (OpenMP, all host cores) wherever it finishes in seconds: C1 / C2 in
+full, the whole C3 genome, 2 Mb slices of C4 with the exact 800-PWM bench library and thresholds
+(narrow / sticky block plan asserted), slices of C5 beyond 2^31.  The whole 100 Mb x 800 and 3.1 Gb
+scans (CPU hours) are additionally checked through size-independent properties: cross-kernel
+consistency, shard invariance, idempotence."""
 import numpy as np
 import pytest
 
 from discover_tfbs_b200 import dnashape, sharding, synth
+from oracle import pssm_oracle as po
+from oracle import shape_oracle as so
 
 pytestmark = pytest.mark.gpu
+
+SCORE_ATOL = 1e-4  # north_star tolerance of dense fp32 scores
+THREADS = 0        # oracle: every host core this process may use (sched_getaffinity, not OMP_NUM_THREADS)
+
+
+def _assert_hits_equal_oracle(hits, seq, logodds, lens, thr, offset=0):
+    """hits (sorted (motif, pos, strand)) == oracle search of `seq`, bit-exact incl. scores."""
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=THREADS)
+    assert cnt == hits.size, (cnt, hits.size)
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"]) - offset
+    assert np.array_equal(hits["motif"], mot)
+    assert np.array_equal(gpos, pos)
+    assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
+    assert np.array_equal(hits["score"], score)
+    return cnt
+
+
+def _c1_c2_records():
+    """Configs C1 / C2: 5 000 fg x 200 bp (motif implanted) + 50 000 bkg x 204 bp (2+2 padded)."""
+    mats = [synth.consensus_pwm(39 + i, L) for i, L in enumerate((12, 8, 10, 14, 17, 20))]
+    fg, bkg = synth.peak_set(39, 5000, 200, 10, motif=mats[0][1])
+    bf, sf, lf = synth.join_records(fg)
+    bb, sb, lb = synth.join_records(bkg)
+    buf = np.concatenate([bf, np.array([10], np.uint8), bb])
+    starts = np.concatenate([sf, sb + bf.size + 1])
+    lens = np.concatenate([lf, lb])
+    return buf, starts, lens, [m[0] for m in mats]
+
+
+def test_c1_c2_full_dense_scores_best_windows_and_shape_matrix_vs_oracle(ctx):
+    """C1 (1 PWM, L = 12) and C2 (6 PWMs, L 8-20) over all 55 000 records: every per-position score of
+    both strands within 1e-4 of the oracle, per-record best windows bit-exact, and the 5-track shape
+    matrix bit-exact with oracle_shape_tracks_set."""
+    buf, starts, lens, mats = _c1_c2_records()
+    assert starts.size == 55_000 and buf.size == 5000 * 201 + 50_000 * 205
+    enc = ctx.encode(buf)
+    for name, use in (("C1", mats[:1]), ("C2", mats)):
+        lib = ctx.upload_pwms(use)
+        fwd, rev = ctx.scan_dense(enc, lib)
+        best = ctx.scan_best(enc, lib, starts, lens)
+        for m, mat in enumerate(use):
+            L = mat.shape[0]
+            for strand, arr, mm in ((0, fwd[m], mat), (1, rev[m], po.reverse_complement(mat))):
+                ref = po.calculate(buf, mm, threads=THREADS)
+                got = arr[: ref.size]
+                assert np.array_equal(np.isnan(got), np.isnan(ref)), (name, m, strand)
+                ok = ~np.isnan(ref)
+                assert float(np.max(np.abs(got[ok].astype(np.float64) - ref[ok]))) <= SCORE_ATOL, (name, m, strand)
+                assert np.isnan(arr[ref.size:]).all()
+                # per-record maximum of the oracle's scores (records are ACGT only: no NaN inside a record)
+                for ln in np.unique(lens):
+                    rows = np.flatnonzero(lens == ln)
+                    idx = starts[rows][:, None] + np.arange(int(ln) - L + 1)[None, :]
+                    assert np.array_equal(best[rows, m, strand], ref[idx].max(axis=1)), (name, m, strand, ln)
+        lib.close()
+    tables, kinds = dnashape.synthetic_tables()
+    tab = ctx.upload_shapes(tables, kinds)
+    tracks = ctx.shape_tracks(enc, tab, starts, lens)
+    ref = so.tracks_set(buf, starts, lens, tables, kinds, threads=THREADS)
+    assert np.array_equal(tracks, ref, equal_nan=True)
+    # the per-record matrices the feature table is built from (fg: mode 0 slices, bkg: mode 1 trims)
+    bkg_rows = np.flatnonzero(lens == 204)
+    sites = ctx.shape_sites(enc, tab, starts[bkg_rows], lens[bkg_rows], width=201, mode=1)
+    for t, kind in enumerate(kinds):
+        lo, w = (2, 200) if kind == 0 else (1, 201)
+        idx = starts[bkg_rows][:, None] + lo + np.arange(w)[None, :]
+        want = np.nan_to_num(ref[t][idx], nan=0.0)
+        assert np.array_equal(sites[:, t, :w], want)
+    tab.close()
+    enc.close()
+
+
+def test_c3_whole_genome_hits_vs_oracle(ctx):
+    """C3 in full: 14.3 Mb, 8 chromosomes, 6 PWMs, thresholds 0.8 x max score: the hit set with its
+    scores is bit-exact with the oracle's search over the same buffer."""
+    buf, starts, lens_rec = _c3_genome()
+    mats = [synth.consensus_pwm(39 + i, L)[0] for i, L in enumerate((8, 10, 12, 14, 17, 20))]
+    lib = ctx.upload_pwms(mats)
+    thr = np.array([0.8 * m.max(axis=1).sum() for m in mats], dtype=np.float32)
+    enc = ctx.encode(buf)
+    hits = ctx.scan_hits(enc, lib, thr, cap=1 << 22, sort=True)
+    n = _assert_hits_equal_oracle(hits, buf, lib.logodds, lib.lens, thr)
+    assert n > 100
+    # a second, much denser threshold set (rate ~1e-3 per strand) on the same genome
+    thr2 = synth.thresholds_for_rate(lib.logodds, lib.lens, rate=1e-3, gc=0.335, seed=3, sample=100_000)
+    hits2 = ctx.scan_hits(enc, lib, thr2, cap=1 << 22, sort=True)
+    n2 = _assert_hits_equal_oracle(hits2, buf, lib.logodds, lib.lens, thr2)
+    assert n2 > 50_000
+    enc.close()
+    lib.close()
+
+
+@pytest.mark.parametrize("rate", [1e-4, 1e-3])
+def test_c4_bench_library_slices_vs_oracle(ctx, rate):
+    """The exact bench workload (synth.pwm_library(39, 800, 6, 30), thresholds as bench.py computes
+    them) on three 2 Mb slices of the 100 Mb genome — one starting at 0, one placed across an N run
+    and 32 256-start tile edges, one ending at the genome end: hit sets bit-exact with the oracle, and
+    the block plan really contains the two-motifs-per-lane forms this library is benchmarked with."""
+    total = 100_000_000
+    logodds, lens = synth.pwm_library(39, 800, 6, 30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=rate, gc=0.41, seed=39, sample=100_000)
+    lib = ctx.upload_pwms(logodds, lens)
+    n = 2_000_000
+    # a slice start that puts an N run inside it: search the position-addressable generator
+    blocks = np.arange(40_000_000 >> 14, 90_000_000 >> 14, dtype=np.uint64)   # one candidate run per 16 Ki block
+    rn = synth._mix(39, 2, blocks)
+    b = int(np.flatnonzero((rn & np.uint64(0xFFFF)) < np.uint64(213))[0])
+    n_at = (int(blocks[b]) << 14) + int((rn[b] >> np.uint64(16)) & np.uint64(16383))
+    assert synth.genome(39, n_at, 1, gc=0.41)[0] == ord("N")
+    for start in (0, n_at - 1_000_003, total - n):
+        seq = synth.genome(39, start, n, gc=0.41)
+        enc = ctx.encode(seq)
+        hits = ctx.scan_hits(enc, lib, thr, cap=1 << 22, sort=True)
+        cnt = _assert_hits_equal_oracle(hits, seq, logodds, lens, thr)
+        assert cnt > 0.5 * 2 * rate * n * 800
+        enc.close()
+    forms = [b[2] for b in lib.hits_blocks()]
+    assert sum(b[3] for b in lib.hits_blocks()) == 800
+    assert any(f != 0 for f in forms), forms          # narrow and/or sticky blocks were exercised
+    if rate == 1e-4:
+        assert sum(1 for f in forms if f != 0) >= 8, forms
+    lib.close()
+
+
+def test_c5_slices_beyond_2_31_vs_oracle(ctx):
+    """C5 (3.1 Gb as one flat record): three 1 Mb stretches whose coordinates exceed 2^31 are cut out
+    of the full scan's hit list and compared with the oracle run on the regenerated bases."""
+    n = 3_100_000_000
+    logodds, lens = synth.pwm_library(5, 4, lmin=10, lmax=20)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-5, gc=0.41, seed=5, sample=2_000_000)
+    lib = ctx.upload_pwms(logodds, lens)
+    dev = ctx.synth_ascii(39, 0, n, gc=0.41)
+    enc = ctx.encode_device(dev.ptr, n)
+    dev.close()
+    hits = ctx.scan_hits(enc, lib, thr, cap=1 << 23, sort=True)
+    enc.close()
+    lib.close()
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    w = 1_000_000
+    lmax = int(lens.max())
+    for start in (2**31 - w // 2, 2_600_000_123, n - w):
+        seq = synth.genome(39, start, w, gc=0.41)
+        # windows fully inside [start, start + w): the oracle sees exactly these
+        sel = (gpos >= start) & (gpos + lens[hits["motif"]] <= start + w)
+        part = hits[sel]
+        cnt = _assert_hits_equal_oracle(part, seq, logodds, lens, thr, offset=start)
+        assert cnt > 20 and start + w - lmax > 2**31
 
 
 def _c3_genome():

@@ -135,6 +135,26 @@ def test_dense_every_motif_length_and_minus_inf(ctx):
     _check_dense(ctx, _noisy_seq(rng, 6000), lo, lens)
 
 
+def test_dense_adversarial_sharp_long_motifs(ctx):
+    """L = 30 / 32, consensus-only columns, 5e4 / 1e5 counts, pseudocounts 0.01 /
+    0.001; 3 M random windows plus the all-worst-base and consensus windows on both strands.  The
+    fp32-accumulating kernel of round 1 reached 1.8e-4 here; the fixed-point kernel must stay within
+    SCORE_ATOL of the double-accumulating oracle."""
+    from test_host import adversarial_dense_cases, adversarial_dense_sequence
+
+    cases = adversarial_dense_cases()
+    lo = np.zeros((len(cases), 32, 4))
+    lens = np.array([c[1].shape[0] for c in cases], dtype=np.int32)
+    for i, (_, m) in enumerate(cases):
+        lo[i, : m.shape[0]] = m
+    tails = [adversarial_dense_sequence(m, 0) for _, m in cases]  # worst / consensus windows of every motif
+    seq = np.concatenate([adversarial_dense_sequence(cases[0][1], 3_000_000)] + tails)
+    worst = _check_dense(ctx, seq, lo, lens)
+    ref_min = max(float(po.calculate(seq[-5000:], c[1]).min()) for c in cases)
+    assert ref_min < -550.0, ref_min  # the regime is actually reached
+    print(f"dense adversarial: worst |err| = {worst:.3e}")
+
+
 def test_dense_sequence_shorter_than_motif_and_record_set(ctx):
     logodds, lens = synth.pwm_library(5, 6, lmin=8, lmax=20)
     # a ragged record set: windows crossing the '\n' separators must be NaN
@@ -153,6 +173,54 @@ def test_dense_sequence_shorter_than_motif_and_record_set(ctx):
                 assert np.allclose(fwd[m, s: s + ref.size], ref, atol=SCORE_ATOL, rtol=0)
                 covered[s: s + ref.size] = True
         assert np.isnan(fwd[m, ~covered]).all() and np.isnan(rev[m, ~covered]).all()
+    enc.close()
+    lib.close()
+
+
+def _oracle_best(rec, mat):
+    """(max, first argmax) over the windows of one record, NaN windows skipped; (nan, -1) if none."""
+    if len(rec) < mat.shape[0]:
+        return np.float32(np.nan), -1
+    sc = po.calculate(rec, mat)
+    if np.isnan(sc).all():
+        return np.float32(np.nan), -1
+    return np.nanmax(sc), int(np.nanargmax(sc))
+
+
+def test_scan_best_bit_exact_vs_oracle(ctx):
+    """tfbs_scan_best (per-record PWM feature columns): ragged records with N runs, records shorter than
+    the motif, -inf entries; values bit-exact with max over the oracle's calculate(), offsets = first max."""
+    rng = np.random.default_rng(21)
+    recs = []
+    for k in (0, 1, 5, 8, 19, 20, 21, 33, 64, 200, 204, 1000, 4097):
+        r = rng.choice(list("ACGTacgt"), size=k)
+        if k >= 20:
+            r[rng.integers(0, k, size=max(k // 40, 1))] = "N"
+        recs.append("".join(r))
+    recs.append("N" * 50)
+    recs.append("ACGT" * 10)  # periodic: many ties, first maximum must win
+    mats = []
+    for L in (1, 6, 8, 12, 16, 17, 20, 24, 25, 30, 32):
+        counts = rng.integers(0, 50, size=(L, 4)).astype(float)
+        if L in (12, 25):
+            counts[rng.random((L, 4)) < 0.15] = 0.0
+            counts[counts.sum(axis=1) == 0, 2] = 3.0
+            mats.append(po.log_odds(po.normalize(counts)))
+        else:
+            mats.append(po.log_odds(po.normalize(counts, 0.5)))
+    buf, starts, lens = synth.join_records(recs)
+    enc = ctx.encode(buf)
+    lib = ctx.upload_pwms(mats)
+    best, pos = ctx.scan_best(enc, lib, starts, lens, with_pos=True)
+    only = ctx.scan_best(enc, lib, starts, lens)
+    assert np.array_equal(best, only, equal_nan=True)
+    for s, rec in enumerate(recs):
+        for m, mat in enumerate(mats):
+            for strand, mm in ((0, mat), (1, po.reverse_complement(mat))):
+                want, at = _oracle_best(rec, mm)
+                got = best[s, m, strand]
+                assert (np.isnan(want) and np.isnan(got)) or want == got, (s, m, strand, want, got)
+                assert pos[s, m, strand] == at, (s, m, strand, at, pos[s, m, strand])
     enc.close()
     lib.close()
 
@@ -431,8 +499,10 @@ def test_similarity_pairs_vs_reference_golden(ctx, golden):
 
 def test_similarity_all_pairs_vs_scalar_host(ctx):
     """200-bp records (k = 8), low-complexity repeats (k-mer multiplicities > 1) and a mixed-length
-    true set (several k) against the scalar restatement of the reference's loops."""
+    true set (several k) against the scalar restatement of the reference's loops
+    (oracle/similarity_oracle.py, itself pinned to the reference's outputs in tests/test_host.py)."""
     from discover_tfbs_b200 import similarity as sm
+    from oracle import similarity_oracle as so_sim
 
     rng = np.random.default_rng(12)
     def rnd(n, alphabet="ACGT"):
@@ -442,8 +512,8 @@ def test_similarity_all_pairs_vs_scalar_host(ctx):
     mh, pas, pps = sm.similarity_columns_gpu(ctx, cand, set(true))
     uniq = set(true)
     for i, c in enumerate(cand):
-        assert abs(mh[i] - sm.minhash_similarity(c, uniq)) < 1e-12
-        ref = sm.pac_similarity(c, uniq)
+        assert abs(mh[i] - so_sim.minhash_similarity(c, uniq)) < 1e-12
+        ref = so_sim.pac_similarity(c, uniq)
         assert abs(pas[i] - ref["PAS"]) < 1e-12 and abs(pps[i] - ref["PPS"]) < 1e-12, i
 
 
@@ -560,33 +630,36 @@ def test_legacy_get_shape_data_vs_reference_golden(ctx, golden, tmp_path):
 
 
 @pytest.mark.parametrize("from_sequence", [False, True])
-def test_build_features_driver_vs_reference_golden(ctx, golden, tmp_path, from_sequence):
-    """discover_tfbs_b200.build_features.main with the reference's command line: the feather it writes
-    equals what build_features.py:200-261 yields from the reference's own tables (goldens), both with
-    the ten DNAshapeR text files and with --genome-fasta (shapes from sequence on the GPU)."""
-    from discover_tfbs_b200 import build_features as bf
-
+def test_training_table_flow_vs_reference_golden(ctx, golden, tmp_path, from_sequence):
+    """The calls the reference's driver makes (build_features.py:200-261: fg table with genome-wide
+    shapes, bkg table merged with the trimmed bkg shapes, concat, dropna(axis=1)) give the table the
+    reference itself produced (goldens) — with the DNAshapeR text files as input and with every shape
+    value computed from sequence on the GPU."""
     ft, bg = golden["feature_table"], golden["background"]
     shapes = golden["meta"]["shapes"]
+    tables, kinds = dnashape.synthetic_tables(tuple(shapes), seed=golden["meta"]["table_seed"])
+    fg_path, bkg_path = str(tmp_path / "fg.fasta"), str(tmp_path / "bkg.fasta")
     (tmp_path / "fg.fasta").write_text("".join(f">{n}\n{s}\n" for n, s in ft["fg"]))
-    (tmp_path / "fg.bed").write_text("")
     (tmp_path / "bkg.fasta").write_text("".join(f">{n}\n{s}\n" for n, s in bg["records"]))
-    (tmp_path / "genome.fasta").write_text("".join(f">{c}\n{s}\n" for c, s in golden["genome"].items()))
-    bkg_files, gw_files = [], []
-    for shape in shapes:
-        p = tmp_path / f"bkg.fasta.{shape}"
-        p.write_text(bg["shape_file_text"][shape])
-        bkg_files.append(str(p))
-        q = tmp_path / f"genome_oneline.fasta.{shape}"
-        q.write_text("".join(f">{c}\n" + ",".join(golden["shape_tokens"][shape][c]) + "\n" for c in golden["genome"]))
-        gw_files.append(str(q))
-    out = tmp_path / "train.feather"
-    argv = ["tec1", str(tmp_path / "fg.fasta"), str(tmp_path / "fg.bed"), str(tmp_path / "bkg.fasta"), *bkg_files,
-            *gw_files, str(out), str(tmp_path / "pca.pdf")]
     if from_sequence:
-        argv += ["--genome-fasta", str(tmp_path / "genome.fasta")]
-    bf.main(argv)
-    got = pd.read_feather(out)
+        shape_data = U.GenomeShapeSource(records=golden["genome"], tables=tables, kinds=kinds, shapes=tuple(shapes), ctx=ctx)
+        shapes_df = U.background_shape_table(bkg_path, tables, kinds, tuple(shapes), ctx=ctx)
+    else:
+        shape_data = {sh: {c: golden["shape_tokens"][sh][c] for c in golden["genome"]} for sh in shapes}
+        rows = {}
+        for sh in shapes:  # the text DNAshapeR wrote for the background FASTA, trimmed as the driver does
+            path = tmp_path / f"bkg.fasta.{sh}"
+            path.write_text(bg["shape_file_text"][sh])
+            for name, body in U.parse_fasta(str(path)):
+                rows.setdefault(name, {}).update(so.bkg_trim(body.strip().split(",") if sh in ("MGW", "ProT", "EP")
+                                                             else body.split(","), sh))
+        shapes_df = pd.DataFrame.from_dict(rows, orient="index").reset_index().rename(columns={"index": "location"})
+    pos_df = U.build_feature_table(fg_path, fg_path, shape_data, minhash=True, ctx=ctx)
+    pos_df.insert(1, "seq_type", "True")
+    neg_df = U.build_feature_table(bkg_path, fg_path, minhash=True, ctx=ctx)
+    neg_df = neg_df.merge(shapes_df, how="left", left_on="location", right_on="location")
+    neg_df.insert(1, "seq_type", "Not_True")
+    got = pd.concat([pos_df, neg_df], sort=False).dropna(axis=1).reset_index()
     pos = pd.DataFrame(ft["fg_table"]["rows"], columns=ft["fg_table"]["columns"])
     pos.insert(1, "seq_type", "True")
     neg = pd.DataFrame(bg["negative_data_df"]["rows"], columns=bg["negative_data_df"]["columns"])

@@ -144,6 +144,10 @@ def test_primitives_vs_reference_golden(golden):
 
 
 def test_similarity_vs_reference_golden(golden):
+    """The scalar restatement (oracle/similarity_oracle.py) against the reference's own outputs; the
+    GPU kernel is then checked against it (tests/test_gpu_parity.py)."""
+    from oracle import similarity_oracle as similarity
+
     for kmer, h in golden["similarity"]["minhash_kmer"]:
         assert similarity._canonical_hash(kmer) == h
     assert similarity.murmurhash3_32(b"foo", 0) == (-156908512) & 0xFFFFFFFF
@@ -415,3 +419,170 @@ def test_scan_genome_cli_wiring(tmp_path, monkeypatch):
     assert scan_genome.main([str(fa), str(jaspar), out, "--threshold", "7.5", "--gc", "0.4"]) == 0
     assert list(seen["thresholds"]) == [7.5]
     assert np.isclose(seen["matrices"][0][0, 1], np.log2((16.5 / 22) / 0.2))
+
+
+# ---- dense scan: fixed-point arithmetic replayed on the host --------------------------------------
+def adversarial_dense_cases():
+    """Sharp, long motifs: consensus-only columns with large counts and small
+    pseudocounts give entries near -20 .. -25 and window scores down to -800, where summing
+    fp32-rounded group entries in fp32 drifts past 1e-4.  -> list of (name, log-odds [L][4])."""
+    from oracle import pssm_oracle as po
+
+    cases = []
+    for L in (30, 32):
+        for total, pc in ((5e4, 0.01), (1e5, 0.001), (1e5, 0.01), (5e4, 0.001)):
+            rng = np.random.default_rng([L, int(total), int(pc * 1e4)])
+            counts = np.zeros((L, 4))
+            counts[np.arange(L), rng.integers(0, 4, size=L)] = total
+            cases.append((f"L{L}_n{int(total)}_pc{pc}", po.log_odds(po.normalize(counts, pc))))
+    return cases
+
+
+def adversarial_dense_sequence(pssm, n_random=3_000_000, seed=1):
+    """n_random uniform bases followed by the all-worst-base window and the consensus window."""
+    rng = np.random.default_rng(seed)
+    worst = np.argmin(pssm, axis=1)
+    best = np.argmax(pssm, axis=1)
+    codes = np.concatenate([rng.integers(0, 4, size=n_random), worst, best, worst[::-1], 3 - worst[::-1]])
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+
+
+def test_dense_fixed_point_replay_on_adversarial_motifs():
+    """The dense kernel's arithmetic — int32 sums of the per-motif scaled k-mer entries, one
+    int->float conversion, one exact multiply by 2^-e — replayed in NumPy with the kernel's own tables
+    (tfbs_debug_dense_tables) against the double-accumulating oracle: <= 1e-4 on every window."""
+    from discover_tfbs_b200 import _lib
+    from oracle import pssm_oracle as po
+
+    for name, pssm in adversarial_dense_cases():
+        L = pssm.shape[0]
+        K, G, e, neg, ent = _lib.dense_tables(pssm)
+        assert K == 3 and G == (L + 2) // 3 and neg == -2**31
+        # every window sum must fit in int32
+        assert np.abs(ent.astype(np.int64)).max(axis=(1, 2)).sum() < 2**31
+        seq = adversarial_dense_sequence(pssm, 300_000)
+        code = np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), seq)
+        nwin = seq.size - L + 1
+        for strand, mat in ((0, pssm), (1, po.reverse_complement(pssm))):
+            acc = np.zeros(nwin, dtype=np.int64)
+            for g in range(G):
+                x = np.zeros(nwin, dtype=np.int64)
+                for j in range(K):
+                    if K * g + j < L:
+                        x |= code[K * g + j: K * g + j + nwin].astype(np.int64) << (2 * j)
+                acc += ent[g, x, strand]
+            assert np.abs(acc).max() < 2**31
+            got = acc.astype(np.int32).astype(np.float32) * np.float32(2.0 ** -e)
+            ref = po.calculate(seq, mat)
+            err = float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))))
+            assert err <= 1e-4, (name, strand, err)
+            assert float(ref.min()) < -550.0  # the regime the fp32 path failed in
+
+
+def test_dense_fixed_point_minus_inf_sentinel():
+    """A motif with -inf entries: any window with a -inf group sums below neg_thr, every finite window
+    stays at or above it, and no sum leaves int32."""
+    from discover_tfbs_b200 import _lib
+    from oracle import pssm_oracle as po
+
+    rng = np.random.default_rng(8)
+    for L in (5, 12, 24, 25, 32):
+        counts = rng.integers(0, 1000, size=(L, 4)).astype(float)
+        counts[rng.random((L, 4)) < 0.3] = 0.0
+        counts[counts.sum(axis=1) == 0, 1] = 7.0
+        pssm = po.log_odds(po.normalize(counts))
+        assert np.isneginf(pssm).any()
+        K, G, e, neg, ent = _lib.dense_tables(pssm)
+        e64 = ent.astype(np.int64)
+        sentinel = e64.min()
+        finite = e64 != sentinel
+        rq = sum(np.abs(np.where(finite[g], e64[g], 0)).max() for g in range(G))
+        assert neg == -rq and sentinel == -(2 * rq + 1)
+        assert G * (2 * rq + 1) + rq < 2**31
+        assert e >= 16  # still far finer than 1e-4 / G
+
+
+# ---- pentamer tables are never fabricated silently ------------------------------------------------
+def test_shape_entry_points_require_tables(tmp_path, monkeypatch):
+    """VERDICT r01 / ADVICE: GenomeShapeSource, background_shape_table and getDNAShape without tables
+    must raise (before touching the GPU) instead of substituting the synthetic stand-in tables."""
+    monkeypatch.delenv("TFBS_SHAPE_TABLES", raising=False)
+    fa = tmp_path / "g.fasta"
+    fa.write_text(">chr1\nACGTACGTACGTACGT\n")
+    with pytest.raises(ValueError, match="pentamer tables"):
+        U.GenomeShapeSource(str(fa))                      # the exact call of INTEGRATION.md §2 without tables
+    with pytest.raises(ValueError, match="pentamer tables"):
+        U.background_shape_table(str(fa))
+    with pytest.raises(ValueError, match="pentamer tables"):
+        dnashape.getDNAShape(str(fa), "MGW")
+    with pytest.raises(ValueError, match="pentamer tables"):
+        dnashape.resolve_tables()
+    with pytest.warns(UserWarning, match="SYNTHETIC"):
+        t, k = dnashape.resolve_tables(synthetic=True)
+    assert t.shape == (5, 2, 1024) and list(k) == [0, 1, 0, 0, 1]
+
+
+def test_shape_table_file_roundtrip_half_tables_and_env(tmp_path, monkeypatch):
+    tables, kinds = dnashape.synthetic_tables()
+    path = dnashape.save_tables(str(tmp_path / "tables.tsv"), tables, kinds)
+    t2, k2 = dnashape.load_tables(path)
+    assert np.array_equal(t2, tables) and np.array_equal(k2, kinds)
+    # a 512-row file (one pentamer of every reverse-complement pair) is completed by symmetry
+    lines = open(path).read().split("\n")
+    rc = dnashape._revcomp_index(np.arange(1024))
+    half = [lines[0]] + [lines[1 + i] for i in range(1024) if i < rc[i]]
+    assert len(half) == 513
+    (tmp_path / "half.tsv").write_text("\n".join(half) + "\n")
+    t3, _ = dnashape.load_tables(str(tmp_path / "half.tsv"))
+    assert np.array_equal(t3, tables)
+    # a subset of shapes, and the environment variable route
+    t4, k4 = dnashape.load_tables(path, ("MGW", "Roll"))
+    assert np.array_equal(t4[0], tables[2]) and np.array_equal(t4[1], tables[4]) and list(k4) == [0, 1]
+    monkeypatch.setenv("TFBS_SHAPE_TABLES", path)
+    t5, _ = dnashape.resolve_tables()
+    assert np.array_equal(t5, tables)
+    # a file that lacks a pentamer pair raises
+    (tmp_path / "bad.tsv").write_text("\n".join(half[:-1]) + "\n")
+    with pytest.raises(ValueError, match="missing pentamers"):
+        dnashape.load_tables(str(tmp_path / "bad.tsv"))
+
+
+def test_tables_from_dnashaper_output_of_the_pentamer_fasta(tmp_path):
+    """The documented export route: DNAshapeR run on the 1024 five-base records gives back the tables.
+    DNAshapeR is played by the oracle (SURVEY.md A.2 semantics, text format of create_bkg_seqs.py:365)."""
+    from oracle import shape_oracle as so
+
+    tables, kinds = dnashape.synthetic_tables()
+    fa = dnashape.write_pentamer_fasta(str(tmp_path / "pentamers.fa"))
+    recs = list(U.parse_fasta(fa))
+    assert len(recs) == 1024 and recs[27] == ("AACGT", "AACGT")
+    for t, shape in enumerate(dnashape.SHAPES):
+        with open(f"{fa}.{shape}", "w") as fh:
+            for name, seq in recs:
+                tr = so.tracks(seq, tables[t: t + 1], kinds[t: t + 1])[0]
+                fh.write(f">{name}\n" + ",".join(so.tokens(tr, int(kinds[t]), 5)) + "\n")
+    got, k = dnashape.tables_from_shape_files(fa)
+    assert np.array_equal(k, kinds)
+    for t in range(5):
+        assert np.array_equal(got[t, 0], tables[t, 0])
+        if kinds[t]:
+            assert np.array_equal(got[t, 1], tables[t, 1])
+
+
+def test_shim_runs_a_reference_driver_with_the_hot_path_swapped(tmp_path, capsys):
+    """discover_tfbs_b200.shim executes the reference's own driver unchanged: `from utils import ...`
+    resolves to the reference's utils.py with only the hot-path names replaced."""
+    from discover_tfbs_b200 import shim
+
+    (tmp_path / "utils.py").write_text(
+        "def build_feature_table(*a, **k):\n    return 'reference'\n"
+        "def parse_fasta(f):\n    return 'reference'\n"
+        "def random_dna(n):\n    return 'N' * n\n")
+    (tmp_path / "driver.py").write_text(
+        "import sys\nfrom utils import build_feature_table, parse_fasta, random_dna\n"
+        "print(build_feature_table.__module__, parse_fasta.__module__, random_dna(3), sys.argv[1:])\n")
+    shim.main([str(tmp_path / "driver.py"), "tec1", "fg.fasta"])
+    out = capsys.readouterr().out.strip()
+    assert out == "discover_tfbs_b200.utils discover_tfbs_b200.utils NNN ['tec1', 'fg.fasta']"
+    import sys
+    sys.modules.pop("utils", None)

@@ -115,3 +115,21 @@ def test_shape_edge_rules():
     tr2 = so.tracks("ACGTANGTACGT", tables, kinds)
     assert np.isnan(tr2[2, 3:8]).all() and not np.isnan(tr2[2, 8:10]).any()
     assert np.isnan(tr2[1, 2:8]).all() and not np.isnan(tr2[1, 8])
+
+
+def test_openmp_forms_equal_the_plain_loops():
+    """oracle_pwm_search_mt / oracle_pwm_calculate_mt (used by the config-size GPU tests) give exactly
+    the output of the single-threaded loops, in the same order, with more hits than fit one pass."""
+    from discover_tfbs_b200 import synth
+
+    seq = synth.genome(7, 0, 150_000)
+    lo, lens = synth.pwm_library(7, 12, 6, 30)
+    thr = synth.thresholds_for_rate(lo, lens, rate=2e-3, sample=20_000)
+    a = po.search_library(seq, lo, lens, thr)
+    b = po.search_library(seq, lo, lens, thr, threads=3)
+    assert a[4] == b[4] > 1000
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    for m in (0, 5):
+        mat = lo[m, : lens[m]]
+        assert np.array_equal(po.calculate(seq, mat), po.calculate(seq, mat, threads=0), equal_nan=True)
