@@ -113,6 +113,7 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     free_scratch(ctx->dense_rev);
     free_scratch(ctx->hits);
     free_scratch(ctx->hit_count);
+    free_scratch(ctx->cand);
     free_scratch(ctx->tracks);
     free_scratch(ctx->sites);
     free_scratch(ctx->misc);

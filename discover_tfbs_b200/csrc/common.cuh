@@ -53,6 +53,7 @@ struct tfbs_ctx {
     tfbs_scratch dense_fwd, dense_rev;  // dense scan outputs [M][pitch]
     tfbs_scratch hits;                  // tfbs_hit[cap]
     tfbs_scratch hit_count;             // unsigned long long + work counters
+    tfbs_scratch cand;                  // candidate list of the hits scan (8 B records)
     tfbs_scratch tracks;                // shape tracks [T][pitch]
     tfbs_scratch sites;                 // shape sites out / args
     tfbs_scratch misc;                  // small argument staging

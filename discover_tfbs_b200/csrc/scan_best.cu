@@ -8,8 +8,9 @@
 // reduces on the device and writes float[S][M][2] (+ the offset of the best window) only.
 //
 // Arithmetic: every window is scored exactly as the oracle does — left-to-right double sum of the
-// exact log-odds entries — and the maximum double is cast to float once.  The cast is monotonic, so
-// (float)max_i s_i == max_i (float)s_i: results are BIT-EXACT with max over the oracle's calculate().
+// exact log-odds entries, cast to float — and the maximum is taken over the FLOAT scores (two windows
+// whose double sums differ may be equal as floats; numpy.nanargmax then reports the first), so values
+// and offsets are BIT-EXACT with max / first argmax over the oracle's calculate().
 // One warp per (record, motif); lanes stride over the window starts; windows touching an invalid
 // byte are skipped (np.nanmax semantics); a record without a valid window yields NaN / -1.
 #include <cmath>
@@ -33,7 +34,7 @@ struct BestParams {
     int32_t *pos;            // [S][M][2] or nullptr
 };
 
-__device__ __forceinline__ void take_better(double &v, int32_t &p, double ov, int32_t op)
+__device__ __forceinline__ void take_better(float &v, int32_t &p, float ov, int32_t op)
 {
     // larger score wins; equal scores keep the smaller offset (np.nanargmax: first maximum); p < 0 = none yet
     if (op >= 0 && (p < 0 || ov > v || (ov == v && op < p))) { v = ov; p = op; }
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kBestThreads) scan_best_kernel(const BestParam
         const double *F = P.exact + (size_t)m * 2 * TFBS_MAX_MOTIF_LEN * 4;
         const double *R = F + TFBS_MAX_MOTIF_LEN * 4;
         const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-        double bf = 0.0, br = 0.0;
+        float bf = 0.f, br = 0.f;
         int32_t pf = -1, pr = -1;
         for (int64_t i = lane; i < nwin; i += 32) {
             const int64_t p = r0 + i;
@@ -72,20 +73,20 @@ __global__ void __launch_bounds__(kBestThreads) scan_best_kernel(const BestParam
                 sf += __ldg(F + j * 4 + c);
                 sr += __ldg(R + j * 4 + c);
             }
-            take_better(bf, pf, sf, (int32_t)i);
-            take_better(br, pr, sr, (int32_t)i);
+            take_better(bf, pf, (float)sf, (int32_t)i);
+            take_better(br, pr, (float)sr, (int32_t)i);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-            const double of = __shfl_xor_sync(0xFFFFFFFFu, bf, d), orv = __shfl_xor_sync(0xFFFFFFFFu, br, d);
+            const float of = __shfl_xor_sync(0xFFFFFFFFu, bf, d), orv = __shfl_xor_sync(0xFFFFFFFFu, br, d);
             const int32_t opf = __shfl_xor_sync(0xFFFFFFFFu, pf, d), opr = __shfl_xor_sync(0xFFFFFFFFu, pr, d);
             take_better(bf, pf, of, opf);
             take_better(br, pr, orv, opr);
         }
         if (lane == 0) {
             const float qnan = __uint_as_float(0x7FC00000u);
-            P.best[w * 2 + 0] = pf >= 0 ? (float)bf : qnan;
-            P.best[w * 2 + 1] = pr >= 0 ? (float)br : qnan;
+            P.best[w * 2 + 0] = pf >= 0 ? bf : qnan;
+            P.best[w * 2 + 1] = pr >= 0 ? br : qnan;
             if (P.pos) {
                 P.pos[w * 2 + 0] = pf;
                 P.pos[w * 2 + 1] = pr;

@@ -21,10 +21,15 @@
 //     2-bit packed words staged in shared memory by TMA); A + B loads feed A + B of the 32 ring
 //     accumulators held in registers; finalised accumulators are tested up to 8 at a time (their AND
 //     keeps a flag bit set unless one of them cleared it), with a warp vote.
-//   * candidates (rare) go to a per-warp shared-memory queue and are verified 32 at a time:
-//     invalid-base mask check, then the oracle's arithmetic — left-to-right double sum cast to
-//     float, compared with >= — so hit sets and scores are bit-exact.  Hits are compacted with
-//     ballot/popc and one global atomic per warp batch.
+//   * candidates (rare) go to a per-warp shared-memory queue; a full queue is appended to a global
+//     candidate list (one atomic per batch, coalesced 8-byte records).  A second kernel
+//     (verify_candidates_kernel, full occupancy, exact matrices served by L1/L2) re-scores every
+//     candidate with the oracle's arithmetic — invalid-base mask check, left-to-right double sum cast
+//     to float, compared with >= — so hit sets and scores are bit-exact; hits are compacted with
+//     ballot/popc and one global atomic per CTA batch.  Verifying inside the scan kernel (round 1)
+//     stalled its 16 warps per SM on L2 latency: ~0.2 ns per candidate, 13 % of the scan at a 1e-4 hit
+//     rate and most of it at 1e-3.  The in-kernel verifier is kept as the overflow path (candidate
+//     list or queue full: flood thresholds), so no threshold vector can lose a hit.
 //   * NARROW blocks: 64 motifs per block, two per lane, four 8-bit fields per entry (motif lane: fwd,
 //     rev; motif lane + 32: fwd, rev).  The same LDS.32 + IADD now scores two motifs, halving
 //     shared-memory traffic per motif — the resource this kernel is bound by.  Only
@@ -33,10 +38,11 @@
 //     verifier, which keeps the hit set bit-exact, has more to do.
 //   * STICKY narrow blocks (5 or more groups): flag bits, once set, are OR-ed back after every add
 //     (acc = (acc + v) | (acc & 0x80808080), one more ALU op per load), so a dead field may wrap
-//     without looking alive again.  A wrapping field carries +1 into the field above it, at most
-//     (2 + 127 G + 4) / 256 <= 4 times per window; a field with a neighbour below therefore starts
-//     that many steps lower, which keeps {candidates} a superset of {hits}, and >= 121 quantisation
-//     steps are usable whatever G is: the 8-bit filter is then almost as sharp as the 16-bit one.
+//     without looking alive again.  A dead field counts modulo 128 below its restored flag and sends
+//     +1 into the field above it on every wrap, at most (2 + 127 G + c_in) / 128 - 1 <= 8 times per
+//     window; a field with a neighbour below therefore starts that many steps lower, which keeps
+//     {candidates} a superset of {hits}, and >= 117 quantisation steps are usable whatever G is: the
+//     8-bit filter is then almost as sharp as the 16-bit one.
 //     Wide, narrow or sticky is chosen per block and per threshold vector by a cost model
 //     (tfbs_build_hits_tables).
 //   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
@@ -84,10 +90,17 @@ struct HitsParams {
     const float *thr;            // [M]
     const double *exact;         // [M][2][32][4]
     tfbs_hit *hits;
-    unsigned long long *hit_count;
+    unsigned long long *hit_count;   // [0] hits, [1] candidates handed to a verifier, [2] error flag, [4] list length
     unsigned long long cap;
     unsigned int *work_counter;
+    unsigned long long *cand;        // global candidate list: (pos << 24) | (motif << 1) | strand
+    unsigned long long cand_cap;
+    int64_t owned_end;               // window starts >= owned_end belong to the next shard (halo): not reported
+    int64_t pos_offset;              // added to every reported position (shard start in genome coordinates)
 };
+constexpr int kCandCountSlot = 4;                      // index into hit_count of the candidate-list length
+constexpr unsigned long long kCandEmpty = ~0ull;       // list entry to skip
+constexpr int kCandMotifBits = 23;
 
 struct Smem {
     // small buffers first, then the block table on the next 32 KB boundary of the shared window
@@ -152,13 +165,14 @@ struct VerifyCtx {
     const float *thr;
     const double *exact;
     int64_t tile_start;
+    int64_t owned_end, pos_offset;
 };
 
 // Oracle arithmetic for one candidate (tile-local start p, motif slot ml, strand).
 __device__ __forceinline__ bool verify(const VerifyCtx &V, int p, int ml, int strand, int *motif_out, float *score_out)
 {
     const int m = V.s_motif[ml];
-    if (m < 0) return false;
+    if (m < 0 || V.tile_start + p >= V.owned_end) return false;
     const int L = V.s_len[ml];
     const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
     const uint32_t inv = __funnelshift_r(V.s_mask[p >> 5], V.s_mask[(p >> 5) + 1], p & 31) & lmask;
@@ -205,16 +219,27 @@ struct PushCtx {
     tfbs_hit *hits;
     unsigned long long *hit_count;
     unsigned long long cap;
+    unsigned long long *cand;
+    unsigned long long cand_cap;
 };
 
-// Warp-synchronous verification of the queued candidates, 32 at a time; hits are compacted with
-// ballot/popc and one atomic per batch.
+// Warp-synchronous hand-over of the queued candidates to the global candidate list (one atomic per
+// call, coalesced 8-byte stores).  Entries that do not fit the list are verified here, 32 at a time
+// (hits compacted with ballot/popc and one atomic per batch): the overflow path of flood thresholds.
 // `qn` = entries pushed since the last drain (warp-uniform register; entries beyond kQueueCap were
 // verified inline by push_group).
 __device__ __noinline__ void drain_queue(const PushCtx &C, uint32_t qn)
 {
     __syncwarp();
     const uint32_t cnt = min(qn, (uint32_t)kQueueCap);
+    if (cnt == 0) return;
+    unsigned long long list0 = 0;
+    if (C.lane == 0) {
+        list0 = atomicAdd(C.hit_count + kCandCountSlot, (unsigned long long)cnt);
+        atomicAdd(C.hit_count + 1, (unsigned long long)cnt);  // statistics: candidates handed to a verifier
+    }
+    list0 = __shfl_sync(0xFFFFFFFFu, list0, 0);
+    const bool overflow = list0 + cnt > C.cand_cap;  // warp-uniform
     for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t i = base + C.lane;
         bool hit = false;
@@ -224,19 +249,28 @@ __device__ __noinline__ void drain_queue(const PushCtx &C, uint32_t qn)
             const uint32_t e = C.queue[i];
             p = (int)(e & 0xFFFFu);
             strand = (int)(e >> 31);
-            hit = verify(*C.V, p, (int)((e >> 16) & 63u), strand, &m, &f);
+            const int ml = (int)((e >> 16) & 63u);
+            const unsigned long long slot = list0 + i;
+            if (slot < C.cand_cap) {
+                const int mo = C.V->s_motif[ml];
+                C.cand[slot] = mo < 0 ? kCandEmpty
+                                      : (((unsigned long long)(C.V->tile_start + p) << (kCandMotifBits + 1)) |
+                                         ((unsigned long long)mo << 1) | (unsigned long long)strand);
+            } else {
+                hit = verify(*C.V, p, ml, strand, &m, &f);
+            }
         }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-        if (ballot) {
-            unsigned long long slot0 = 0;
-            if (C.lane == 0) slot0 = atomicAdd(C.hit_count, (unsigned long long)__popc(ballot));
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            if (hit)
-                store_hit(C.hits, slot0 + __popc(ballot & ((1u << C.lane) - 1u)), C.cap, C.V->tile_start + p, strand, m, f);
+        if (overflow) {
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+            if (ballot) {
+                unsigned long long slot0 = 0;
+                if (C.lane == 0) slot0 = atomicAdd(C.hit_count, (unsigned long long)__popc(ballot));
+                slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+                if (hit)
+                    store_hit(C.hits, slot0 + __popc(ballot & ((1u << C.lane) - 1u)), C.cap, C.V->tile_start + p + C.V->pos_offset, strand, m, f);
+            }
         }
     }
-    __syncwarp();
-    if (C.lane == 0 && cnt) atomicAdd(C.hit_count + 1, (unsigned long long)cnt);  // statistics: candidates verified
     __syncwarp();
 }
 
@@ -252,7 +286,7 @@ __device__ __noinline__ void verify_now(const PushCtx &C, int p, int ml, int str
         unsigned long long hb = 0;
         if (g.thread_rank() == 0) hb = atomicAdd(C.hit_count, (unsigned long long)g.size());
         hb = g.shfl(hb, 0);
-        store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p, strand, m, sc);
+        store_hit(C.hits, hb + g.thread_rank(), C.cap, C.V->tile_start + p + C.V->pos_offset, strand, m, sc);
     }
 }
 
@@ -467,6 +501,8 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         V.thr = P.thr;
         V.exact = P.exact;
         V.tile_start = tile_start;
+        V.owned_end = P.owned_end;
+        V.pos_offset = P.pos_offset;
         PushCtx C;
         C.queue = S.queue + warp * kQueueCap;
         C.seg_begin = warp * kSeg;
@@ -476,6 +512,8 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         C.hits = P.hits;
         C.hit_count = P.hit_count;
         C.cap = P.cap;
+        C.cand = P.cand;
+        C.cand_cap = P.cand_cap;
         const uint32_t lut_lane_addr = lut_addr + (uint32_t)lane * 4u;
         switch (AB) {
 #define TFBS_CASE(a, b, n) \
@@ -496,6 +534,91 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         }
         if (tid == 0) *S.item = next_item;
         __syncthreads();  // tile buffers are reused by the next item; S.item holds it
+    }
+}
+
+// Second pass: exact re-scoring of the candidate list with the oracle's arithmetic.  One thread per
+// candidate, plain grid-stride kernel at full occupancy: the list is ordered by (motif block, tile), so
+// the exact matrices of 64 motifs and the bases of one tile stay L1-resident.  Hits of a CTA batch are
+// compacted with ballot/popc and ONE global atomic.
+constexpr int kVerifyThreads = 256;
+struct VerifyParams {
+    const uint32_t *packed;
+    const uint32_t *mask;
+    const int32_t *lens;
+    const float *thr;
+    const double *exact;
+    const unsigned long long *cand;
+    unsigned long long cand_cap;
+    tfbs_hit *hits;
+    unsigned long long *hit_count;
+    unsigned long long cap;
+    int64_t owned_end, pos_offset;
+};
+
+__global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const VerifyParams P)
+{
+    __shared__ uint32_t s_warp_hits[kVerifyThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned long long n = min(P.hit_count[kCandCountSlot], P.cand_cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * kVerifyThreads; base < n;
+         base += (unsigned long long)gridDim.x * kVerifyThreads) {
+        const unsigned long long i = base + threadIdx.x;
+        bool hit = false;
+        int m = 0, strand = 0;
+        int64_t gpos = 0;
+        float f = 0.f;
+        const unsigned long long rec = i < n ? P.cand[i] : kCandEmpty;
+        if (rec != kCandEmpty && (int64_t)(rec >> (kCandMotifBits + 1)) < P.owned_end) {
+            strand = (int)(rec & 1u);
+            m = (int)((rec >> 1) & ((1u << kCandMotifBits) - 1u));
+            gpos = (int64_t)(rec >> (kCandMotifBits + 1));
+            const int L = __ldg(P.lens + m);
+            const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+            const uint32_t *mp = P.mask + (gpos >> 5);
+            const uint32_t inv = __funnelshift_r(__ldg(mp), __ldg(mp + 1), (int)(gpos & 31)) & lmask;
+            if (!inv) {  // a window touching an invalid base is NaN in the oracle, never a hit
+                const uint32_t *wp = P.packed + (gpos >> 4);
+                const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
+                const int sh = (int)(gpos & 15) * 2;
+                uint64_t bases = (uint64_t)__funnelshift_r(a0, a1, sh) | ((uint64_t)__funnelshift_r(a1, a2, sh) << 32);
+                const double *mat = P.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+                // left-to-right double sum (the oracle's order); the loads of 8 columns are issued together
+                double s = 0.0;
+                for (int j0 = 0; j0 < L; j0 += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int j = j0 + k;
+                        v[k] = j < L ? __ldg(mat + j * 4 + (int)((bases >> (2 * k)) & 3u)) : 0.0;
+                    }
+                    bases >>= 16;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (j0 + k < L) s += v[k];
+                }
+                f = (float)s;
+                hit = f >= __ldg(P.thr + m);
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+        if (lane == 0) s_warp_hits[warp] = (uint32_t)__popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kVerifyThreads / 32; w++) {
+                const uint32_t c = s_warp_hits[w];
+                s_warp_hits[w] = total;
+                total += c;
+            }
+            s_base = total ? atomicAdd(P.hit_count, (unsigned long long)total) : 0ull;
+        }
+        __syncthreads();
+        if (hit)
+            store_hit(P.hits, s_base + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u)), P.cap, gpos + P.pos_offset, strand, m, f);
+        __syncthreads();  // s_warp_hits / s_base are rewritten by the next batch
     }
 }
 
@@ -557,6 +680,37 @@ int sort_hits_device(tfbs_ctx *ctx, int64_t n, int M)
         return TFBS_ERR_CUDA;
     }
     return TFBS_OK;
+}
+
+// Capacity of the candidate list for a call that may return `cap` hits: twice as many entries (the
+// filters pass 1.1 - 2x the hits at the rates they are chosen for), at least 1 Mi, at most 2 GiB of
+// records.  What does not fit is verified inside the scan kernel, so this only tunes speed.
+int reserve_candidates(tfbs_ctx *ctx, int64_t cap, unsigned long long *cand_cap)
+{
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(2 * cap, (int64_t)1 << 20), (int64_t)1 << 28);
+    int rc = tfbs_scratch_reserve(ctx->cand, (size_t)want * 8);
+    if (rc) return rc;
+    *cand_cap = ctx->cand.bytes / 8;
+    return TFBS_OK;
+}
+
+void launch_verify(tfbs_ctx *ctx, const HitsParams &P)
+{
+    VerifyParams V;
+    V.packed = P.packed;
+    V.mask = P.mask;
+    V.lens = P.lens;
+    V.thr = P.thr;
+    V.exact = P.exact;
+    V.cand = P.cand;
+    V.cand_cap = P.cand_cap;
+    V.hits = P.hits;
+    V.hit_count = P.hit_count;
+    V.cap = P.cap;
+    V.owned_end = P.owned_end;
+    V.pos_offset = P.pos_offset;
+    verify_candidates_kernel<<<(unsigned)(ctx->sm_count * 8), kVerifyThreads, 0, ctx->stream>>>(V);
+    tfbs_launched(ctx);
 }
 
 // Dynamic shared memory to request: small buffers + padding up to the next 32 KB boundary of the
@@ -704,15 +858,27 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
             }
             int slack = 0;
             if (mode == kSticky) {
-                // the field one byte below: the reverse strand of the same motif, or (below the reverse
-                // field of slot l < 32) the forward strand of slot l + 32; the lowest field has none.
-                // It starts at most at 2 (127 - Dq - slack with Dq >= 125 - slack; a threshold of -inf
-                // starts higher but adds zeros), adds Gl entries <= 127 and receives <= 4 carries itself.
-                int Gl = 0;
-                if (s == 0) Gl = Gm;
-                else if (half == 0 && l + 32 < count)
-                    for (int g = 0; g < G && gcol[g] < pw->lens[motifs[l + 32]]; g++) Gl++;
-                slack = Gl ? (2 + Gl * 127 + 4) / 256 : 0;
+                // Carries the field receives from the byte below it.  Bytes from the top: slot l forward,
+                // slot l reverse, slot l + 32 forward, slot l + 32 reverse.  A field starts at most at 2
+                // (127 - Dq - slack with Dq >= 125 - slack), adds one entry <= 127 per group of its motif
+                // and the carries it receives itself.  Its first crossing of 128 only sets the flag; from
+                // then on the OR puts the flag back after every wrap, so the low 7 bits count modulo 128
+                // and every further 128 sends one carry up: at most (2 + 127 Gl + c_in) / 128 - 1 carries.
+                // (Round 1 divided by 256 — the flag-restoring OR was forgotten — and lost hits of sharp
+                // motifs at tight thresholds: tests/test_host.py::test_sticky_carry_slack_adversarial.)
+                // An unused or unreachable field keeps zero entries and never carries.
+                auto groups_of = [&](int slot) {
+                    int n = 0;
+                    if (slot < count)
+                        for (int g = 0; g < G && gcol[g] < pw->lens[motifs[slot]]; g++) n++;
+                    return n;
+                };
+                auto carries_out = [](int groups, int c_in) { return groups ? std::max(0, (2 + 127 * groups + c_in) / 128 - 1) : 0; };
+                const int lo = l & 31, hi = lo + 32;
+                const int c0 = carries_out(groups_of(hi), 0);   // out of slot hi reverse  -> into slot hi forward
+                const int c1 = carries_out(groups_of(hi), c0);  // out of slot hi forward  -> into slot lo reverse
+                const int c2 = carries_out(groups_of(lo), c1);  // out of slot lo reverse  -> into slot lo forward
+                slack = half == 0 ? (s == 0 ? c2 : c1) : (s == 0 ? c0 : 0);
             }
             if (std::isnan(t)) reachable = false;
             // D: how much a hit may lose against the best possible score (plus slack for the
@@ -787,7 +953,7 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
             } else if (mode == kSticky) {
                 // sticky fields may wrap (their flag is kept by the OR): entries <= 127, and `slack` steps
                 // of the field absorb the carries a wrapping neighbour sends in
-                expected += quantise(125 - slack, 127, true);
+                expected += quantise(125 - slack, 127, true);  // slack <= 8: >= 117 steps at any G
             } else {
                 // Plain 8-bit fields must not wrap.  Either every entry above the budget kills alone
                 // (capq = dq_max + 2, which leaves only (128 - 2 Gm) / (Gm - 1) steps), or the steps are
@@ -839,7 +1005,7 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int cou
     int A2 = 0, B2 = 1;
     tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
     const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
-    // the sticky filter (>= 121 steps) also estimates the candidates of the wide form: measured,
+    // the sticky filter (>= 117 steps) also estimates the candidates of the wide form: measured,
     // it passes about 1.5x as many
     const double c_sticky = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
     const double c_narrow = fill_block(pw, thr, motifs, count, A, B, kNarrow, lut, kinit);
@@ -927,10 +1093,14 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     if (rc) return rc;
     rc = tfbs_build_hits_tables(pwms, thr);
     if (rc) return rc;
+    TFBS_REQUIRE(M < (1 << kCandMotifBits) && n < ((int64_t)1 << (63 - kCandMotifBits)), "tfbs_scan_hits: library or sequence too large");
     TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->thr.ptr, thr, (size_t)M * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     TFBS_CHECK_CUDA(cudaMemsetAsync(ctx->hit_count.ptr, 0, 64, ctx->stream));
 
     HitsParams P;
+    rc = reserve_candidates(ctx, cap, &P.cand_cap);
+    if (rc) return rc;
+    P.cand = (unsigned long long *)ctx->cand.ptr;
     P.packed = seq->packed;
     P.mask = seq->mask;
     P.n_tiles = (n + kTilePos - 1) / kTilePos;
@@ -948,6 +1118,8 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
     P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 24);
+    P.owned_end = n;
+    P.pos_offset = 0;
     TFBS_REQUIRE(P.n_tiles * P.n_blocks < (int64_t)0xFFFF0000ll, "tfbs_scan_hits: too many work items");  // + one prefetch per CTA
     TFBS_REQUIRE((P.n_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits: sequence padding too small");
 
@@ -959,6 +1131,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     tfbs_begin(ctx);
     scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
     tfbs_launched(ctx);
+    launch_verify(ctx, P);
     rc = tfbs_end(ctx);
     if (rc) return rc;
     unsigned long long cnt2[3] = {0, 0, 0};
@@ -991,12 +1164,20 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
 // tile boundaries; H2D copies (stream_in), encode + scan (compute stream) and the D2H copies of
 // every chunk's hits (stream_out) overlap, so the PCIe time hides behind the scan.  Results are the
 // same as tfbs_encode + tfbs_scan_hits (hit order is unspecified unless `sorted`).
-extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
-                                   const tfbs_pwms *pwms_c, const float *thr, tfbs_hit *out_host, int64_t cap,
-                                   int32_t chunks, int32_t sorted, int64_t *n_hits)
+//
+// Shard form (tfbs_scan_hits_host_shard): the buffer is one shard [shard_start, shard_start + n) of a
+// longer sequence, scanned with its right halo; only windows starting in its first `owned` bases are
+// reported (the halo's windows belong to the next shard) and `shard_start` is added to every position,
+// both on the device, so per-shard results concatenate without a host-side filter.
+// With `sorted` the hits are ordered on the device (radix sort) after the last chunk and copied back in
+// one piece; without it every chunk's hits are copied while the next chunk is scanned.
+static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                               const tfbs_pwms *pwms_c, const float *thr, tfbs_hit *out_host, int64_t cap,
+                               int32_t chunks, int32_t sorted, int64_t owned, int64_t shard_start, int64_t *n_hits)
 {
     TFBS_REQUIRE(ctx && ascii_host && seq && pwms_c && thr && out_host && n_hits && cap >= 0 && n > 0,
                  "tfbs_scan_hits_host: bad argument");
+    TFBS_REQUIRE(owned >= 0 && owned <= n && shard_start >= 0, "tfbs_scan_hits_host: bad shard bounds");
     TFBS_REQUIRE(seq->ctx == ctx && pwms_c->ctx == ctx && seq->n == n, "tfbs_scan_hits_host: handle mismatch");
     tfbs_pwms *pwms = const_cast<tfbs_pwms *>(pwms_c);
     TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
@@ -1010,6 +1191,7 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     if (rc) return rc;
     rc = tfbs_build_hits_tables(pwms, thr);
     if (rc) return rc;
+    TFBS_REQUIRE(M < (1 << kCandMotifBits) && n < ((int64_t)1 << (63 - kCandMotifBits)), "tfbs_scan_hits_host: library or sequence too large");
     if (seq->staging_bytes < (size_t)n) {
         if (seq->staging) cudaFree(seq->staging);
         seq->staging = nullptr;
@@ -1038,6 +1220,9 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream_out, ev_start, 0));
 
     HitsParams P;
+    rc = reserve_candidates(ctx, cap, &P.cand_cap);
+    if (rc) return rc;
+    P.cand = (unsigned long long *)ctx->cand.ptr;
     P.packed = seq->packed;
     P.mask = seq->mask;
     P.n_blocks = pwms->n_blocks;
@@ -1052,6 +1237,8 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     P.hits = (tfbs_hit *)ctx->hits.ptr;
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
+    P.owned_end = owned;
+    P.pos_offset = shard_start;
     size_t smem = 0;
     rc = hits_smem_plan(ctx, pwms->hits_lut_bytes, &smem);
     if (rc) return rc;
@@ -1072,28 +1259,43 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
         P.tile0 = t0;
         P.n_tiles = t1 - t0;
         P.work_counter = (unsigned int *)((char *)ctx->hit_count.ptr + 24);
-        TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 4, ctx->stream));
+        // work counter (offset 24) and candidate-list length (offset 32) restart for every chunk
+        TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 16, ctx->stream));
         const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
         scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
         tfbs_launched(ctx);
+        launch_verify(ctx, P);
         TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned_counts + c, ctx->hit_count.ptr, sizeof(unsigned long long),
                                         cudaMemcpyDeviceToHost, ctx->stream));
         TFBS_CHECK_CUDA(cudaEventRecord(ctx->pipe_events[2 * c + 1], ctx->stream));
     }
-    // drain: as soon as a chunk's scan is done its hits go home while the next chunk is scanned
     unsigned long long done = 0;
-    for (int64_t c = 0; c < C; c++) {
-        TFBS_CHECK_CUDA(cudaEventSynchronize(ctx->pipe_events[2 * c + 1]));
-        const unsigned long long upto = std::min<unsigned long long>(ctx->pinned_counts[c], (unsigned long long)cap);
-        if (upto > done) {
-            TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host + done, (tfbs_hit *)ctx->hits.ptr + done,
-                                            (size_t)(upto - done) * sizeof(tfbs_hit), cudaMemcpyDeviceToHost,
-                                            ctx->stream_out));
-            done = upto;
+    if (sorted) {
+        // ordered output: radix sort on the device once every chunk is scanned, then one copy
+        TFBS_CHECK_CUDA(cudaEventSynchronize(ctx->pipe_events[2 * (C - 1) + 1]));
+        done = std::min<unsigned long long>(ctx->pinned_counts[C - 1], (unsigned long long)cap);
+        if (done > 1) {
+            rc = sort_hits_device(ctx, (int64_t)done, M);
+            if (rc) return rc;
         }
+        if (done > 0)
+            TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host, ctx->hits.ptr, (size_t)done * sizeof(tfbs_hit), cudaMemcpyDeviceToHost,
+                                            ctx->stream));
+    } else {
+        // drain: as soon as a chunk's scan is done its hits go home while the next chunk is scanned
+        for (int64_t c = 0; c < C; c++) {
+            TFBS_CHECK_CUDA(cudaEventSynchronize(ctx->pipe_events[2 * c + 1]));
+            const unsigned long long upto = std::min<unsigned long long>(ctx->pinned_counts[c], (unsigned long long)cap);
+            if (upto > done) {
+                TFBS_CHECK_CUDA(cudaMemcpyAsync(out_host + done, (tfbs_hit *)ctx->hits.ptr + done,
+                                                (size_t)(upto - done) * sizeof(tfbs_hit), cudaMemcpyDeviceToHost,
+                                                ctx->stream_out));
+                done = upto;
+            }
+        }
+        TFBS_CHECK_CUDA(cudaEventRecord(ev_out, ctx->stream_out));
+        TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out, 0));  // a region timer on the compute stream sees the copies
     }
-    TFBS_CHECK_CUDA(cudaEventRecord(ev_out, ctx->stream_out));
-    TFBS_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ev_out, 0));  // a region timer on the compute stream sees the copies
     rc = tfbs_end(ctx);
     if (rc) return rc;
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream_out));
@@ -1102,10 +1304,12 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
         TFBS_CHECK_CUDA(cudaMemcpy(&flag, (char *)ctx->hit_count.ptr + 16, sizeof(flag), cudaMemcpyDeviceToHost));
         TFBS_REQUIRE(flag == 0, "tfbs_scan_hits_host: no kernel instantiation for column grouping A=%u B=%u",
                      (unsigned)((flag >> 8) & 255), (unsigned)(flag & 255));
+        unsigned long long cand = 0;
+        TFBS_CHECK_CUDA(cudaMemcpy(&cand, (char *)ctx->hit_count.ptr + 8, sizeof(cand), cudaMemcpyDeviceToHost));
+        ctx->last_candidates = (int64_t)cand;
     }
     const unsigned long long cnt = ctx->pinned_counts[C - 1];
     *n_hits = (int64_t)cnt;
-    if (sorted && done > 0) std::sort(out_host, out_host + done, HitLess());
     if ((int64_t)cnt > cap) {
         tfbs_set_error("tfbs_scan_hits_host: %llu hits exceed capacity %lld", cnt, (long long)cap);
         return TFBS_ERR_OVERFLOW;
@@ -1113,6 +1317,21 @@ extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int
     return TFBS_OK;
 }
 
+
+extern "C" int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                                   const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
+                                   int32_t chunks, int32_t sorted, int64_t *n_hits)
+{
+    return scan_hits_host_impl(ctx, ascii_host, n, seq, pwms, thr, out_host, cap, chunks, sorted, n, 0, n_hits);
+}
+
+extern "C" int tfbs_scan_hits_host_shard(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                                         const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
+                                         int32_t chunks, int32_t sorted, int64_t owned, int64_t shard_start,
+                                         int64_t *n_hits)
+{
+    return scan_hits_host_impl(ctx, ascii_host, n, seq, pwms, thr, out_host, cap, chunks, sorted, owned, shard_start, n_hits);
+}
 
 // Test hook (host only, no CUDA): run the candidate FILTER of the hits kernel on the host, with the
 // kernel's own tables (fill_block) and its 32-bit field arithmetic, so the CPU test-suite can check

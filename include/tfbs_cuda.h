@@ -138,8 +138,8 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
  * calculate() gives (windows touching an invalid byte are skipped, numpy.nanmax semantics; NaN when
  * the record has no valid window or is shorter than the motif).  pos[s][m][strand] (may be NULL) =
  * offset of the first best window inside the record, -1 when none.  Every window is summed left to
- * right in double and the maximum is cast to float once, so values are bit-exact with
- * max(oracle calculate()).  Only S*M*2 floats cross PCIe instead of the [M][n] dense arrays. */
+ * right in double and cast to float, the maximum is taken over the floats: values and offsets are
+ * bit-exact with max / first argmax of the oracle's calculate().  Only S*M*2 floats cross PCIe instead of the [M][n] dense arrays. */
 int tfbs_scan_best(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const int64_t *rec_start,
                    const int64_t *rec_len, int64_t S, float *best_host, int32_t *pos_host);
 /* Hits mode: every (motif, start, strand) with (float)score >= thr[motif].  A packed

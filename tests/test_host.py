@@ -586,3 +586,43 @@ def test_shim_runs_a_reference_driver_with_the_hot_path_swapped(tmp_path, capsys
     assert out == "discover_tfbs_b200.utils discover_tfbs_b200.utils NNN ['tec1', 'fg.fasta']"
     import sys
     sys.modules.pop("utils", None)
+
+
+@pytest.mark.parametrize("form", [0, 1, 2, 3])
+def test_sticky_carry_slack_adversarial(form):
+    """Sharp 30-column motifs at thresholds set exactly on a window's score: the window is a hit of
+    motif 0 (forward), while the reverse-strand field of the same motif and the fields of the motif that
+    shares its lane collect the largest deficits the tables can hold.  In the sticky form those fields
+    wrap and carry into the hit's field; round 1 under-counted the carries (one hit in 2.6 M lost at a
+    1e-6 hit rate on B200, 206 of 400 of these cases on the host).  No form may lose the hit."""
+    from oracle import pssm_oracle as po
+
+    rng = np.random.default_rng(1)
+    L, M = 30, 64
+
+    def sharp(cons):
+        counts = np.full((L, 4), 1.0)
+        counts[np.arange(L), cons] += 200
+        return po.log_odds(po.normalize(counts, 0.5))
+
+    cons = rng.integers(0, 4, size=L)
+    mats = [sharp(rng.integers(0, 4, size=L)) for _ in range(M)]
+    mats[0] = sharp(cons)
+    anti = np.full((L, 4), 30.0)
+    anti[np.arange(L), (cons + 2) % 4] += 200
+    anti[np.arange(L), cons] = 0.0
+    mats[32] = po.log_odds(po.normalize(anti, 0.01))      # shares lane 0 with motif 0 in a narrow block
+    lo, lens = np.stack(mats), np.full(M, L, dtype=np.int32)
+    for trial in range(120):
+        w = cons.copy()
+        k = int(rng.integers(1, 6))
+        idx = rng.choice(L, size=k, replace=False)
+        w[idx] = rng.integers(0, 4, size=k)
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[w]
+        thr = np.full(M, 1e9, dtype=np.float32)
+        thr[0] = po.calculate(seq, mats[0])[0]             # the window scores exactly the threshold: a hit
+        thr[32] = po.calculate(seq, mats[32])[0] if trial % 2 else -1e9
+        cand = _lib.hits_filter_host(lo, lens, thr, form, w.astype(np.uint8))
+        assert cand[0, 0, 0] == 1, (form, trial)
+        if trial % 2:
+            assert cand[0, 32, 0] == 1, (form, trial)
