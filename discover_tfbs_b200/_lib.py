@@ -32,15 +32,19 @@ _PROTOTYPES = {
     "tfbs_last_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_total_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_last_scan_candidates": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "tfbs_last_hits_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tfbs_timer_start": (C.c_int, [_vp]),
     "tfbs_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_host_alloc": (C.c_int, [_pp, _i64]),
     "tfbs_host_free": (C.c_int, [_vp]),
+    "tfbs_host_register": (C.c_int, [_vp, _i64]),
+    "tfbs_host_unregister": (C.c_int, [_vp]),
     "tfbs_flush_l2": (C.c_int, [_vp]),
     "tfbs_encode": (C.c_int, [_vp, _vp, _i64, _pp]),
     "tfbs_encode_device": (C.c_int, [_vp, _vp, _i64, _pp]),
     "tfbs_encode_into": (C.c_int, [_vp, _vp, _i64, _vp]),
     "tfbs_encode_device_into": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "tfbs_seq_create": (C.c_int, [_vp, _i64, _pp]),
     "tfbs_seq_destroy": (C.c_int, [_vp]),
     "tfbs_seq_length": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_seq_download": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -55,6 +59,7 @@ _PROTOTYPES = {
     "tfbs_scan_best": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "tfbs_scan_hits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, C.POINTER(_i64)]),
     "tfbs_scan_hits_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, C.POINTER(_i64)]),
+    "tfbs_scan_hits_host_shard": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, C.POINTER(_i64)]),
     "tfbs_shapes_upload": (C.c_int, [_vp, _vp, _vp, _i32, _pp]),
     "tfbs_shapes_destroy": (C.c_int, [_vp]),
     "tfbs_shape_tracks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -201,6 +206,32 @@ class PinnedBuffer:
             pass
 
 
+class RegisteredHost:
+    """Page-locks a caller-owned NumPy array in place for the lifetime of the object (or `with` block)."""
+
+    def __init__(self, array: np.ndarray):
+        self.array = array
+        self._ptr = array.ctypes.data
+        _check(load().tfbs_host_register(C.c_void_p(self._ptr), int(array.nbytes)))
+
+    def close(self):
+        if self._ptr:
+            load().tfbs_host_unregister(C.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One B200 + one stream.  All compute goes through a Context."""
 
@@ -252,6 +283,12 @@ class Context:
         _check(self._lib.tfbs_last_scan_candidates(self._h, C.byref(n)))
         return int(n.value)
 
+    def last_hits_ms(self):
+        """(scan_ms, verify_ms) of the filter scan and the exact verify pass of the last scan_hits."""
+        a, b = C.c_float(0), C.c_float(0)
+        _check(self._lib.tfbs_last_hits_ms(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     def timer_start(self):
         _check(self._lib.tfbs_timer_start(self._h))
 
@@ -269,6 +306,12 @@ class Context:
         h = C.c_void_p()
         _check(self._lib.tfbs_encode(self._h, _ptr(a), a.size, C.byref(h)))
         return EncodedSeq(self, h, a.size)
+
+    def alloc_seq(self, n: int) -> "EncodedSeq":
+        """An empty handle for n bases (device buffers only; filled by reencode / scan_hits_host)."""
+        h = C.c_void_p()
+        _check(self._lib.tfbs_seq_create(self._h, int(n), C.byref(h)))
+        return EncodedSeq(self, h, int(n))
 
     def encode_device(self, dev_ptr: int, n: int) -> "EncodedSeq":
         h = C.c_void_p()
@@ -355,6 +398,19 @@ class Context:
         n = _i64(0)
         _check(self._lib.tfbs_scan_hits_host(self._h, _ptr(a), a.size, seq._h, pwms._h, _ptr(thr), _ptr(out),
                                              out.size, int(chunks), int(sort), C.byref(n)))
+        return out[: n.value]
+
+    def scan_hits_host_shard(self, ascii_host: np.ndarray, seq: "EncodedSeq", pwms: "MotifLibrary", thresholds,
+                             out: np.ndarray, owned: int, shard_start: int, chunks: int = 8, sort: bool = False):
+        """scan_hits_host for one shard of a longer sequence (buffer = shard + right halo): only windows
+        starting in the first `owned` bases are reported, positions are shifted by `shard_start` — both
+        on the device."""
+        thr = np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, dtype=np.float32), (pwms.M,)))
+        a = as_ascii(ascii_host)
+        n = _i64(0)
+        _check(self._lib.tfbs_scan_hits_host_shard(self._h, _ptr(a), a.size, seq._h, pwms._h, _ptr(thr), _ptr(out),
+                                                   out.size, int(chunks), int(sort), int(owned), int(shard_start),
+                                                   C.byref(n)))
         return out[: n.value]
 
     # -- (3) shape -------------------------------------------------------------------------

@@ -90,6 +90,7 @@ int tfbs_ctx_create(int device, tfbs_ctx **out)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_mid);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking);
@@ -122,6 +123,7 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     free_scratch(ctx->sort);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     for (cudaEvent_t ev : ctx->pipe_events) cudaEventDestroy(ev);
@@ -169,6 +171,14 @@ int tfbs_last_scan_candidates(tfbs_ctx *ctx, int64_t *n)
     return TFBS_OK;
 }
 
+int tfbs_last_hits_ms(tfbs_ctx *ctx, float *scan_ms, float *verify_ms)
+{
+    TFBS_REQUIRE(ctx && scan_ms && verify_ms, "tfbs_last_hits_ms: null argument");
+    *scan_ms = ctx->last_scan_ms;
+    *verify_ms = ctx->last_verify_ms;
+    return TFBS_OK;
+}
+
 int tfbs_timer_start(tfbs_ctx *ctx)
 {
     TFBS_REQUIRE(ctx, "tfbs_timer_start: null argument");
@@ -191,6 +201,20 @@ int tfbs_host_alloc(void **ptr, int64_t bytes)
 {
     TFBS_REQUIRE(ptr && bytes >= 0, "tfbs_host_alloc: bad argument");
     TFBS_CHECK_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return TFBS_OK;
+}
+
+int tfbs_host_register(void *ptr, int64_t bytes)
+{
+    TFBS_REQUIRE(ptr && bytes > 0, "tfbs_host_register: bad argument");
+    TFBS_CHECK_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return TFBS_OK;
+}
+
+int tfbs_host_unregister(void *ptr)
+{
+    TFBS_REQUIRE(ptr, "tfbs_host_unregister: null argument");
+    TFBS_CHECK_CUDA(cudaHostUnregister(ptr));
     return TFBS_OK;
 }
 

@@ -42,6 +42,8 @@ struct tfbs_ctx {
     int sm_count = TFBS_SM_COUNT_FALLBACK;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // per-call kernel bracket
+    cudaEvent_t ev_mid = nullptr;              // between the filter scan and the verify pass of tfbs_scan_hits
+    float last_scan_ms = 0.f, last_verify_ms = 0.f;
     cudaEvent_t evt0 = nullptr, evt1 = nullptr;  // user region timer
     cudaStream_t stream_in = nullptr, stream_out = nullptr;  // copy streams of the pipelined host path
     std::vector<cudaEvent_t> pipe_events;

@@ -305,6 +305,26 @@ int tfbs_encode_device(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq
     return TFBS_OK;
 }
 
+int tfbs_seq_create(tfbs_ctx *ctx, int64_t n, tfbs_seq **out)
+{
+    TFBS_REQUIRE(ctx && out && n >= 0, "tfbs_seq_create: bad argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    tfbs_seq *s = nullptr;
+    int rc = alloc_seq(ctx, n, &s);
+    if (rc) return rc;
+    // until something is encoded into it the handle holds n invalid bases
+    cudaError_t e = cudaMemsetAsync(s->packed, 0, (size_t)s->n_words * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->mask, 0xFF, (size_t)s->n_mask * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        tfbs_set_error("tfbs_seq_create: %s", cudaGetErrorString(e));
+        tfbs_seq_destroy(s);
+        return TFBS_ERR_CUDA;
+    }
+    *out = s;
+    return TFBS_OK;
+}
+
 int tfbs_encode_into(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq)
 {
     TFBS_REQUIRE(ctx && seq && (ascii_host || n == 0), "tfbs_encode_into: null argument");

@@ -47,9 +47,13 @@
 //     (tfbs_build_hits_tables).
 //   * persistent CTAs (1 per SM, 16 warps) pull (motif block, tile) items from an atomic counter in
 //     block-major order, so a CTA re-loads its table (up to 192 KB) only when the block changes.
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cooperative_groups.h>
+#include <thread>
 #include <cub/device/device_radix_sort.cuh>
 #include <cstdlib>
 #include <cstring>
@@ -769,12 +773,14 @@ void tfbs_hits_group_plan(int L, int *A_out, int *B_out)
 
 // ---- block plan + filter tables (host) ------------------------------------------------------------
 // Cost model of the block form, in warp-wide shared-memory loads per window start, fitted to B200
-// measurements at 100 Mb x 800 PWMs and hit rates 1e-6 .. 1e-2 (profiles/r01/SUMMARY.md): one load
-// costs 4.1 ps per window; a candidate handed to the exact verifier costs 0.16 / 0.22 / 0.20 ns in a
-// wide / narrow / sticky block; a load of the sticky form costs kStickyLoad plain loads (one more ALU
-// op each).  A narrow block of G groups replaces two wide blocks of G and G2 groups.
-constexpr double kCandidateCost[3] = {39.0, 54.0, 50.0};
-constexpr double kStickyLoad = 1.18;
+// measurements at 100 Mb x 800 PWMs and hit rates 1e-6 .. 1e-2 (profiles/r02/SUMMARY.md): one load
+// costs 3.75 ps per window; a candidate (queue + list hand-over in the scan, exact re-score in the
+// verify kernel) costs 0.08 - 0.10 ns = 21 / 24 / 26 loads in a wide / narrow / sticky block (0.16 -
+// 0.22 ns while the scan kernel verified in place, round 1); a load of the sticky form costs
+// kStickyLoad plain loads (one more ALU op each).  A narrow block of G groups replaces two wide blocks
+// of G and G2 groups.
+constexpr double kCandidateCost[3] = {21.0, 24.0, 26.0};
+constexpr double kStickyLoad = 1.08;
 constexpr int kSaturatingSteps[] = {48, 64};  // step counts tried for saturating plain 8-bit fields (32, 96 and
                                               // 124 were almost never the best on the 800-PWM library)
 enum { kWide = 0, kNarrow = 1, kSticky = 2 };
@@ -1034,10 +1040,52 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     int64_t words = 0;   // table words of the blocks emitted so far
     int nb = 0;
     const int32_t *order = pw->order.data();
-    // a narrow / sticky block is built in place by choose_form, a wide one by emit below
+    // The form of a block depends only on where it starts, and every block starts at a multiple of 32
+    // motifs: the forms (and tables) of all possible starts are worked out speculatively on the host's
+    // cores, then the sequential cut below picks the ones it reaches.  (Planning the 800-PWM library
+    // one block after the other took 0.2 - 0.3 s per new threshold vector, ten times the scan.)
+    struct Spec {
+        int form = -1, A = 0, B = 0, count = 0;
+        std::vector<uint32_t> lut, kinit;
+    };
+    std::vector<Spec> spec((size_t)(M + 31) / 32);
+    std::vector<int> starts;
+    for (int i = 0; i < M; i += 32) {
+        Spec &S = spec[(size_t)i / 32];
+        tfbs_hits_group_plan(pw->lens_desc[i], &S.A, &S.B);
+        S.count = std::min(M - i, 64);
+        if (S.A + S.B <= TFBS_NARROW_MAX_GROUPS && M - i > 32) starts.push_back(i);
+    }
+    {
+        cpu_set_t set;
+        unsigned cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
+        unsigned T = std::max(1u, std::min<unsigned>(std::min(cores, 32u), (unsigned)starts.size()));
+        const int forced = env_int("TFBS_PLAN_THREADS");  // 1 = plan in the calling thread
+        if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t k = next.fetch_add(1); k < starts.size(); k = next.fetch_add(1)) {
+                Spec &S = spec[(size_t)starts[k] / 32];
+                S.lut.assign((size_t)S.A * 8192 + (size_t)S.B * 2048, 0u);
+                S.kinit.assign(32, kPoison);
+                double expected;
+                S.form = choose_form(pw, thr, starts[k], S.count, S.A, S.B, S.lut.data(), S.kinit.data(), &expected);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+    }
+    // a narrow / sticky block's tables were built by choose_form above, a wide one is built by emit below
     auto accept = [&](int first, int count, int A, int B) -> int {
-        double expected;
-        return choose_form(pw, thr, first, count, A, B, qlut.data() + words, kinit.data() + (size_t)nb * 32, &expected);
+        const Spec &S = spec[(size_t)first / 32];
+        (void)count; (void)A; (void)B;
+        if (S.form != kWide) {
+            std::copy(S.lut.begin(), S.lut.end(), qlut.begin() + words);
+            std::copy(S.kinit.begin(), S.kinit.end(), kinit.begin() + (size_t)nb * 32);
+        }
+        return S.form;
     };
     pw->blk_A.clear();
     pw->blk_B.clear();
@@ -1131,9 +1179,12 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     tfbs_begin(ctx);
     scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
     tfbs_launched(ctx);
+    cudaEventRecord(ctx->ev_mid, ctx->stream);
     launch_verify(ctx, P);
     rc = tfbs_end(ctx);
     if (rc) return rc;
+    cudaEventElapsedTime(&ctx->last_scan_ms, ctx->ev0, ctx->ev_mid);
+    cudaEventElapsedTime(&ctx->last_verify_ms, ctx->ev_mid, ctx->ev1);
     unsigned long long cnt2[3] = {0, 0, 0};
     TFBS_CHECK_CUDA(cudaMemcpyAsync(cnt2, ctx->hit_count.ptr, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream));
     TFBS_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,10 +1,11 @@
-"""Chunk + halo sharding of a genome scan across GPUs (one process or thread per GPU).
+"""Chunk + halo sharding of a genome scan across GPUs (one process or thread per GPU), and
+record-index sharding of record sets.
 
 The path has no cross-shard reduction: a window belongs to the shard that
 contains its start, so every shard scans `[start, owned_end + halo)` independently and keeps
-only hits that start before `owned_end`; results are concatenated on the host in shard order.
-No collective is used on the data path (torch.distributed only provides the barrier / timing
-reduction in bench.py).
+only hits that start before `owned_end` (dropped on the device by `tfbs_scan_hits_host_shard`);
+results are concatenated on the host in shard order.  No collective is used on the data path
+(torch.distributed only provides the barrier / timing reduction in bench.py).
 """
 from dataclasses import dataclass
 
@@ -68,7 +69,8 @@ def filter_owned(hits: np.ndarray, shard: Shard) -> np.ndarray:
 
 
 def merge_shard_hits(per_shard: list) -> np.ndarray:
-    """Concatenate per-shard hit arrays (already global) and order them (motif, pos, strand)."""
+    """Concatenate per-shard hit arrays (already global) and order them (motif, pos, strand) with one
+    global sort.  Generic form (any per-shard order); `concat_sorted_shards` is the fast path."""
     if not per_shard:
         return np.zeros(0, dtype=_lib.HIT_DTYPE)
     allh = np.concatenate(per_shard)
@@ -77,38 +79,181 @@ def merge_shard_hits(per_shard: list) -> np.ndarray:
     return allh[order]
 
 
-def scan_genome_multi_gpu(genome: np.ndarray, logodds, lens, thresholds, devices=None, cap=1 << 22):
-    """Hits-mode scan of one host-resident genome across several GPUs of one node, one host thread
-    per device (ctypes releases the GIL).  Returns globally ordered hits."""
+def concat_sorted_shards(per_shard: list, n_motifs: int) -> np.ndarray:
+    """Whole-genome (motif, pos, strand) order from per-shard arrays that are each in that order and
+    hold global positions: shards are position-ordered, so for every motif the shard pieces are simply
+    laid end to end — an ordered concatenation, no comparison sort."""
+    if not per_shard:
+        return np.zeros(0, dtype=_lib.HIT_DTYPE)
+    if len(per_shard) == 1:
+        return per_shard[0]
+    bounds = [np.searchsorted(h["motif"], np.arange(n_motifs + 1)) for h in per_shard]  # [shard][motif] -> row
+    counts = np.stack([np.diff(b) for b in bounds])                   # [shard][motif]
+    out = np.empty(int(counts.sum()), dtype=_lib.HIT_DTYPE)
+    # destination of (motif m, shard k) = hits of motifs < m + hits of motif m in shards < k
+    motif_base = np.concatenate([[0], np.cumsum(counts.sum(axis=0))[:-1]])
+    within = np.cumsum(counts, axis=0) - counts
+    for k, h in enumerate(per_shard):
+        if h.size == 0:
+            continue
+        # row i of shard k (motif m) goes to motif_base[m] + within[k][m] + (i - bounds[k][m])
+        m = h["motif"]
+        dst = motif_base[m] + within[k][m] + (np.arange(h.size) - bounds[k][m])
+        out[dst] = h
+    return out
+
+
+class _DeviceWorker:
+    """One GPU of the node: context, motif library, shard-sized device buffers, pinned output."""
+
+    def __init__(self, device, logodds, lens, shard: Shard, cap: int):
+        self.ctx = _lib.Context(device)
+        self.lib = self.ctx.upload_pwms(logodds, lens)
+        self.enc = self.ctx.alloc_seq(shard.scanned)
+        self.out = _lib.PinnedBuffer(cap * _lib.HIT_DTYPE.itemsize)
+        self.hits = self.out.view(_lib.HIT_DTYPE)
+        self.shard = shard
+
+    def close(self):
+        self.enc.close()
+        self.lib.close()
+        self.out.close()
+        self.ctx.close()
+
+
+class MultiGpuScanner:
+    """Hits-mode scan of host-resident genomes across the GPUs of one node (chunk +
+    (Lmax - 1) halo shards, no collective).  One host thread per device (ctypes releases the GIL);
+    every thread runs the chunk-pipelined host path `tfbs_scan_hits_host_shard` on its shard — H2D,
+    encode + scan and D2H overlap on three streams per GPU; halo duplicates are dropped and positions
+    made global ON THE DEVICE; per-shard outputs (device-sorted) are joined by ordered concatenation.
+    Contexts, libraries, device buffers and pinned outputs persist across `scan()` calls."""
+
+    def __init__(self, n_bases: int, logodds, lens, devices=None, cap_per_device: int = 1 << 22):
+        ndev = _lib.device_count()
+        self.devices = list(range(ndev)) if devices is None else list(devices)
+        if not self.devices:
+            raise RuntimeError("no CUDA device; there is no CPU fallback")
+        self.lens = np.asarray(lens, dtype=np.int32)
+        self.n = int(n_bases)
+        self.shards = plan_shards(self.n, len(self.devices), int(self.lens.max()) - 1)
+        self.workers = [None] * len(self.devices)
+        self._run(lambda i: self._make(i, logodds, cap_per_device))
+        self.last_ms = None
+
+    def _make(self, i, logodds, cap):
+        self.workers[i] = _DeviceWorker(self.devices[i], logodds, self.lens, self.shards[i], cap)
+
+    def _run(self, fn):
+        import threading
+
+        errors = []
+
+        def guarded(i):
+            try:
+                fn(i)
+            except Exception as exc:  # surfaced below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=guarded, args=(i,)) for i in range(len(self.devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def scan(self, genome: np.ndarray, thresholds, sort: bool = True, chunks: int = 8, merge: bool = True):
+        """genome: uint8[n_bases] in host memory (page-locked for full PCIe rate: `_lib.PinnedBuffer` or
+        `_lib.RegisteredHost`).  Returns the whole-genome hit array (a fresh array owned by the caller) —
+        (motif, pos, strand) order when `sort` — or, with merge=False, the list of per-shard views into
+        the pinned outputs (zero-copy; valid until the next scan() or close())."""
+        import time
+
+        if genome.size != self.n:
+            raise ValueError(f"genome has {genome.size} bases, scanner was planned for {self.n}")
+        parts = [None] * len(self.workers)
+        t0 = time.perf_counter()
+
+        def work(i):
+            w = self.workers[i]
+            sh = w.shard
+            parts[i] = w.ctx.scan_hits_host_shard(genome[sh.start: sh.scan_end], w.enc, w.lib, thresholds, w.hits,
+                                                  owned=sh.owned, shard_start=sh.start, chunks=chunks, sort=sort)
+
+        self._run(work)
+        t1 = time.perf_counter()
+        if not merge:
+            out = parts   # views into the workers' pinned buffers: valid until the next scan() / close()
+        elif len(parts) == 1:
+            out = parts[0].copy()
+        elif sort:
+            out = concat_sorted_shards(parts, int(self.lens.size))
+        else:
+            out = np.concatenate(parts)
+        self.last_ms = {"scan_wall_ms": (t1 - t0) * 1e3, "merge_wall_ms": (time.perf_counter() - t1) * 1e3}
+        return out
+
+    def close(self):
+        for w in self.workers:
+            if w is not None:
+                w.close()
+        self.workers = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def scan_genome_multi_gpu(genome: np.ndarray, logodds, lens, thresholds, devices=None, cap=1 << 22, sort=True,
+                          chunks: int = 8):
+    """One-shot form of `MultiGpuScanner`: page-locks `genome` in place for the duration of the call,
+    scans it on every visible GPU (or `devices`) and returns globally ordered hits."""
+    genome = np.ascontiguousarray(genome, dtype=np.uint8)
+    with MultiGpuScanner(genome.size, logodds, lens, devices, cap) as sc:
+        with _lib.RegisteredHost(genome):
+            return sc.scan(genome, thresholds, sort=sort, chunks=chunks)
+
+
+# ---- record sets (configs C1 / C2): shard by record index ---------------------------------------------
+def plan_record_shards(n_records: int, n_shards: int):
+    """[(first, last_exclusive), ...]: contiguous, near-equal ranges of record indices (SURVEY.md §8e:
+    "small-sequence workloads shard by sequence index instead").  Records are independent, so there is
+    no halo."""
+    if n_shards < 1:
+        raise ValueError("n_shards must be >= 1")
+    edges = [(n_records * i) // n_shards for i in range(n_shards + 1)]
+    return list(zip(edges[:-1], edges[1:]))
+
+
+def map_record_shards(fn, n_records: int, devices=None):
+    """Run fn(ctx, first, last) for every record shard on its own GPU (one thread + Context per device)
+    and return the results in shard order.  fn must only use the Context it is given."""
     import threading
 
     ndev = _lib.device_count()
     devices = list(range(ndev)) if devices is None else list(devices)
     if not devices:
         raise RuntimeError("no CUDA device; there is no CPU fallback")
-    lens = np.asarray(lens)
-    shards = plan_shards(genome.size, len(devices), int(lens.max()) - 1)
-    results = [None] * len(shards)
-    errors = []
+    ranges = plan_record_shards(n_records, len(devices))
+    results, errors = [None] * len(devices), []
 
-    def work(i, dev):
+    def work(i):
         try:
-            sh = shards[i]
-            with _lib.Context(dev) as ctx:
-                lib = ctx.upload_pwms(logodds, lens)
-                enc = ctx.encode(genome[sh.start: sh.scan_end])
-                hits = ctx.scan_hits(enc, lib, thresholds, cap=cap, sort=False)
-                results[i] = filter_owned(hits, sh)
-                enc.close()
-                lib.close()
-        except Exception as exc:  # surfaced below
+            first, last = ranges[i]
+            if last > first:
+                with _lib.Context(devices[i]) as ctx:
+                    results[i] = fn(ctx, first, last)
+        except Exception as exc:
             errors.append(exc)
 
-    threads = [threading.Thread(target=work, args=(i, d)) for i, d in enumerate(devices)]
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(devices))]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     if errors:
         raise errors[0]
-    return merge_shard_hits(results)
+    return [r for r in results if r is not None]

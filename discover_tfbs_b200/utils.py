@@ -89,13 +89,29 @@ class GenomeShapeSource:
         buf, starts, lens = join_records([records[k] for k in self.names])
         self.start = dict(zip(self.names, starts.tolist()))
         self.length = dict(zip(self.names, lens.tolist()))
-        self.enc = self.ctx.encode(buf)
         self.shapes = tuple(shapes)
         self.kinds = np.asarray(kinds, dtype=np.int32)
-        self.tables = self.ctx.upload_shapes(tables, kinds)
+        self._buf, self._tables_host = buf, np.asarray(tables, dtype=np.float32)
+        self._place(self.ctx)
+        self._replicas = {}
         # True: token lists come from the awk-flattened one-line files (.COMMANDS.txt:290-293),
         # whose trailing comma adds one '' token per chromosome
         self.trailing_empty = bool(trailing_empty)
+
+    def _place(self, ctx):
+        self.ctx = ctx
+        self.enc = ctx.encode(self._buf)
+        self.tables = ctx.upload_shapes(self._tables_host, self.kinds)
+
+    def on(self, ctx):
+        """The same source resident on another context / device (multi-GPU feature builds)."""
+        if ctx is self.ctx:
+            return self
+        rep = object.__new__(GenomeShapeSource)
+        rep.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("enc", "tables", "ctx", "_replicas")})
+        rep._replicas = {}
+        rep._place(ctx)
+        return rep
 
     def __bool__(self):
         return True
@@ -147,7 +163,7 @@ def _get_DNA_shape(loc: str, shapedata, shape: str) -> dict:
     return {f"{shape}_{i + 1:02d}": float(v) for i, v in enumerate(row) if v == v}
 
 
-def _shape_rows(locs, shapedata, shape) -> np.ndarray:
+def _shape_rows(locs, shapedata, shape, ctx=None) -> np.ndarray:
     """float64[S][W] of reference-format values (NaN = key absent)."""
     chrom, start, end, strand = parse_locations(locs)
     width = int(np.max(end - start)) + 1 if len(locs) else 1
@@ -158,7 +174,7 @@ def _shape_rows(locs, shapedata, shape) -> np.ndarray:
         out = src.sites(locs, width)[:, t, :]
         return dnashape.to_reference_float64(out)
     # legacy dict input: parse each needed chromosome's token list once, gather on the GPU
-    ctx = default_context()
+    ctx = ctx or default_context()
     used = sorted(set(chrom))
     vals, off, ntok, pos = [], {}, {}, 0
     for c in used:
@@ -195,30 +211,19 @@ def get_shape_data(bedfile: str, shapefiles: list) -> dict:
 
 
 # ---- feature table ----------------------------------------------------------------------------
-def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=None, minhash=True, *,
-                        pwms=None, pwm_names=None, similarity_features=True, ctx=None):
-    """utils.py:1088-1173.  Returns a DataFrame with columns `location, sequence, GC_content,
-    [MinHash,] PAS, PPS, EP_01.., HelT_01.., MGW_01.., ProT_01.., Roll_01..` in the reference's
-    order and dtypes (float64).  GC content and every shape column come from the GPU.
+_SHAPE_LABELS = {"EP": "Electrostatic potential", "HelT": "Helix Twist", "MGW": "Minor groove width",
+                 "ProT": "Propeller twist", "Roll": "Roll"}
 
-    Keyword-only extensions: `pwms` (list of log-odds matrices) adds `<name>_fwd_max`,
-    `<name>_rev_max` best-window scores per sequence; `similarity_features=False` skips the
-    host-side MinHash/PAC columns."""
-    ctx = ctx or default_context()
-    print(strftime("%x %X | Begin building feature table"))
-    records = {header: seq for header, seq in parse_fasta(infasta)}
-    tf_data = pd.DataFrame({"location": list(records.keys()), "sequence": list(records.values())})
-    true_seqs = {seq for header, seq in parse_fasta(truefasta)}
-    seqs = list(records.values())
 
-    print(strftime("%x %X | Calculating GC content of input sequences"))
+def _feature_columns(ctx, locs, seqs, true_seqs, shape_data, minhash, pwms, similarity_features, quiet=False):
+    """Feature columns of one set (or one record shard) of sequences on one GPU: ordered dict
+    name -> float64[len(seqs)] for the scalar columns, plus 'shape' -> {shape: float64[S][W]}."""
+    say = (lambda *_: None) if quiet else (lambda msg: print(strftime(f"%x %X | {msg}")))
+    cols = {}
+    say("Calculating GC content of input sequences")
     buf, starts, lens = join_records(seqs)
     enc = ctx.encode(buf) if len(seqs) else None
-    if enc is not None:
-        gc = enc.gc_counts(starts, lens)
-        tf_data["GC_content"] = gc.astype(np.int64) / lens
-    else:
-        tf_data["GC_content"] = np.zeros(0)
+    cols["GC_content"] = enc.gc_counts(starts, lens).astype(np.int64) / lens if enc is not None else np.zeros(0)
 
     if similarity_features:
         if len(seqs):
@@ -229,43 +234,86 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
                                  "similarity_features=False to skip these columns")
             # all-pairs kernel (tfbs_similarity_sums); k-mer / hash preparation is vectorised host code
             if minhash:
-                print(strftime("%x %X | Calculating MinHash similarity score"))
-            print(strftime("%x %X | Calculating Poisson similarity scores"))
+                say("Calculating MinHash similarity score")
+            say("Calculating Poisson similarity scores")
             mh, pas, pps = similarity.similarity_columns_gpu(ctx, seqs, true_seqs)
-            if minhash:
-                tf_data["MinHash"] = mh
-            tf_data["PAS"] = pas
-            tf_data["PPS"] = pps
         else:
-            if minhash:
-                tf_data["MinHash"] = np.zeros(0)
-            tf_data["PAS"] = np.zeros(0)
-            tf_data["PPS"] = np.zeros(0)
+            mh = pas = pps = np.zeros(0)
+        if minhash:
+            cols["MinHash"] = mh
+        cols["PAS"] = pas
+        cols["PPS"] = pps
 
     if pwms is not None and enc is not None:
-        print(strftime("%x %X | Scoring position weight matrices on both strands"))
-        lib = ctx.upload_pwms(list(pwms))
+        say("Scoring position weight matrices on both strands")
+        mats, names = pwms
+        lib = ctx.upload_pwms(list(mats))
         # reduced on the device (tfbs_scan_best): S x M x 2 floats cross PCIe, not the dense [M][n] arrays
         best = ctx.scan_best(enc, lib, starts, lens)
-        names = pwm_names or [f"PWM{i + 1}" for i in range(lib.M)]
         for m, name in enumerate(names):
-            tf_data[f"{name}_fwd_max"] = best[:, m, 0].astype(np.float64)
-            tf_data[f"{name}_rev_max"] = best[:, m, 1].astype(np.float64)
+            cols[f"{name}_fwd_max"] = best[:, m, 0].astype(np.float64)
+            cols[f"{name}_rev_max"] = best[:, m, 1].astype(np.float64)
         lib.close()
 
-    if genome_wide_shape_data:
-        labels = {"EP": "Electrostatic potential", "HelT": "Helix Twist", "MGW": "Minor groove width",
-                  "ProT": "Propeller twist", "Roll": "Roll"}
-        locs = list(tf_data["location"])
+    shape_rows = {}
+    if shape_data:
         for shape in ("EP", "HelT", "MGW", "ProT", "Roll"):
-            print(strftime(f"%x %X | Retrieving {labels[shape]} shape values"))
-            rows = _shape_rows(locs, genome_wide_shape_data[shape], shape)
-            # json_normalize in the reference only creates the keys that exist in some row
-            keep = [w for w in range(rows.shape[1]) if not np.isnan(rows[:, w]).all()] if len(locs) else []
-            block = pd.DataFrame({f"{shape}_{w + 1:02d}": rows[:, w] for w in keep}, index=tf_data.index)
-            tf_data = tf_data.join(block)
+            say(f"Retrieving {_SHAPE_LABELS[shape]} shape values")
+            shape_rows[shape] = _shape_rows(locs, shape_data[shape], shape, ctx=ctx)
     if enc is not None:
         enc.close()
+    return cols, shape_rows
+
+
+def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=None, minhash=True, *,
+                        pwms=None, pwm_names=None, similarity_features=True, ctx=None, devices=None):
+    """utils.py:1088-1173.  Returns a DataFrame with columns `location, sequence, GC_content,
+    [MinHash,] PAS, PPS, EP_01.., HelT_01.., MGW_01.., ProT_01.., Roll_01..` in the reference's
+    order and dtypes (float64).  GC content and every shape column come from the GPU.
+
+    Keyword-only extensions: `pwms` (list of log-odds matrices) adds `<name>_fwd_max`,
+    `<name>_rev_max` best-window scores per sequence; `similarity_features=False` skips the
+    MinHash/PAC columns; `devices=[0, 1, ...]` shards the records by index over several GPUs of the
+    node, one host thread and context per device, rows returned in input order."""
+    print(strftime("%x %X | Begin building feature table"))
+    records = {header: seq for header, seq in parse_fasta(infasta)}
+    locs, seqs = list(records.keys()), list(records.values())
+    tf_data = pd.DataFrame({"location": locs, "sequence": seqs})
+    true_seqs = {seq for header, seq in parse_fasta(truefasta)}
+    pw = None
+    if pwms is not None:
+        mats = list(pwms)
+        pw = (mats, list(pwm_names) if pwm_names else [f"PWM{i + 1}" for i in range(len(mats))])
+
+    if devices is not None and len(devices) > 1 and len(seqs) >= len(devices):
+        from . import sharding
+
+        def shard(c, first, last):
+            sd = genome_wide_shape_data
+            if isinstance(sd, GenomeShapeSource):
+                sd = sd.on(c)  # the chromosomes + tables resident on THIS device
+            return _feature_columns(c, locs[first:last], seqs[first:last], true_seqs, sd, minhash, pw,
+                                    similarity_features, quiet=True)
+
+        print(strftime(f"%x %X | Computing feature columns on {len(devices)} GPUs (records sharded by index)"))
+        parts = sharding.map_record_shards(shard, len(seqs), devices)
+        cols = {k: np.concatenate([p[0][k] for p in parts]) for k in parts[0][0]}
+        width = {sh: max(p[1][sh].shape[1] for p in parts) for sh in parts[0][1]}
+        shape_rows = {}
+        for sh, w in width.items():  # ragged widths across shards: pad with NaN (= key absent)
+            shape_rows[sh] = np.concatenate([np.pad(p[1][sh], ((0, 0), (0, w - p[1][sh].shape[1])), constant_values=np.nan)
+                                             for p in parts])
+    else:
+        cols, shape_rows = _feature_columns(ctx or default_context(), locs, seqs, true_seqs, genome_wide_shape_data,
+                                            minhash, pw, similarity_features)
+
+    for name, values in cols.items():
+        tf_data[name] = values
+    for shape, rows in shape_rows.items():
+        # json_normalize in the reference only creates the keys that exist in some row
+        keep = [w for w in range(rows.shape[1]) if not np.isnan(rows[:, w]).all()] if len(locs) else []
+        block = pd.DataFrame({f"{shape}_{w + 1:02d}": rows[:, w] for w in keep}, index=tf_data.index)
+        tf_data = tf_data.join(block)
     print(strftime("%x %X | Finished building feature table"))
     return tf_data
 

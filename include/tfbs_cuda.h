@@ -75,6 +75,9 @@ int tfbs_last_kernel_launches(tfbs_ctx *ctx, int64_t *n);
 int tfbs_total_kernel_launches(tfbs_ctx *ctx, int64_t *n);
 /* How many filter candidates the most recent tfbs_scan_hits verified exactly (>= hits). */
 int tfbs_last_scan_candidates(tfbs_ctx *ctx, int64_t *n);
+/* Device time of the two kernels of the most recent tfbs_scan_hits: the filter scan and the exact
+ * verify pass over its candidate list (bench.py reports a roofline for each). */
+int tfbs_last_hits_ms(tfbs_ctx *ctx, float *scan_ms, float *verify_ms);
 /* Region timer: CUDA events recorded on the context's stream; stop synchronises and returns the
  * elapsed device time of everything enqueued in between (kernels and async copies). */
 int tfbs_timer_start(tfbs_ctx *ctx);
@@ -96,6 +99,9 @@ int tfbs_encode_device(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq
 /* Re-encode into an existing handle of the same length (no allocation; bench inner loop). */
 int tfbs_encode_into(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq);
 int tfbs_encode_device_into(tfbs_ctx *ctx, const void *ascii_dev, int64_t n, tfbs_seq *seq);
+/* An empty handle for n bases (all invalid until tfbs_encode_into / tfbs_scan_hits_host fill it):
+ * lets the end-to-end paths allocate once and re-use the device buffers for every shard or step. */
+int tfbs_seq_create(tfbs_ctx *ctx, int64_t n, tfbs_seq **out);
 int tfbs_seq_destroy(tfbs_seq *seq);
 int tfbs_seq_length(const tfbs_seq *seq, int64_t *n);
 /* Copy the encoding back: packed[ceil(n/16)], mask[ceil(n/32)] (parity tests). */
@@ -158,6 +164,20 @@ int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, co
 int tfbs_scan_hits_host(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
                         const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
                         int32_t chunks, int32_t sorted, int64_t *n_hits);
+/* Shard form of tfbs_scan_hits_host for chunk + halo sharding across GPUs: the buffer
+ * is one shard [shard_start, shard_start + n) of a longer sequence, passed WITH its right halo of
+ * (Lmax - 1) bases; only windows that start in its first `owned` bases are reported (the halo's
+ * windows belong to the next shard) and shard_start is added to every position — both on the device,
+ * so the per-shard outputs concatenate into the whole-genome result without a host-side filter.
+ * With `sorted` the shard's hits are ordered (motif, pos, strand) on the device before the copy. */
+int tfbs_scan_hits_host_shard(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t n, tfbs_seq *seq,
+                              const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
+                              int32_t chunks, int32_t sorted, int64_t owned, int64_t shard_start,
+                              int64_t *n_hits);
+/* Page-lock caller-owned host memory in place (cudaHostRegister) so the copies of the end-to-end
+ * paths run at full PCIe rate without a staging copy; undo with tfbs_host_unregister. */
+int tfbs_host_register(void *ptr, int64_t bytes);
+int tfbs_host_unregister(void *ptr);
 /* The blocks the last hits scan of this library used: narrow (64 motifs, 8-bit filter fields) or wide
  * (32 motifs, 16-bit) is chosen per block from the thresholds by a cost model (expected candidates
  * against shared-memory loads saved).  out[4b..4b+3] = {A, B, narrow, motifs}; `cap` = blocks `out`

@@ -3,12 +3,13 @@
 one 12-bp TF PWM, 5 000 foreground 200-bp peaks + 50 000 shuffled 2+2-padded backgrounds,
 GC + MinHash/PAS/PPS + PWM + DNA-shape features, assembled exactly like build_features.py:193-258.
 Prints per-stage wall-clock and, beside it, the host-CPU cost of the same stages measured on a
-sample with the scalar restatement of the reference's loops (discover_tfbs_b200.similarity)."""
+sample with the scalar restatement of the reference's loops (oracle/similarity_oracle.py)."""
 import os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import io, contextlib
 import numpy as np, pandas as pd
-from discover_tfbs_b200 import _lib, dnashape, synth, similarity as sm
+from discover_tfbs_b200 import _lib, dnashape, synth
+from oracle import similarity_oracle as sm
 from discover_tfbs_b200 import utils as U
 
 def main():

@@ -438,6 +438,25 @@ def test_build_feature_table_vs_reference_golden(ctx, golden, tmp_path):
     _assert_table_equal(U.build_feature_table(str(fg), str(fg), src, minhash=True), ft["fg_table"])
     _assert_table_equal(U.build_feature_table(str(cand), str(fg), src, minhash=True), ft["cand_table"])
     _assert_table_equal(U.build_feature_table(str(cand), str(fg), minhash=False), ft["cand_noshape_table"])
+    # records sharded by index over "several" devices (two contexts on GPU 0 when the box has one GPU):
+    # same table, rows in input order, both shape input forms
+    devs = list(range(_lib.device_count())) if _lib.device_count() > 1 else [0, 0]
+    _assert_table_equal(U.build_feature_table(str(cand), str(fg), src, minhash=True, devices=devs), ft["cand_table"])
+    _assert_table_equal(U.build_feature_table(str(fg), str(fg), golden["shape_tokens"], minhash=True, devices=devs),
+                        ft["fg_table"])
+    # PWM columns: device-reduced best windows == max over the oracle's scores, single- and multi-device
+    mats = [synth.consensus_pwm(3 + i, L)[0] for i, L in enumerate((6, 9))]
+    t1 = U.build_feature_table(str(cand), str(fg), pwms=mats, pwm_names=["tfA", "tfB"], similarity_features=False)
+    t2 = U.build_feature_table(str(cand), str(fg), pwms=mats, pwm_names=["tfA", "tfB"], similarity_features=False,
+                               devices=devs)
+    assert list(t1.columns) == ["location", "sequence", "GC_content", "tfA_fwd_max", "tfA_rev_max", "tfB_fwd_max",
+                                "tfB_rev_max"]
+    assert t1.equals(t2)
+    for (name, seq), (_, row) in zip(ft["cand"], t1.iterrows()):
+        for m, tag in enumerate(("tfA", "tfB")):
+            if len(seq) >= mats[m].shape[0]:
+                assert row[f"{tag}_fwd_max"] == np.nanmax(po.calculate(seq, mats[m]))
+                assert row[f"{tag}_rev_max"] == np.nanmax(po.calculate(seq, po.reverse_complement(mats[m])))
 
 
 def test_background_shape_table_vs_reference_golden(ctx, golden, tmp_path):

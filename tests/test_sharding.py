@@ -52,6 +52,30 @@ def test_sharded_oracle_equals_unsharded(n_shards):
     assert got.size == want.size and np.array_equal(got, want)
 
 
+def test_ordered_concatenation_of_sorted_shards_equals_global_sort():
+    """Shards are position-ordered, so per-shard (motif, pos, strand)-sorted arrays with global
+    positions join by ordered concatenation: same result as one global lexsort."""
+    genome, logodds, lens, thr = _workload()
+    for n_shards in (1, 2, 5):
+        parts = []
+        for sh in sharding.plan_shards(genome.size, n_shards, int(lens.max()) - 1):
+            local = _oracle_hits(genome[sh.start: sh.scan_end], logodds, lens, thr)  # oracle order is (motif, pos, strand)
+            parts.append(sharding.filter_owned(local, sh))
+        got = sharding.concat_sorted_shards(parts, len(lens))
+        assert np.array_equal(got, sharding.merge_shard_hits(parts))
+    empty = np.zeros(0, dtype=_lib.HIT_DTYPE)
+    assert sharding.concat_sorted_shards([empty, empty], len(lens)).size == 0
+
+
+@pytest.mark.parametrize("n,k", [(0, 3), (1, 4), (55_000, 8), (7, 7), (10, 3)])
+def test_record_shards_cover_every_record_once(n, k):
+    r = sharding.plan_record_shards(n, k)
+    assert len(r) == k and r[0][0] == 0 and r[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    sizes = [b - a for a, b in r]
+    assert max(sizes) - min(sizes) <= 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -106,6 +130,69 @@ def test_shards_run_sequentially_on_one_gpu_match_single_scan(ctx):
     lib.close()
     multi = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=[0])
     assert np.array_equal(multi, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sort", [True, False])
+def test_shard_entry_point_drops_halo_and_shifts_positions_on_the_device(ctx, sort):
+    """tfbs_scan_hits_host_shard, shard after shard on one GPU: outputs carry global positions, no halo
+    duplicates, and (sorted) join by ordered concatenation into exactly the oracle's whole-genome list."""
+    genome, logodds, lens, thr = _workload(n=300_000, M=70)
+    lib = ctx.upload_pwms(logodds, lens)
+    want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
+    for n_shards in (1, 3, 7):
+        parts = []
+        for sh in sharding.plan_shards(genome.size, n_shards, int(lens.max()) - 1):
+            enc = ctx.alloc_seq(sh.scanned)
+            out = np.empty(1 << 18, dtype=_lib.HIT_DTYPE)
+            part = ctx.scan_hits_host_shard(genome[sh.start: sh.scan_end], enc, lib, thr, out, owned=sh.owned,
+                                            shard_start=sh.start, chunks=3, sort=sort)
+            g = np.where(part["pos"] < 0, ~part["pos"], part["pos"])
+            assert part.size == 0 or (g.min() >= sh.start and g.max() < sh.owned_end)
+            parts.append(part.copy())
+            enc.close()
+        got = sharding.concat_sorted_shards(parts, len(lens)) if sort else sharding.merge_shard_hits(parts)
+        assert np.array_equal(got, want), n_shards
+    lib.close()
+
+
+@pytest.mark.gpu
+def test_scanner_is_reusable_across_genomes_and_thresholds(ctx):
+    genome, logodds, lens, thr = _workload(n=200_000, M=40)
+    ndev = _lib.device_count()
+    with sharding.MultiGpuScanner(genome.size, logodds, lens, devices=list(range(ndev)), cap_per_device=1 << 18) as sc:
+        pinned = _lib.PinnedBuffer(genome.size)
+        for seed, scale in ((3, 1.0), (4, 1.0), (3, 1.05)):
+            g = synth.genome(seed, 0, genome.size)
+            pinned.array[:] = g
+            t = (thr * scale).astype(np.float32)
+            got = sc.scan(pinned.array, t)
+            assert np.array_equal(got, sharding.merge_shard_hits([_oracle_hits(g, logodds, lens, t)]))
+            assert sc.last_ms["scan_wall_ms"] > 0
+        pinned.close()
+
+
+@pytest.mark.gpu
+def test_record_shards_reproduce_the_single_gpu_feature_columns(ctx):
+    """Shard-by-record-index (configs C1 / C2): per-record best windows computed shard by shard on
+    every visible GPU equal the single-context result."""
+    fg, bkg = synth.peak_set(5, 300, 200, 2)
+    buf, starts, lens_rec = synth.join_records(fg)
+    mats = [synth.consensus_pwm(5 + i, L)[0] for i, L in enumerate((8, 12, 20))]
+    enc = ctx.encode(buf)
+    lib = ctx.upload_pwms(mats)
+    want = ctx.scan_best(enc, lib, starts, lens_rec)
+
+    def per_shard(c, first, last):
+        b, st, ln = synth.join_records(fg[first:last])
+        e = c.encode(b)
+        l2 = c.upload_pwms(mats)
+        return c.scan_best(e, l2, st, ln)
+
+    got = np.concatenate(sharding.map_record_shards(per_shard, fg.shape[0]))
+    assert np.array_equal(got, want)
+    enc.close()
+    lib.close()
 
 
 @pytest.mark.gpu
