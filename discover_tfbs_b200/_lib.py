@@ -66,6 +66,7 @@ _PROTOTYPES = {
     "tfbs_shape_sites": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "tfbs_track_sites": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "tfbs_similarity_sums": (C.c_int, [_vp] + [_vp] * 6 + [_i64] + [_vp] * 6 + [_i64, _vp]),
+    "tfbs_svc_decision": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, C.c_double, C.c_double, _vp]),
     "tfbs_debug_swar4": (C.c_int, [_u32, C.POINTER(_u32), C.POINTER(_u32)]),
     "tfbs_debug_dense_tables": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _vp, _i64]),
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),

@@ -238,6 +238,17 @@ int tfbs_similarity_sums(tfbs_ctx *ctx, const uint32_t *c_words, const uint16_t 
                          const uint16_t *t_counts, const int32_t *t_woff, const int32_t *t_nk,
                          const uint32_t *t_hash, const int32_t *t_hoff, int64_t U, double *out_host);
 
+/* ---- (5) scaler + SVC decision function ("next" row) -----------------
+ * Replaces the inference arithmetic of predict.py:286-319 for a FITTED model: x1 = x * mm_scale + mm_min
+ * (MinMaxScaler), x2 = (x1 - st_mean) / st_scale (StandardScaler; cross_validate_model.py:182-189), then
+ * sklearn SVC.decision_function: kernel 0 (linear): sv = coef_ [F], out = coef_ . x2 + intercept;
+ * kernel 1 (rbf): out = sum_i dual[i] * exp(-gamma * |sv[i] - x2|^2) + intercept, sv = [n_sv][F].
+ * X: double[S][F] raw features; out: double[S].  All arithmetic in double. */
+int tfbs_svc_decision(tfbs_ctx *ctx, const double *X_host, int64_t S, int32_t F, const double *mm_scale,
+                      const double *mm_min, const double *st_mean, const double *st_scale, int32_t kernel,
+                      const double *sv, const double *dual, int32_t n_sv, double gamma, double intercept,
+                      double *out_host);
+
 /* ---- test hooks (host-only, no device needed) -------------------------------------------
  * The encode kernel converts 4 ASCII bytes per 32-bit word with integer bit tricks; this runs
  * the same inline function on the host so the CPU test-suite can check it exhaustively. */

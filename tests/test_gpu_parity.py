@@ -184,7 +184,8 @@ def _oracle_best(rec, mat):
     sc = po.calculate(rec, mat)
     if np.isnan(sc).all():
         return np.float32(np.nan), -1
-    return np.nanmax(sc), int(np.nanargmax(sc))
+    ok = np.flatnonzero(~np.isnan(sc))   # (numpy.nanargmax would answer a NaN slot when the maximum is -inf)
+    return sc[ok].max(), int(ok[np.argmax(sc[ok])])
 
 
 def test_scan_best_bit_exact_vs_oracle(ctx):
@@ -843,3 +844,36 @@ def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypat
     assert h1.size == cnt and np.array_equal(h1["score"], score) and np.array_equal(h1["motif"], mot)
     enc.close()
     lib.close()
+
+
+# ---- (5) scaler + SVC decision function -------------------------------------
+@pytest.mark.parametrize("kernel,gamma", [("linear", "scale"), ("rbf", "scale"), ("rbf", 0.05)])
+def test_svc_decision_function_vs_sklearn(ctx, kernel, gamma):
+    """predict.py:286-319 with a fitted model: MinMax -> Standard -> SVC.decision_function / predict /
+    distance from the hyperplane equal sklearn's on the same matrix (1e-9; labels identical)."""
+    from numpy.linalg import norm
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+    from sklearn.svm import SVC
+
+    from discover_tfbs_b200.classify import GpuSVC
+
+    rng = np.random.default_rng(39)
+    F = 66                                                   # feature columns of a 12-bp TF (SURVEY.md a5)
+    X_train = rng.normal(size=(400, F)) * rng.uniform(0.1, 30, size=F) + rng.uniform(-20, 40, size=F)
+    X_train[:, 5] = 3.0                                      # a constant column: both scalers map it to 0
+    y = (X_train[:, 0] / 30 + np.sin(X_train[:, 1] / 10) + rng.normal(scale=0.3, size=400) > 0.4)
+    labels = np.where(y, "True", "Not_True")
+    pipe = Pipeline([("scale", MinMaxScaler()), ("standardize", StandardScaler())])
+    Xt = pipe.fit_transform(X_train)
+    clf = SVC(kernel=kernel, C=3.0, gamma=gamma, class_weight="balanced", random_state=39).fit(Xt, labels)
+    X_pred = rng.normal(size=(5000, F)) * rng.uniform(0.1, 30, size=F) + rng.uniform(-20, 40, size=F)
+    want = clf.decision_function(pipe.transform(X_pred))
+    gpu = GpuSVC.from_sklearn(pipe, clf, ctx=ctx)
+    got = gpu.decision_function(X_pred)
+    assert np.max(np.abs(got - want)) <= 1e-9
+    sure = np.abs(want) > 1e-9
+    assert np.array_equal(gpu.predict(X_pred)[sure], clf.predict(pipe.transform(X_pred))[sure])
+    if kernel == "linear":
+        assert np.max(np.abs(gpu.hyperplane_distance(X_pred) - want / norm(clf.coef_))) <= 1e-9
+    assert gpu.decision_function(np.zeros((0, F))).size == 0
