@@ -444,9 +444,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    host_group = None
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group: ranks that wait while rank 0 drives every GPU must not park a spinning NCCL
+        # kernel on their device (it would time-slice with rank 0's work there)
+        host_group = dist.new_group(backend="gloo")
     n_gpus = world
 
     ctx = _lib.Context(local)  # raises if the library or the GPU is missing: no CPU fallback
@@ -618,6 +622,8 @@ def run_ours(args):
                 line["product_api"] = product_api(ctx, args, logodds, lens, thr, n_gpus)
             except Exception as exc:
                 line["product_api"] = {"error": repr(exc)}
+        if host_group is not None:
+            dist.barrier(group=host_group)   # the other ranks sleep on the host, their GPUs stay idle
         barrier()
 
     if rank == 0:

@@ -90,16 +90,18 @@ def concat_sorted_shards(per_shard: list, n_motifs: int) -> np.ndarray:
     bounds = [np.searchsorted(h["motif"], np.arange(n_motifs + 1)) for h in per_shard]  # [shard][motif] -> row
     counts = np.stack([np.diff(b) for b in bounds])                   # [shard][motif]
     out = np.empty(int(counts.sum()), dtype=_lib.HIT_DTYPE)
-    # destination of (motif m, shard k) = hits of motifs < m + hits of motif m in shards < k
-    motif_base = np.concatenate([[0], np.cumsum(counts.sum(axis=0))[:-1]])
-    within = np.cumsum(counts, axis=0) - counts
-    for k, h in enumerate(per_shard):
-        if h.size == 0:
-            continue
-        # row i of shard k (motif m) goes to motif_base[m] + within[k][m] + (i - bounds[k][m])
-        m = h["motif"]
-        dst = motif_base[m] + within[k][m] + (np.arange(h.size) - bounds[k][m])
-        out[dst] = h
+    # motif by motif, the shard pieces are laid end to end: n_motifs x n_shards contiguous block copies
+    # (copied as plain 2 x uint64 rows: slice assignment of a structured dtype goes field by field)
+    raw_out = out.view(np.uint64).reshape(-1, 2)
+    raw_in = [np.ascontiguousarray(h).view(np.uint64).reshape(-1, 2) for h in per_shard]
+    at = 0
+    for m in range(n_motifs):
+        for k in range(len(per_shard)):
+            c = int(counts[k][m])
+            if c:
+                lo = int(bounds[k][m])
+                raw_out[at: at + c] = raw_in[k][lo: lo + c]
+                at += c
     return out
 
 
