@@ -40,6 +40,7 @@ _PROTOTYPES = {
     "tfbs_host_register": (C.c_int, [_vp, _i64]),
     "tfbs_host_unregister": (C.c_int, [_vp]),
     "tfbs_flush_l2": (C.c_int, [_vp]),
+    "tfbs_measure_smem_gbs": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_encode": (C.c_int, [_vp, _vp, _i64, _pp]),
     "tfbs_encode_device": (C.c_int, [_vp, _vp, _i64, _pp]),
     "tfbs_encode_into": (C.c_int, [_vp, _vp, _i64, _vp]),
@@ -297,6 +298,12 @@ class Context:
         ms = C.c_float(0)
         _check(self._lib.tfbs_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def measure_smem_gbs(self) -> float:
+        """Measured shared-memory load bandwidth (GB/s) of this GPU: conflict-free LDS.32 probe kernel."""
+        g = C.c_float(0)
+        _check(self._lib.tfbs_measure_smem_gbs(self._h, C.byref(g)))
+        return float(g.value)
 
     def flush_l2(self):
         _check(self._lib.tfbs_flush_l2(self._h))

@@ -238,6 +238,57 @@ int tfbs_flush_l2(tfbs_ctx *ctx)
     return TFBS_OK;
 }
 
+namespace {
+// Shared-memory load bandwidth probe: every thread streams conflict-free LDS.32 (lane-consecutive words,
+// the access pattern of the hits kernel's table look-ups) from a 32 KB table; the loaded value feeds the
+// next address so the loads cannot be hoisted, 8 independent chains per thread keep the pipe full.
+__global__ void __launch_bounds__(1024, 1) smem_probe_kernel(int iters, unsigned int *sink)
+{
+    __shared__ uint32_t tab[8192];
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) tab[i] = (uint32_t)(i * 2654435761u) & 0x1F80u;  // multiples of 128 B
+    __syncthreads();
+    const uint32_t lane_off = (threadIdx.x & 31u) * 4u;
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (uint32_t)((threadIdx.x >> 5) * 8 + k) * 128u & 0x7F80u;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (a[k] | lane_off)) : "memory");
+            a[k] = (a[k] + v + 128u) & 0x7F80u;
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x ^= a[k];
+    if (x == (uint32_t)iters) *sink = x;  // (x is a multiple of 128, iters is not) keeps the chains alive
+}
+}  // namespace
+
+int tfbs_measure_smem_gbs(tfbs_ctx *ctx, float *gbs)
+{
+    TFBS_REQUIRE(ctx && gbs, "tfbs_measure_smem_gbs: null argument");
+    TFBS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    int rc = tfbs_scratch_reserve(ctx->misc, 64);
+    if (rc) return rc;
+    const int iters = 20000;
+    float best = 0.f;
+    for (int rep = 0; rep < 4; rep++) {
+        tfbs_begin(ctx);
+        smem_probe_kernel<<<ctx->sm_count, 1024, 0, ctx->stream>>>(iters, (unsigned int *)ctx->misc.ptr);
+        tfbs_launched(ctx);
+        rc = tfbs_end(ctx);
+        if (rc) return rc;
+        const double bytes = (double)ctx->sm_count * 1024.0 * 8.0 * iters * 4.0;
+        const float g = (float)(bytes / (ctx->last_ms * 1e-3) / 1e9);
+        if (rep > 0 && g > best) best = g;  // first launch is the warm-up
+    }
+    *gbs = best;
+    return TFBS_OK;
+}
+
 int tfbs_device_free(tfbs_ctx *ctx, void *dev_ptr)
 {
     TFBS_REQUIRE(ctx, "tfbs_device_free: null argument");

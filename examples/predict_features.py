@@ -21,14 +21,14 @@ from discover_tfbs_b200 import candidates, dnashape  # noqa: E402
 from discover_tfbs_b200 import utils as U  # noqa: E402
 
 
-def run(genome_fasta, fg_fasta, motifs, out_prefix, tables=None, kinds=None, ctx=None):
+def run(genome_fasta, fg_fasta, motifs, out_prefix, tables=None, kinds=None, ctx=None, synthetic=False):
     records = dict(U.parse_fasta(genome_fasta))
     cands = candidates.scan_candidates(records, [candidates.exact_match_pwm(m) for m in motifs], 0.0,
                                        names=list(motifs), ctx=ctx)
     candidates.write_bed6(cands, out_prefix + ".bed")
     candidates.write_fasta(cands, out_prefix + ".fasta")
-    if tables is None:
-        tables, kinds = dnashape.synthetic_tables()
+    # real pentamer tables (argument or $TFBS_SHAPE_TABLES); seeded stand-ins only on explicit request
+    tables, kinds = dnashape.resolve_tables(tables, kinds, synthetic=synthetic)
     shapes = U.GenomeShapeSource(records=records, tables=tables, kinds=kinds, ctx=ctx)
     table = U.build_feature_table(out_prefix + ".fasta", fg_fasta, shapes, minhash=True, ctx=ctx)
     return cands, table
@@ -40,9 +40,16 @@ def main():
     ap.add_argument("fg_fasta")
     ap.add_argument("motifs", nargs="+")
     ap.add_argument("--out", default="prediction_features.feather")
+    ap.add_argument("--shape-tables", default=None, help="pentamer table file (dnashape.save_tables format); "
+                                                         "default: $TFBS_SHAPE_TABLES")
+    ap.add_argument("--synthetic-tables", action="store_true", help="demo only: seeded stand-in tables, NOT DNAshapeR's")
     args = ap.parse_args()
     prefix = os.path.splitext(args.out)[0]
-    cands, table = run(args.genome_fasta, args.fg_fasta, args.motifs, prefix)
+    tables = kinds = None
+    if args.shape_tables:
+        tables, kinds = dnashape.load_tables(args.shape_tables)
+    cands, table = run(args.genome_fasta, args.fg_fasta, args.motifs, prefix, tables, kinds,
+                       synthetic=args.synthetic_tables)
     table.reset_index().to_feather(args.out)
     print(f"{len(cands)} candidate sites -> {args.out} ({table.shape[1]} columns)")
 

@@ -85,6 +85,10 @@ int tfbs_timer_stop(tfbs_ctx *ctx, float *ms);
 /* Pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
 int tfbs_host_alloc(void **ptr, int64_t bytes);
 int tfbs_host_free(void *ptr);
+/* Measured shared-memory load bandwidth of this GPU in GB/s (conflict-free LDS.32 streamed by 148 x 32
+ * warps, best of 3): the denominator bench.py uses for the hits kernel's look-up-table roofline, next to
+ * the nominal 148 SM x 128 B/clk x clock. */
+int tfbs_measure_smem_gbs(tfbs_ctx *ctx, float *gbs);
 /* Overwrite a >L2-sized scratch buffer so the next timed launch starts with a cold L2. */
 int tfbs_flush_l2(tfbs_ctx *ctx);
 

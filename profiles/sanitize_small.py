@@ -21,5 +21,14 @@ ctx.shape_sites(enc, tab, [0, 0], [40_000, 40_000], [5, 100], [17, 112], [1, -1]
 ctx.track_sites(np.arange(100, dtype=np.float32), [0, 0], [100, 100], [5, 90], [17, 102], [1, -1], 13)
 c = ["".join(np.random.default_rng(i).choice(list("ACGT"), 12)) for i in range(9)]
 print(ctx.similarity_sums(sm.prepare(c, 6), sm.prepare(c[:4], 6)).shape)
+print("best", ctx.scan_best(enc, lib, [0, 100, 39_990], [50, 3000, 10], with_pos=True)[0].shape)
+out = np.empty(1 << 16, dtype=_lib.HIT_DTYPE)
+e2 = ctx.alloc_seq(seq.size)
+print("host shard", ctx.scan_hits_host_shard(seq, e2, lib, thr, out, owned=30_000, shard_start=7, chunks=3, sort=True).size)
+print("narrow cap", ctx.scan_hits(enc, lib, thr, cap=16, grow=True).size)
+from discover_tfbs_b200.classify import GpuSVC
+g = GpuSVC(np.ones(5), np.zeros(5), np.zeros(5), np.ones(5), "rbf", np.random.default_rng(0).normal(size=(7, 5)),
+           np.ones(7), 0.1, 0.0, ["a", "b"], ctx=ctx)
+print("svc", g.decision_function(np.random.default_rng(1).normal(size=(33, 5))).shape)
 d = ctx.synth_ascii(39, 5, 1000); d.download(); d.close()
 print("sanitize pass done")
