@@ -58,13 +58,18 @@ def parse_args():
     return ap.parse_args()
 
 
+try:
+    _ALL_CPUS = os.sched_getaffinity(0)     # before any NUMA binding of the GPU arm
+except AttributeError:
+    _ALL_CPUS = None
+
+
 def host_threads() -> int:
     """Cores this process may run on.  NOT the OpenMP default: torch.distributed.run exports
     OMP_NUM_THREADS=1, which made the round-1 CPU arm single-threaded at N >= 2."""
-    try:
-        return max(len(os.sched_getaffinity(0)), 1)
-    except AttributeError:
-        return max(os.cpu_count() or 1, 1)
+    if _ALL_CPUS is not None:
+        return max(len(_ALL_CPUS), 1)
+    return max(os.cpu_count() or 1, 1)
 
 
 def workload(args):
@@ -453,6 +458,7 @@ def run_ours(args):
         host_group = dist.new_group(backend="gloo")
     n_gpus = world
 
+    numa_before = _lib.bind_thread_near(local)   # pinned buffers of this rank live next to its GPU
     ctx = _lib.Context(local)  # raises if the library or the GPU is missing: no CPU fallback
     logodds, lens, thr = workload(args)
     halo = int(lens.max()) - 1
@@ -634,7 +640,11 @@ def run_ours(args):
             dist.barrier(group=host_group)   # the other ranks sleep on the host, their GPUs stay idle
         barrier()
 
+    if numa_before is not None:
+        os.sched_setaffinity(0, numa_before)     # the CPU arms below use every core again
     if rank == 0:
+        line["numa"] = {"bound_to_gpu_local_cpus": numa_before is not None,
+                        "gpu_local_cpus": sorted(_lib.device_local_cpus(local) or [])[:64]}
         if not args.no_extras and n_gpus == 1:
             try:
                 line["kernel_rooflines"] = extras(ctx, args, measured_peak_gbs()[0])

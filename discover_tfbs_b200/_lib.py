@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "tfbs_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_host_alloc": (C.c_int, [_pp, _i64]),
     "tfbs_host_free": (C.c_int, [_vp]),
+    "tfbs_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, _i32]),
     "tfbs_host_register": (C.c_int, [_vp, _i64]),
     "tfbs_host_unregister": (C.c_int, [_vp]),
     "tfbs_flush_l2": (C.c_int, [_vp]),
@@ -170,6 +171,45 @@ def device_count() -> int:
     n = C.c_int(0)
     rc = load().tfbs_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def device_local_cpus(device: int):
+    """CPUs on the NUMA node the GPU hangs off (from /sys/bus/pci/devices/<bus id>/local_cpulist),
+    intersected with the CPUs this process may use; None when unknown."""
+    buf = C.create_string_buffer(32)
+    if load().tfbs_device_pci_bus_id(int(device), buf, 32) != 0:
+        return None
+    try:
+        with open(f"/sys/bus/pci/devices/{buf.value.decode().lower()}/local_cpulist") as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
+def bind_thread_near(device: int):
+    """Pin the CALLING thread to the CPUs local to `device` (pinned buffers it allocates and touches then
+    live in that socket's memory).  Returns the previous affinity, or None when nothing was changed
+    (unknown topology, or TFBS_NUMA_BIND=0)."""
+    if os.environ.get("TFBS_NUMA_BIND", "1") == "0":
+        return None
+    cpus = device_local_cpus(device)
+    if not cpus:
+        return None
+    before = os.sched_getaffinity(0)
+    try:
+        os.sched_setaffinity(0, cpus)
+    except OSError:
+        return None
+    return before
 
 
 def as_ascii(seq) -> np.ndarray:

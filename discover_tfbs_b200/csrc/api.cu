@@ -204,6 +204,13 @@ int tfbs_host_alloc(void **ptr, int64_t bytes)
     return TFBS_OK;
 }
 
+int tfbs_device_pci_bus_id(int device, char *buf, int32_t len)
+{
+    TFBS_REQUIRE(buf && len >= 16, "tfbs_device_pci_bus_id: buffer of at least 16 bytes needed");
+    TFBS_CHECK_CUDA(cudaDeviceGetPCIBusId(buf, len, device));
+    return TFBS_OK;
+}
+
 int tfbs_host_register(void *ptr, int64_t bytes)
 {
     TFBS_REQUIRE(ptr && bytes > 0, "tfbs_host_register: bad argument");
@@ -239,26 +246,23 @@ int tfbs_flush_l2(tfbs_ctx *ctx)
 }
 
 namespace {
-// Shared-memory load bandwidth probe: every thread streams conflict-free LDS.32 (lane-consecutive words,
-// the access pattern of the hits kernel's table look-ups) from a 32 KB table; the loaded value feeds the
-// next address so the loads cannot be hoisted, 8 independent chains per thread keep the pipe full.
+// Shared-memory load bandwidth probe: pointer chasing through a 32 KB table of 256 rows x 32 words.
+// Every word of a row holds the byte offset of the next row, so the 32 lanes of a warp always read the
+// 32 consecutive words of one row (conflict-free, one 128 B wavefront per LDS.32 — the access pattern of
+// the hits kernel's table look-ups) and a load costs one LDS + one IADD.  8 independent chains per
+// thread x 32 warps keep far more loads in flight than latency x bandwidth needs.
 __global__ void __launch_bounds__(1024, 1) smem_probe_kernel(int iters, unsigned int *sink)
 {
     __shared__ uint32_t tab[8192];
-    for (int i = threadIdx.x; i < 8192; i += blockDim.x) tab[i] = (uint32_t)(i * 2654435761u) & 0x1F80u;  // multiples of 128 B
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) tab[i] = (uint32_t)((((i >> 5) * 37 + 11) & 255) * 128);
     __syncthreads();
-    const uint32_t lane_off = (threadIdx.x & 31u) * 4u;
+    const uint32_t lane_base = (uint32_t)__cvta_generic_to_shared(tab) + (threadIdx.x & 31u) * 4u;
     uint32_t a[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = (uint32_t)((threadIdx.x >> 5) * 8 + k) * 128u & 0x7F80u;
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab);
+    for (int k = 0; k < 8; k++) a[k] = (uint32_t)(((threadIdx.x >> 5) * 8 + k) & 255) * 128u;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t v;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (a[k] | lane_off)) : "memory");
-            a[k] = (a[k] + v + 128u) & 0x7F80u;
-        }
+        for (int k = 0; k < 8; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a[k]) : "r"(a[k] + lane_base));
     }
     uint32_t x = 0;
 #pragma unroll

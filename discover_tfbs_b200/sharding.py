@@ -109,6 +109,7 @@ class _DeviceWorker:
     """One GPU of the node: context, motif library, shard-sized device buffers, pinned output."""
 
     def __init__(self, device, logodds, lens, shard: Shard, cap: int):
+        _lib.bind_thread_near(device)   # this thread allocates the GPU's pinned output: keep it in the GPU's socket
         self.ctx = _lib.Context(device)
         self.lib = self.ctx.upload_pwms(logodds, lens)
         self.enc = self.ctx.alloc_seq(shard.scanned)
@@ -180,6 +181,7 @@ class MultiGpuScanner:
         def work(i):
             w = self.workers[i]
             sh = w.shard
+            _lib.bind_thread_near(self.devices[i])
             parts[i] = w.ctx.scan_hits_host_shard(genome[sh.start: sh.scan_end], w.enc, w.lib, thresholds, w.hits,
                                                   owned=sh.owned, shard_start=sh.start, chunks=chunks, sort=sort)
 

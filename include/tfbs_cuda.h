@@ -178,6 +178,10 @@ int tfbs_scan_hits_host_shard(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t 
                               const tfbs_pwms *pwms, const float *thr, tfbs_hit *out_host, int64_t cap,
                               int32_t chunks, int32_t sorted, int64_t owned, int64_t shard_start,
                               int64_t *n_hits);
+/* PCI bus id of a device ("0000:1b:00.0"): the host layer reads the device's NUMA-local CPU list from
+ * /sys/bus/pci/devices/<id>/local_cpulist and pins the thread that allocates and fills the pinned
+ * buffers of that GPU to it, so that 8 GPUs' copies do not all cross to one socket's memory. */
+int tfbs_device_pci_bus_id(int device, char *buf, int32_t len);
 /* Page-lock caller-owned host memory in place (cudaHostRegister) so the copies of the end-to-end
  * paths run at full PCIe rate without a staging copy; undo with tfbs_host_unregister. */
 int tfbs_host_register(void *ptr, int64_t bytes);
