@@ -72,12 +72,17 @@ constexpr int kTilePos = kWarps * kSeg;   // 32256 starts per tile (multiple of 
 constexpr int kTileBases = kTilePos + 128;
 constexpr int kTileWords = kTileBases / 16;  // 2024 words  = 8096 B (multiple of 16)
 constexpr int kTileMask = kTileBases / 32;   // 1012 words  = 4048 B (multiple of 16)
-constexpr int kQueueCap = 256;            // candidate queue entries per warp
+constexpr int kQueueCap = 128;            // candidate queue entries per warp
+constexpr int kQueueWarpsA = 13;          // warps whose queue sits before the table (the others: behind it)
+constexpr int kTileBufs = 2;              // tile ring: warps run up to one tile ahead of the slowest warp
 constexpr int kMaxG = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 constexpr uint32_t kPoison = 0x80008000u;        // flag bits of the two 16-bit fields (wide blocks)
 constexpr uint32_t kPoisonNarrow = 0x80808080u;  // flag bits of the four 8-bit fields (narrow blocks)
 constexpr int kLutBudget = 192 * 1024;    // shared memory for one block table (6 x 32 KB)
-constexpr int kSmallBytes = kTileWords * 4 + kTileMask * 4 + kWarps * kQueueCap * 4 + 2 * TFBS_BLOCK_SLOTS * 4 + 32;
+// before the table: tile ring, motif/len of the block, mbarriers + ring bookkeeping; after it: the queues
+constexpr int kBookBytes = kTileBufs * (kTileWords * 4 + kTileMask * 4) + 2 * TFBS_BLOCK_SLOTS * 4 + 64;
+constexpr int kSmallBytes = kBookBytes + kQueueWarpsA * kQueueCap * 4;   // 31 520 B: fits below the first 32 KB boundary
+constexpr int kQueueBytes = (kWarps - kQueueWarpsA) * kQueueCap * 4;       // behind the table
 
 struct HitsParams {
     const uint32_t *packed;
@@ -88,6 +93,7 @@ struct HitsParams {
     const uint32_t *qlut;        // per block [A][256][32] then [B][64][32] packed deficits
     const int32_t *blk_lut_off;  // [n_blocks] offset into qlut (uint32 units)
     const int32_t *blk_AB;       // [n_blocks] (mode << 16) | (A << 8) | B: 4- and 3-column groups of the block
+    uint32_t lut_bytes;          // largest block table of the library: the warp queues sit right behind it
     const uint32_t *kinit;       // [n_blocks][32] initial field values per lane (0x7FFF - Dq or 0x7F - Dq each)
     const int32_t *blk_motif;    // [n_blocks][64] original motif index or -1 (slot = lane + 32 * half)
     const int32_t *lens;         // [M]
@@ -107,15 +113,18 @@ constexpr unsigned long long kCandEmpty = ~0ull;       // list entry to skip
 constexpr int kCandMotifBits = 23;
 
 struct Smem {
-    // small buffers first, then the block table on the next 32 KB boundary of the shared window
+    // tile ring and bookkeeping first, then the block table on the next 32 KB boundary of the shared
+    // window, then the warps' candidate queues
     uint32_t *lut;       // [A][256][32] then [B][64][32]
-    uint32_t *words;     // [kTileWords]
-    uint32_t *mask;      // [kTileMask]
+    uint32_t *words;     // [kTileBufs][kTileWords]
+    uint32_t *mask;      // [kTileBufs][kTileMask]
     uint32_t *queue;     // [kWarps][kQueueCap]
     int32_t *motif;      // [64]
     int32_t *len;        // [64]
-    uint64_t *bar;       // mbarrier
-    uint32_t *item;      // broadcast slot
+    uint64_t *full;      // [kTileBufs] mbarriers: tile landed (and its item slot is valid)
+    uint64_t *tab;       // mbarrier: block table landed
+    uint32_t *item;      // [kTileBufs] work item staged in each buffer
+    uint32_t *done;      // [kTileBufs] warps that have finished with the buffer's current tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,11 +138,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
+    uint32_t spins = 0;
     do {
+        if (++spins == (1u << 24)) __trap();  // a lost arrival must fail the launch, not hang the GPU
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
@@ -420,6 +435,37 @@ __device__ __forceinline__ void scan_segment(const PushCtx &C, const uint32_t *s
     drain_queue(C, qn);
 }
 
+// Offsets of the bookkeeping words inside the dynamic shared window (the tile ring comes first).
+constexpr int kOffMask = kTileBufs * kTileWords * 4;
+constexpr int kOffMotif = kOffMask + kTileBufs * kTileMask * 4;
+constexpr int kOffLen = kOffMotif + TFBS_BLOCK_SLOTS * 4;
+constexpr int kOffFull = kOffLen + TFBS_BLOCK_SLOTS * 4;
+constexpr int kOffTab = kOffFull + kTileBufs * 8;
+constexpr int kOffItem = kOffTab + 8;
+constexpr int kOffDone = kOffItem + kTileBufs * 4;
+static_assert(kOffDone + kTileBufs * 4 <= kBookBytes, "bookkeeping does not fit kBookBytes");
+static_assert(kSmallBytes <= 32768 - 1024, "small buffers must end below the first 32 KB boundary of the shared window");
+static_assert(kOffFull % 8 == 0, "mbarriers must be 8-byte aligned");
+
+// Stage the tile of work item `item` in ring buffer `buf` and publish the item (called by ONE thread).
+// An item past the end carries no data: the barrier is completed by a plain arrival so that the warps
+// waiting for the buffer wake up and see it.
+__device__ __noinline__ void stage_tile(const HitsParams &P, uint8_t *smem_raw, int buf, uint32_t item)
+{
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kOffFull) + buf;
+    reinterpret_cast<uint32_t *>(smem_raw + kOffItem)[buf] = item;
+    if (item < (uint32_t)(P.n_tiles * P.n_blocks)) {
+        const int64_t tile_start = (P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles)) * kTilePos;
+        // order earlier generic-proxy reads of the buffer before the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(full, kTileWords * 4 + kTileMask * 4);
+        tma_load_1d(smem_raw + buf * kTileWords * 4, P.packed + (tile_start >> 4), kTileWords * 4, full);
+        tma_load_1d(smem_raw + kOffMask + buf * kTileMask * 4, P.mask + (tile_start >> 5), kTileMask * 4, full);
+    } else {
+        mbar_arrive(full);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
 {
@@ -429,59 +475,64 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         if (threadIdx.x == 0) *smem_base_probe = raw;
         return;
     }
-    // Shared memory: the small buffers first, then the block table on the next 32 KB boundary of the
-    // shared window so that  (g << 15) | (x << 7) | (lane << 2)  can be OR-ed into the address.
+    // Shared memory: the tile ring and bookkeeping first, then the block table on the next 32 KB boundary
+    // of the shared window so that  (g << 15) | (x << 7) | (lane << 2)  can be OR-ed into the address,
+    // then the candidate queues.
     Smem S;
-    uint8_t *p = smem_raw;
-    S.words = reinterpret_cast<uint32_t *>(p);
-    p += kTileWords * 4;
-    S.mask = reinterpret_cast<uint32_t *>(p);
-    p += kTileMask * 4;
-    S.queue = reinterpret_cast<uint32_t *>(p);
-    p += kWarps * kQueueCap * 4;
-    S.motif = reinterpret_cast<int32_t *>(p);
-    p += TFBS_BLOCK_SLOTS * 4;
-    S.len = reinterpret_cast<int32_t *>(p);
-    p += TFBS_BLOCK_SLOTS * 4;
-    S.bar = reinterpret_cast<uint64_t *>(p);
-    p += 16;
-    S.item = reinterpret_cast<uint32_t *>(p);
+    S.words = reinterpret_cast<uint32_t *>(smem_raw);
+    S.mask = reinterpret_cast<uint32_t *>(smem_raw + kOffMask);
+    S.motif = reinterpret_cast<int32_t *>(smem_raw + kOffMotif);
+    S.len = reinterpret_cast<int32_t *>(smem_raw + kOffLen);
+    S.full = reinterpret_cast<uint64_t *>(smem_raw + kOffFull);
+    S.tab = reinterpret_cast<uint64_t *>(smem_raw + kOffTab);
+    S.item = reinterpret_cast<uint32_t *>(smem_raw + kOffItem);
+    S.done = reinterpret_cast<uint32_t *>(smem_raw + kOffDone);
     const uint32_t lut_addr = (raw + (uint32_t)kSmallBytes + 32767u) & ~32767u;
     S.lut = reinterpret_cast<uint32_t *>(smem_raw + (lut_addr - raw));
+    // queues of warps 0 .. kQueueWarpsA-1 in front of the table, the rest behind the largest table
+    uint32_t *queue_a = reinterpret_cast<uint32_t *>(smem_raw + kBookBytes);
+    uint32_t *queue_b = reinterpret_cast<uint32_t *>(smem_raw + (lut_addr - raw) + P.lut_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t total_items = (uint32_t)(P.n_tiles * P.n_blocks);
+
     if (tid == 0) {
-        mbar_init(S.bar, 1);
-        *S.item = atomicAdd(P.work_counter, 1u);
+        for (int i = 0; i < kTileBufs; i++) {
+            mbar_init(S.full + i, 1);
+            S.done[i] = 0;
+        }
+        mbar_init(S.tab, 1);
+        uint32_t first[kTileBufs];
+        for (int i = 0; i < kTileBufs; i++) first[i] = atomicAdd(P.work_counter, 1u);
+        for (int i = 0; i < kTileBufs; i++) stage_tile(P, smem_raw, i, first[i]);
     }
     __syncthreads();
 
-    const uint32_t total_items = (uint32_t)(P.n_tiles * P.n_blocks);
+    // Every warp walks the same item sequence (round k lives in buffer k % kTileBufs) at its own pace: a
+    // warp that is done with a tile moves on to the next one, already staged, instead of waiting for the
+    // slowest warp at a CTA barrier; the LAST warp to leave a buffer refills it with round k + kTileBufs.
+    // The CTA only synchronises when the motif block (the table) changes.
     int cur_block = -1;
-    uint32_t phase = 0;
+    uint32_t tab_phase = 0;
     uint32_t kinit = kPoison;
     int AB = 1;
-    for (;;) {
-        const uint32_t item = *S.item;  // fetched while the previous item was scanned
+    for (uint32_t k = 0;; k++) {
+        const int buf = (int)(k % kTileBufs);
+        mbar_wait(S.full + buf, (k / kTileBufs) & 1u);
+        const uint32_t item = S.item[buf];
         if (item >= total_items) break;
         const int b = (int)(item / (uint32_t)P.n_tiles);
-        const int64_t tile = P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles);
-        const int64_t tile_start = tile * kTilePos;
-        const bool new_block = b != cur_block;
-        if (new_block) AB = __ldg(P.blk_AB + b);
-        if (tid == 0) {
-            // order the previous item's generic-proxy reads before the async-proxy writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const int chunks = new_block ? 4 * ((AB >> 8) & 255) + (AB & 255) : 0;  // 8 KB pieces of the table
-            mbar_expect_tx(S.bar, kTileWords * 4 + kTileMask * 4 + (uint32_t)chunks * 8192u);
-            tma_load_1d(S.words, P.packed + (tile_start >> 4), kTileWords * 4, S.bar);
-            tma_load_1d(S.mask, P.mask + (tile_start >> 5), kTileMask * 4, S.bar);
-            if (new_block) {
+        const int64_t tile_start = (P.tile0 + (int64_t)(item % (uint32_t)P.n_tiles)) * kTilePos;
+        if (b != cur_block) {
+            __syncthreads();  // every warp is done with the previous block's table (and S.motif / S.len)
+            AB = __ldg(P.blk_AB + b);
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int chunks = 4 * ((AB >> 8) & 255) + (AB & 255);  // 8 KB pieces of the table
+                mbar_expect_tx(S.tab, (uint32_t)chunks * 8192u);
                 const uint32_t *src = P.qlut + __ldg(P.blk_lut_off + b);
-                for (int g = 0; g < chunks; g++) tma_load_1d(S.lut + g * 2048, src + g * 2048, 8192, S.bar);
+                for (int g = 0; g < chunks; g++) tma_load_1d(S.lut + g * 2048, src + g * 2048, 8192, S.tab);
             }
-        }
-        if (new_block) {
             if (tid < TFBS_BLOCK_SLOTS) {
                 const int m = __ldg(P.blk_motif + b * TFBS_BLOCK_SLOTS + tid);
                 S.motif[tid] = m;
@@ -489,17 +540,14 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
             }
             kinit = __ldg(P.kinit + b * 32 + lane);
             cur_block = b;
+            mbar_wait(S.tab, tab_phase);
+            tab_phase ^= 1u;
+            __syncthreads();  // S.motif / S.len visible
         }
-        mbar_wait(S.bar, phase);
-        phase ^= 1u;
-        __syncthreads();  // S.motif / S.len visible; everybody has read S.item
-        // ask for the next item now: the round trip of the atomic hides behind the scan
-        uint32_t next_item = 0;
-        if (tid == 0) next_item = atomicAdd(P.work_counter, 1u);
 
         VerifyCtx V;
-        V.s_words = S.words;
-        V.s_mask = S.mask;
+        V.s_words = S.words + buf * kTileWords;
+        V.s_mask = S.mask + buf * kTileMask;
         V.s_motif = S.motif;
         V.s_len = S.len;
         V.thr = P.thr;
@@ -508,7 +556,7 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         V.owned_end = P.owned_end;
         V.pos_offset = P.pos_offset;
         PushCtx C;
-        C.queue = S.queue + warp * kQueueCap;
+        C.queue = warp < kQueueWarpsA ? queue_a + warp * kQueueCap : queue_b + (warp - kQueueWarpsA) * kQueueCap;
         C.seg_begin = warp * kSeg;
         C.seg_end = C.seg_begin + kSeg;
         C.lane = lane;
@@ -521,14 +569,14 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
         const uint32_t lut_lane_addr = lut_addr + (uint32_t)lane * 4u;
         switch (AB) {
 #define TFBS_CASE(a, b, n) \
-    case ((n << 16) | (a << 8) | b): scan_segment<a, b, n>(C, S.words, lut_lane_addr, kinit); break;
+    case ((n << 16) | (a << 8) | b): scan_segment<a, b, n>(C, V.s_words, lut_lane_addr, kinit); break;
             // every (A, B) tfbs_hits_group_plan can return for block lengths 1..32 ...
             TFBS_CASE(1, 0, 0) TFBS_CASE(2, 0, 0) TFBS_CASE(3, 0, 0) TFBS_CASE(4, 0, 0) TFBS_CASE(5, 0, 0)
             TFBS_CASE(6, 0, 0) TFBS_CASE(5, 2, 0) TFBS_CASE(5, 3, 0) TFBS_CASE(5, 4, 0)
             // ... and the narrow form of those with at most TFBS_NARROW_MAX_GROUPS groups
             TFBS_CASE(1, 0, 1) TFBS_CASE(2, 0, 1) TFBS_CASE(3, 0, 1) TFBS_CASE(4, 0, 1) TFBS_CASE(5, 0, 1)
             TFBS_CASE(6, 0, 1) TFBS_CASE(5, 2, 1) TFBS_CASE(5, 3, 1) TFBS_CASE(5, 4, 1)
-            // ... and the sticky narrow form (flag bits kept by masking, 126 quantisation steps) of
+            // ... and the sticky narrow form (flag bits kept by masking, >= 117 quantisation steps) of
             // those with at least TFBS_STICKY_MIN_GROUPS groups
             TFBS_CASE(5, 0, 2) TFBS_CASE(6, 0, 2) TFBS_CASE(5, 2, 2) TFBS_CASE(5, 3, 2) TFBS_CASE(5, 4, 2)
 #undef TFBS_CASE
@@ -536,8 +584,16 @@ scan_hits_kernel(const HitsParams P, uint32_t *smem_base_probe)
                 if (tid == 0) atomicExch(P.hit_count + 2, (unsigned long long)(0x100000000ull | (unsigned)(AB & 0xFFFF)));
                 break;
         }
-        if (tid == 0) *S.item = next_item;
-        __syncthreads();  // tile buffers are reused by the next item; S.item holds it
+        // leave the buffer; the last warp out refills it with the item kTileBufs rounds ahead
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();  // this warp's reads of the tile precede its departure
+            if (atomicAdd(S.done + buf, 1u) == (uint32_t)kWarps - 1u) {
+                __threadfence_block();
+                S.done[buf] = 0;
+                stage_tile(P, smem_raw, buf, atomicAdd(P.work_counter, 1u));
+            }
+        }
     }
 }
 
@@ -739,7 +795,7 @@ int hits_smem_plan(tfbs_ctx *ctx, size_t lut_bytes, size_t *smem_out)
         cached_base = base;
     }
     const size_t lut_at = ((size_t)cached_base + kSmallBytes + 32767) / 32768 * 32768;
-    *smem_out = lut_at - (size_t)cached_base + lut_bytes;
+    *smem_out = lut_at - (size_t)cached_base + lut_bytes + kQueueBytes;
     if (*smem_out > 227 * 1024) {
         tfbs_set_error("scan_hits: %zu bytes of shared memory needed, 232448 available", *smem_out);
         return TFBS_ERR_INVALID;
@@ -1155,6 +1211,7 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.tile0 = 0;
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
+    P.lut_bytes = (uint32_t)pwms->hits_lut_bytes;
     P.blk_lut_off = pwms->blk_lut_off_dev;
     P.blk_AB = pwms->blk_AB_dev;
     P.kinit = pwms->hq_kinit_dev;
@@ -1278,6 +1335,7 @@ static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t
     P.mask = seq->mask;
     P.n_blocks = pwms->n_blocks;
     P.qlut = pwms->hq_lut_dev;
+    P.lut_bytes = (uint32_t)pwms->hits_lut_bytes;
     P.blk_lut_off = pwms->blk_lut_off_dev;
     P.blk_AB = pwms->blk_AB_dev;
     P.kinit = pwms->hq_kinit_dev;
