@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--genome-mb", type=float, default=100.0, help="Mb scanned per GPU (headline, weak scaling)")
     ap.add_argument("--motifs", type=int, default=800)
     ap.add_argument("--rate", type=float, default=1e-4, help="expected hit rate per position per strand")
-    ap.add_argument("--chunks", type=int, default=8, help="chunks of the pipelined end-to-end pass")
+    ap.add_argument("--chunks", type=int, default=6, help="chunks of the pipelined end-to-end pass")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip every additional record")
     ap.add_argument("--c5", choices=["auto", "on", "off"], default="auto",
                     help="config C5 record (387.5 Mb per GPU + 4 shape tracks); auto = when --gpus is 8")

@@ -438,7 +438,7 @@ class Context:
         return buf[: n.value] if to_host else int(n.value)
 
     def scan_hits_host(self, ascii_host: np.ndarray, seq: "EncodedSeq", pwms: "MotifLibrary", thresholds,
-                       out: np.ndarray, chunks: int = 8, sort: bool = False):
+                       out: np.ndarray, chunks: int = 6, sort: bool = False):
         """Chunk-pipelined end-to-end scan of a host buffer (H2D, encode+scan, D2H overlap).
         `out` is a preallocated HIT_DTYPE array (its size is the capacity); returns out[:n_hits]."""
         thr = np.ascontiguousarray(np.broadcast_to(np.asarray(thresholds, dtype=np.float32), (pwms.M,)))
@@ -449,7 +449,7 @@ class Context:
         return out[: n.value]
 
     def scan_hits_host_shard(self, ascii_host: np.ndarray, seq: "EncodedSeq", pwms: "MotifLibrary", thresholds,
-                             out: np.ndarray, owned: int, shard_start: int, chunks: int = 8, sort: bool = False):
+                             out: np.ndarray, owned: int, shard_start: int, chunks: int = 6, sort: bool = False):
         """scan_hits_host for one shard of a longer sequence (buffer = shard + right halo): only windows
         starting in the first `owned` bases are reported, positions are shifted by `shard_start` — both
         on the device."""

@@ -1310,8 +1310,32 @@ static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t
     const int64_t total_tiles = (n + kTilePos - 1) / kTilePos;
     TFBS_REQUIRE((total_tiles * kTilePos + 128) <= seq->n_words * 16, "tfbs_scan_hits_host: sequence padding too small");
     int64_t C = std::max<int64_t>(1, std::min<int64_t>(chunks, std::min<int64_t>(total_tiles, 64)));
-    const int64_t tiles_per = (total_tiles + C - 1) / C;
-    C = (total_tiles + tiles_per - 1) / tiles_per;
+    // Chunk boundaries (in tiles).  Only two transfers are exposed: the H2D copy of the first chunk and the
+    // D2H copy of the last chunk's hits, so with 4 or more chunks those two are made small (with 6 or more:
+    // 0.15 and 0.12 of a middle chunk, their neighbours 0.5) while the middle chunks keep the launches long.
+    std::vector<int64_t> t_edge(1, 0);
+    {
+        std::vector<double> w((size_t)C, 1.0);
+        if (C >= 6 && total_tiles >= 40 * C) {
+            w[0] = 0.15;
+            w[1] = 0.5;
+            w[(size_t)C - 2] = 0.5;
+            w[(size_t)C - 1] = 0.12;
+        } else if (C >= 4 && total_tiles >= 8 * C) {
+            w[0] = 0.4;
+            w[(size_t)C - 2] = 0.6;
+            w[(size_t)C - 1] = 0.25;
+        }
+        double sum = 0.0, acc = 0.0;
+        for (double v : w) sum += v;
+        for (int64_t c = 0; c < C; c++) {
+            acc += w[(size_t)c];
+            const int64_t e = c == C - 1 ? total_tiles : std::min<int64_t>(total_tiles, (int64_t)std::llround(acc / sum * (double)total_tiles));
+            if (e > t_edge.back()) t_edge.push_back(e);
+        }
+        if (t_edge.back() != total_tiles) t_edge.push_back(total_tiles);
+        C = (int64_t)t_edge.size() - 1;
+    }
     while ((int64_t)ctx->pipe_events.size() < 2 * C + 2) {
         cudaEvent_t ev;
         TFBS_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1355,7 +1379,7 @@ static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t
 
     tfbs_begin(ctx);
     for (int64_t c = 0; c < C; c++) {
-        const int64_t t0 = c * tiles_per, t1 = std::min<int64_t>(total_tiles, t0 + tiles_per);
+        const int64_t t0 = t_edge[(size_t)c], t1 = t_edge[(size_t)c + 1];
         const int64_t b0 = t0 * kTilePos;
         // bytes this chunk's scan can touch: its tiles + the 128-base halo (re-copied by the next chunk)
         const int64_t b1 = std::min<int64_t>(n, t1 * kTilePos + 128);

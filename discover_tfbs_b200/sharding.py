@@ -166,7 +166,7 @@ class MultiGpuScanner:
         if errors:
             raise errors[0]
 
-    def scan(self, genome: np.ndarray, thresholds, sort: bool = True, chunks: int = 8, merge: bool = True):
+    def scan(self, genome: np.ndarray, thresholds, sort: bool = True, chunks: int = 6, merge: bool = True):
         """genome: uint8[n_bases] in host memory (page-locked for full PCIe rate: `_lib.PinnedBuffer` or
         `_lib.RegisteredHost`).  Returns the whole-genome hit array (a fresh array owned by the caller) —
         (motif, pos, strand) order when `sort` — or, with merge=False, the list of per-shard views into
@@ -212,7 +212,7 @@ class MultiGpuScanner:
 
 
 def scan_genome_multi_gpu(genome: np.ndarray, logodds, lens, thresholds, devices=None, cap=1 << 22, sort=True,
-                          chunks: int = 8):
+                          chunks: int = 6):
     """One-shot form of `MultiGpuScanner`: page-locks `genome` in place for the duration of the call,
     scans it on every visible GPU (or `devices`) and returns globally ordered hits."""
     genome = np.ascontiguousarray(genome, dtype=np.uint8)
