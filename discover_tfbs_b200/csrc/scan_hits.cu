@@ -751,6 +751,10 @@ int reserve_candidates(tfbs_ctx *ctx, int64_t cap, unsigned long long *cand_cap)
     int rc = tfbs_scratch_reserve(ctx->cand, (size_t)want * 8);
     if (rc) return rc;
     *cand_cap = ctx->cand.bytes / 8;
+    // TFBS_CAND_CAP=<entries> shrinks the list (tests of the overflow path: what does not fit is verified
+    // inside the scan kernel)
+    const char *env = getenv("TFBS_CAND_CAP");
+    if (env && env[0] >= '0' && env[0] <= '9') *cand_cap = std::min<unsigned long long>(*cand_cap, strtoull(env, nullptr, 10));
     return TFBS_OK;
 }
 

@@ -874,6 +874,35 @@ def test_hits_sharp_motifs_at_tight_thresholds_every_form(ctx, form, monkeypatch
     lib.close()
 
 
+@pytest.mark.parametrize("cand_cap", ["0", "1000", "100000"])
+def test_hits_candidate_list_overflow_falls_back_to_in_kernel_verification(ctx, cand_cap, monkeypatch):
+    """The filter scan appends candidates to a global list that a second kernel verifies; entries that do
+    not fit are verified inside the scan kernel.  With the list squeezed to 0 / 1 000 / 100 000 entries
+    (TFBS_CAND_CAP) the hit set must still equal the oracle's, for sparse and for flood thresholds, through
+    the resident and the pipelined host entry points."""
+    monkeypatch.setenv("TFBS_CAND_CAP", cand_cap)
+    logodds, lens = synth.pwm_library(77, 100, 5, 30)
+    seq = synth.genome(77, 5_000_000, 150_000)
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    thr_sparse = synth.thresholds_for_rate(logodds, lens, rate=2e-3, sample=20_000)
+    thr_flood = thr_sparse.copy()
+    thr_flood[::7] = -1e30
+    for thr, n_use in ((thr_sparse, seq.size), (thr_flood, 20_000)):
+        sub = seq[:n_use]
+        e = enc if n_use == seq.size else ctx.encode(sub)
+        pos, mot, strand, score, cnt = po.search_library(sub, logodds, lens, thr, threads=0)
+        hits = ctx.scan_hits(e, lib, thr, cap=max(cnt, 1) + 16, sort=True)
+        out = np.empty(max(cnt, 1) + 16, dtype=_lib.HIT_DTYPE)
+        host = ctx.scan_hits_host(sub, ctx.alloc_seq(n_use), lib, thr, out, chunks=3, sort=True)
+        for h in (hits, host):
+            gpos = np.where(h["pos"] < 0, ~h["pos"], h["pos"])
+            assert h.size == cnt and np.array_equal(gpos, pos) and np.array_equal(h["motif"], mot)
+            assert np.array_equal((h["pos"] < 0).astype(np.int32), strand) and np.array_equal(h["score"], score)
+    enc.close()
+    lib.close()
+
+
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
     """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
     narrow blocks for the short motifs; the plan follows the thresholds of each call."""
