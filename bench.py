@@ -200,7 +200,6 @@ def cpu_legs(threads):
     oracle/refshim.py) as timed in the build container by profiles/reference_cpu_legs.py (the reference
     cannot travel to the GPU box; its committed JSON is quoted with its provenance)."""
     from discover_tfbs_b200 import dnashape, synth
-    from oracle import shape_oracle
 
     out = {}
     n = 20_000_000

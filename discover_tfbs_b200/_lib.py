@@ -252,6 +252,8 @@ class RegisteredHost:
     """Page-locks a caller-owned NumPy array in place for the lifetime of the object (or `with` block)."""
 
     def __init__(self, array: np.ndarray):
+        if not array.flags["C_CONTIGUOUS"]:
+            raise ValueError("only a C-contiguous array can be page-locked in place")
         self.array = array
         self._ptr = array.ctypes.data
         _check(load().tfbs_host_register(C.c_void_p(self._ptr), int(array.nbytes)))

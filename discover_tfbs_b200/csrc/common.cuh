@@ -84,6 +84,10 @@ struct tfbs_pwms {
     std::vector<double> logodds;     // host copy [M][Lmax][4]
     // exact matrices for re-scoring: double[M][2][TFBS_MAX_MOTIF_LEN][4] (strand 0 fwd, 1 revcomp)
     double *exact = nullptr;
+    // verify pass, fast path: column-PAIR sums double[M][2][16][16] (pair j, index code(2j) + 4 code(2j+1);
+    // a missing second column adds 0.0) and the per-motif rounding guard 2^-46 * sum_j max_b |entry|
+    double *exact2 = nullptr;
+    double *guard_eps = nullptr;
     // dense mode: fixed-point k-mer LUTs (k = 4 for L <= 24, else 3): per motif G groups of 4^k int2
     // (fwd, rev) = rint(group sum * 2^e), per-motif scale 2^-e and -inf detection bound
     int2 *lut = nullptr;

@@ -331,6 +331,30 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
         glen[m] = (K << 16) | (Gd << 8) | L;
         dense_lut_bytes = std::max(dense_lut_bytes, (size_t)Gd * (1 << (2 * K)) * 16 * sizeof(int2));
     }
+    // pair tables + rounding guard of the verify pass (scan_hits.cu: verify_candidates_kernel)
+    std::vector<double> exact2((size_t)M * 2 * 16 * 16, 0.0), guard(M, 0.0);
+    for (int m = 0; m < M; m++) {
+        const int L = lens[m];
+        double A = 0.0;
+        for (int s2 = 0; s2 < 2; s2++) {
+            const double *mat = &exact[((size_t)m * 2 + s2) * TFBS_MAX_MOTIF_LEN * 4];
+            double *dst = &exact2[((size_t)m * 2 + s2) * 256];
+            for (int j = 0; 2 * j < L; j++)
+                for (int x = 0; x < 16; x++) {
+                    const double a = mat[(2 * j) * 4 + (x & 3)];
+                    const double b = 2 * j + 1 < L ? mat[(2 * j + 1) * 4 + (x >> 2)] : 0.0;
+                    dst[j * 16 + x] = a + b;
+                }
+            if (s2 == 0)
+                for (int j = 0; j < L; j++) {
+                    double mx = 0.0;
+                    for (int b = 0; b < 4; b++)
+                        if (std::isfinite(mat[j * 4 + b])) mx = std::max(mx, std::fabs(mat[j * 4 + b]));
+                    A += mx;
+                }
+        }
+        guard[m] = std::ldexp(A, -46);
+    }
     p->dense_lut_bytes = dense_lut_bytes;
     p->Gmax = Gmax;
     p->lut_entries = (int64_t)lut.size();
@@ -357,6 +381,10 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->hq_lut_words = words;
 
     cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->exact2, exact2.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->guard_eps, guard.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(p->exact2, exact2.data(), exact2.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->guard_eps, guard.data(), guard.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&p->lut, lut.size() * sizeof(int2));
     if (e == cudaSuccess) e = cudaMalloc(&p->dense_scale, M * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&p->dense_neg, M * sizeof(int32_t));
@@ -389,6 +417,8 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (!p) return TFBS_OK;
     if (p->ctx) cudaSetDevice(p->ctx->device);
     if (p->exact) cudaFree(p->exact);
+    if (p->exact2) cudaFree(p->exact2);
+    if (p->guard_eps) cudaFree(p->guard_eps);
     if (p->lut) cudaFree(p->lut);
     if (p->dense_scale) cudaFree(p->dense_scale);
     if (p->dense_neg) cudaFree(p->dense_neg);

@@ -99,6 +99,8 @@ struct HitsParams {
     const int32_t *lens;         // [M]
     const float *thr;            // [M]
     const double *exact;         // [M][2][32][4]
+    const double *exact2;        // [M][2][16][16] column-pair sums (verify pass, fast path)
+    const double *guard_eps;     // [M] rounding guard of the fast path
     tfbs_hit *hits;
     unsigned long long *hit_count;   // [0] hits, [1] candidates handed to a verifier, [2] error flag, [4] list length
     unsigned long long cap;
@@ -608,6 +610,10 @@ struct VerifyParams {
     const int32_t *lens;
     const float *thr;
     const double *exact;
+    const double *exact2;
+    const double *guard_eps;
+    double guard_scale;      // 1.0; TFBS_VERIFY_GUARD_SCALE inflates the guard so that tests can push every
+                             // candidate through the oracle-order slow path
     const unsigned long long *cand;
     unsigned long long cand_cap;
     tfbs_hit *hits;
@@ -643,22 +649,43 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const
                 const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
                 const int sh = (int)(gpos & 15) * 2;
                 uint64_t bases = (uint64_t)__funnelshift_r(a0, a1, sh) | ((uint64_t)__funnelshift_r(a1, a2, sh) << 32);
-                const double *mat = P.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
-                // left-to-right double sum (the oracle's order); the loads of 8 columns are issued together
+                // Fast path: sum the column-PAIR table (half the loads; the first pair is exactly the oracle's
+                // first two steps).  The pair order differs from the oracle's left-to-right order by at most
+                // guard_eps[m] >= 2 L u sum|entries| in double, so whenever the double sum lies farther than
+                // that from both ends of the rounding interval of its float, the oracle's sum rounds to the
+                // SAME float — the result is bit-exact by construction.  Otherwise (about one candidate in a
+                // million), and for zero / denormal / power-of-two floats, the oracle's loop is replayed.
+                const double *mat2 = P.exact2 + (size_t)(m * 2 + strand) * 256;
                 double s = 0.0;
-                for (int j0 = 0; j0 < L; j0 += 8) {
-                    double v[8];
+                {
+                    uint64_t b2 = bases;
+                    const int npairs = (L + 1) >> 1;
+                    for (int j0 = 0; j0 < npairs; j0 += 8) {
+                        double v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int j = j0 + k;
-                        v[k] = j < L ? __ldg(mat + j * 4 + (int)((bases >> (2 * k)) & 3u)) : 0.0;
+                        for (int k = 0; k < 8; k++) v[k] = j0 + k < npairs ? __ldg(mat2 + (j0 + k) * 16 + (int)((b2 >> (4 * k)) & 15u)) : 0.0;
+                        b2 >>= 32;
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (j0 + k < npairs) s += v[k];
                     }
-                    bases >>= 16;
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        if (j0 + k < L) s += v[k];
                 }
                 f = (float)s;
+                bool exact_enough = isinf(s);   // a -inf entry gives -inf in any order (+inf / NaN entries are rejected at upload)
+                if (!exact_enough) {
+                    const uint32_t fb = __float_as_uint(f);
+                    const uint32_t ex = fb & 0x7F800000u;
+                    if (ex != 0u && ex != 0x7F800000u && (fb & 0x007FFFFFu) != 0u) {
+                        const double half_ulp = (double)__uint_as_float(ex) * 5.9604644775390625e-8;  // 2^-24 * 2^e
+                        exact_enough = half_ulp - fabs(s - (double)f) > __ldg(P.guard_eps + m) * P.guard_scale;
+                    }
+                }
+                if (!exact_enough) {
+                    const double *mat = P.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+                    s = 0.0;  // left-to-right double sum (the oracle's order)
+                    for (int j = 0; j < L; j++) s += __ldg(mat + j * 4 + (int)((bases >> (2 * j)) & 3u));
+                    f = (float)s;
+                }
                 hit = f >= __ldg(P.thr + m);
             }
         }
@@ -766,6 +793,13 @@ void launch_verify(tfbs_ctx *ctx, const HitsParams &P)
     V.lens = P.lens;
     V.thr = P.thr;
     V.exact = P.exact;
+    V.exact2 = P.exact2;
+    V.guard_eps = P.guard_eps;
+    V.guard_scale = 1.0;
+    if (const char *env = getenv("TFBS_VERIFY_GUARD_SCALE")) {
+        const double g = atof(env);
+        if (g >= 1.0) V.guard_scale = g;
+    }
     V.cand = P.cand;
     V.cand_cap = P.cand_cap;
     V.hits = P.hits;
@@ -1223,6 +1257,8 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     P.lens = pwms->lens_dev;
     P.thr = (const float *)ctx->thr.ptr;
     P.exact = pwms->exact;
+    P.exact2 = pwms->exact2;
+    P.guard_eps = pwms->guard_eps;
     P.hits = (tfbs_hit *)ctx->hits.ptr;
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;
@@ -1371,6 +1407,8 @@ static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t
     P.lens = pwms->lens_dev;
     P.thr = (const float *)ctx->thr.ptr;
     P.exact = pwms->exact;
+    P.exact2 = pwms->exact2;
+    P.guard_eps = pwms->guard_eps;
     P.hits = (tfbs_hit *)ctx->hits.ptr;
     P.hit_count = (unsigned long long *)ctx->hit_count.ptr;
     P.cap = (unsigned long long)cap;

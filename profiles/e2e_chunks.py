@@ -2,7 +2,6 @@
 """End-to-end (host buffers) time of the C4 workload vs the number of pipeline chunks."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from discover_tfbs_b200 import _lib, synth
 ctx = _lib.Context(0)
 n = 100_000_000

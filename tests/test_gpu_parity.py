@@ -903,6 +903,40 @@ def test_hits_candidate_list_overflow_falls_back_to_in_kernel_verification(ctx, 
     lib.close()
 
 
+@pytest.mark.parametrize("guard_scale", ["1", "1e6", "1e30"])
+def test_verify_pass_fast_and_oracle_order_paths_agree(ctx, guard_scale, monkeypatch):
+    """The verify pass sums column-PAIR tables (half the loads) and accepts the result only when the
+    double sum is farther than a rounding guard from the ends of its float's rounding interval;
+    otherwise it replays the oracle's left-to-right loop.  With the guard inflated (1e6: a good share of
+    the candidates, 1e30: all of them take the slow path) hit sets and score BITS must not change — and
+    must equal the oracle's — for soft and sharp motifs, -inf entries and odd / even lengths."""
+    monkeypatch.setenv("TFBS_VERIFY_GUARD_SCALE", guard_scale)
+    rng = np.random.default_rng(5)
+    logodds, lens = synth.pwm_library(55, 60, 5, 31)
+    sharp = np.zeros((20, logodds.shape[1], 4))
+    sl = rng.integers(7, 32, size=20).astype(np.int32)
+    for m in range(20):
+        counts = rng.integers(0, 3, size=(sl[m], 4)).astype(float)
+        counts[np.arange(sl[m]), rng.integers(0, 4, size=sl[m])] += rng.integers(20, 100000)
+        sharp[m, : sl[m]] = po.log_odds(po.normalize(counts, None if m % 3 == 0 else 0.01))
+    logodds = np.concatenate([logodds, sharp])
+    lens = np.concatenate([lens, sl]).astype(np.int32)
+    seq = synth.genome(55, 0, 600_000)
+    finite = np.where(np.isinf(logodds), -30.0, logodds)
+    thr = synth.thresholds_for_rate(finite, lens, rate=3e-3, sample=20_000)
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    hits = ctx.scan_hits(enc, lib, thr, cap=cnt + 16, sort=True)
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    assert cnt > 200_000 and hits.size == cnt and np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
+    assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
+    assert np.array_equal(hits["score"].view(np.uint32), score.view(np.uint32))
+    enc.close()
+    lib.close()
+
+
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
     """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
     narrow blocks for the short motifs; the plan follows the thresholds of each call."""

@@ -626,3 +626,43 @@ def test_sticky_carry_slack_adversarial(form):
         assert cand[0, 0, 0] == 1, (form, trial)
         if trial % 2:
             assert cand[0, 32, 0] == 1, (form, trial)
+
+
+def test_pair_sum_rounding_guard_is_sufficient():
+    """The verify pass of the hits scan sums column PAIRS (half the loads) and keeps the result only when
+    it lies farther than guard = 2^-46 * sum_j max_b |entry| from both ends of its float's rounding
+    interval (csrc/scan_hits.cu: verify_candidates_kernel; tables built in csrc/scan.cu).  Replayed here
+    in NumPy on soft and sharp matrices: whenever the guard accepts, the pair-order float equals the
+    float of the oracle's left-to-right double sum; and it accepts almost always."""
+    from oracle import pssm_oracle as po
+
+    rng = np.random.default_rng(17)
+    accepted = total = 0
+    for trial in range(24):
+        L = int(rng.integers(5, 33))
+        counts = rng.integers(0, 4, size=(L, 4)).astype(float) + 1e-3
+        if trial % 2:
+            counts[np.arange(L), rng.integers(0, 4, size=L)] += rng.integers(10, 100000)
+        mat = po.log_odds(po.normalize(counts, 0.001 if trial % 3 else 0.5))
+        n = 200_000
+        codes = rng.integers(0, 4, size=n + L)
+        # oracle order: left-to-right double sum
+        ref = np.zeros(n)
+        for j in range(L):
+            ref = ref + mat[j, codes[j: j + n]]
+        # pair order
+        fast = np.zeros(n)
+        for j in range(0, L, 2):
+            pair = mat[j, codes[j: j + n]] + (mat[j + 1, codes[j + 1: j + 1 + n]] if j + 1 < L else 0.0)
+            fast = fast + pair
+        f = fast.astype(np.float32)
+        bits = f.view(np.uint32)
+        ex = bits & np.uint32(0x7F800000)
+        ok_form = (ex != 0) & (ex != 0x7F800000) & ((bits & np.uint32(0x007FFFFF)) != 0)
+        half_ulp = ex.view(np.float32).astype(np.float64) * 2.0 ** -24
+        guard = 2.0 ** -46 * np.abs(mat).max(axis=1).sum()
+        accept = ok_form & (half_ulp - np.abs(fast - f.astype(np.float64)) > guard)
+        assert np.array_equal(f[accept].view(np.uint32), ref.astype(np.float32)[accept].view(np.uint32)), trial
+        accepted += int(accept.sum())
+        total += n
+    assert accepted > 0.9999 * total
