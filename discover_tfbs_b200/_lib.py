@@ -33,6 +33,7 @@ _PROTOTYPES = {
     "tfbs_total_kernel_launches": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_last_scan_candidates": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tfbs_last_hits_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tfbs_last_direct_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_timer_start": (C.c_int, [_vp]),
     "tfbs_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tfbs_host_alloc": (C.c_int, [_pp, _i64]),
@@ -73,7 +74,9 @@ _PROTOTYPES = {
     "tfbs_debug_dense_tables": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _vp, _i64]),
     "tfbs_debug_hits_group_plan": (C.c_int, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "tfbs_debug_hits_block_plan": (C.c_int, [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "tfbs_pwms_hits_direct": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
+    "tfbs_debug_direct_lookup": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
 }
 
@@ -165,6 +168,19 @@ def hits_filter_host(logodds, lens, thr, form: int, codes, with_plan: bool = Fal
     if not with_plan:
         return out
     return out, [tuple(int(v) for v in row) for row in plan[: nb.value]], expected[: nb.value].copy()
+
+
+def direct_lookup_host(logodds, lens, thr, codes):
+    """Host run of the hits scan's DIRECT path (test hook, no GPU): (cand uint8[n][M][2], info dict)."""
+    lo = np.ascontiguousarray(logodds, dtype=np.float64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    th = np.ascontiguousarray(thr, dtype=np.float32)
+    cd = np.ascontiguousarray(codes, dtype=np.uint8)
+    M, Lmax = int(lo.shape[0]), int(lo.shape[1])
+    out = np.zeros((cd.size, M, 2), dtype=np.uint8)
+    info = np.zeros(4, dtype=np.int64)
+    _check(load().tfbs_debug_direct_lookup(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), _ptr(cd), int(cd.size), _ptr(out), _ptr(info)))
+    return out, {"motifs": int(info[0]), "max_len": int(info[1]), "keys": int(info[2]), "bitmap_bits": int(info[3])}
 
 
 def device_count() -> int:
@@ -332,6 +348,12 @@ class Context:
         a, b = C.c_float(0), C.c_float(0)
         _check(self._lib.tfbs_last_hits_ms(self._h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
+
+    def last_direct_ms(self) -> float:
+        """Part of the last scan_hits' scan time spent in the direct-path kernel."""
+        a = C.c_float(0)
+        _check(self._lib.tfbs_last_direct_ms(self._h, C.byref(a)))
+        return float(a.value)
 
     def timer_start(self):
         _check(self._lib.tfbs_timer_start(self._h))
@@ -593,6 +615,14 @@ class MotifLibrary(_Handle):
         _check(self.ctx._lib.tfbs_pwms_hits_blocks(self._h, out.ctypes.data_as(C.POINTER(_i32)), out.shape[0],
                                                    C.byref(nb)))
         return [tuple(int(v) for v in row) for row in out[: nb.value]]
+
+
+    def hits_direct(self):
+        """(n_motifs, max_len, keys) of the direct path of the last hits scan: the shortest motifs, looked up
+        in an enumerated 12-mer hash instead of the table filter; (0, 0, 0) when the path was not taken."""
+        n, ln, k = _i32(0), _i32(0), _i64(0)
+        _check(self.ctx._lib.tfbs_pwms_hits_direct(self._h, C.byref(n), C.byref(ln), C.byref(k)))
+        return int(n.value), int(ln.value), int(k.value)
 
 
 class ShapeTables(_Handle):

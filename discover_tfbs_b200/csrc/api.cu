@@ -91,6 +91,7 @@ int tfbs_ctx_create(int device, tfbs_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_mid);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_direct);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evt1);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking);
@@ -124,6 +125,7 @@ int tfbs_ctx_destroy(tfbs_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+    if (ctx->ev_direct) cudaEventDestroy(ctx->ev_direct);
     if (ctx->evt0) cudaEventDestroy(ctx->evt0);
     if (ctx->evt1) cudaEventDestroy(ctx->evt1);
     for (cudaEvent_t ev : ctx->pipe_events) cudaEventDestroy(ev);
@@ -176,6 +178,13 @@ int tfbs_last_hits_ms(tfbs_ctx *ctx, float *scan_ms, float *verify_ms)
     TFBS_REQUIRE(ctx && scan_ms && verify_ms, "tfbs_last_hits_ms: null argument");
     *scan_ms = ctx->last_scan_ms;
     *verify_ms = ctx->last_verify_ms;
+    return TFBS_OK;
+}
+
+int tfbs_last_direct_ms(tfbs_ctx *ctx, float *direct_ms)
+{
+    TFBS_REQUIRE(ctx && direct_ms, "tfbs_last_direct_ms: null argument");
+    *direct_ms = ctx->last_direct_ms;
     return TFBS_OK;
 }
 

@@ -43,7 +43,8 @@ struct tfbs_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // per-call kernel bracket
     cudaEvent_t ev_mid = nullptr;              // between the filter scan and the verify pass of tfbs_scan_hits
-    float last_scan_ms = 0.f, last_verify_ms = 0.f;
+    cudaEvent_t ev_direct = nullptr;           // between the direct-path kernel and the table filter
+    float last_scan_ms = 0.f, last_verify_ms = 0.f, last_direct_ms = 0.f;
     cudaEvent_t evt0 = nullptr, evt1 = nullptr;  // user region timer
     cudaStream_t stream_in = nullptr, stream_out = nullptr;  // copy streams of the pipelined host path
     std::vector<cudaEvent_t> pipe_events;
@@ -109,6 +110,16 @@ struct tfbs_pwms {
     int64_t hq_lut_words = 0;        // total uint32 entries of the packed deficit tables
     uint32_t *hq_lut_dev = nullptr, *hq_kinit_dev = nullptr;
     int32_t *blk_AB_dev = nullptr, *blk_lut_off_dev = nullptr, *blk_motif_dev = nullptr, *lens_dev = nullptr;
+    // direct path of the hits scan: the motifs of at most `direct_len` columns (the tail of `order`) are not
+    // filtered through the shared-memory tables at all when thresholds are sparse: every L-mer that
+    // reaches the threshold is enumerated on the host into a 12-mer hash (global memory) behind a 10-mer
+    // bitmap (128 KB, shared memory); see scan_direct_kernel
+    int32_t n_direct = 0, direct_len = 0;
+    int64_t direct_entries = 0;
+    uint32_t *direct_bitmap_dev = nullptr;
+    uint2 *direct_hash_dev = nullptr;
+    size_t direct_hash_slots_dev = 0;   // slots allocated on the device
+    uint32_t direct_hash_mask = 0, direct_hash_shift = 0;
     std::vector<float> hq_thr;       // thresholds the cached tables were built for
     bool hq_valid = false;
 };

@@ -425,6 +425,8 @@ int tfbs_pwms_destroy(tfbs_pwms *p)
     if (p->lut_off) cudaFree(p->lut_off);
     if (p->glen) cudaFree(p->glen);
     if (p->hq_lut_dev) cudaFree(p->hq_lut_dev);
+    if (p->direct_bitmap_dev) cudaFree(p->direct_bitmap_dev);
+    if (p->direct_hash_dev) cudaFree(p->direct_hash_dev);
     if (p->hq_kinit_dev) cudaFree(p->hq_kinit_dev);
     if (p->blk_AB_dev) cudaFree(p->blk_AB_dev);
     if (p->blk_lut_off_dev) cudaFree(p->blk_lut_off_dev);

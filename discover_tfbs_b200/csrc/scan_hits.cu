@@ -622,6 +622,63 @@ struct VerifyParams {
     int64_t owned_end, pos_offset;
 };
 
+// Exact score of one candidate record with the oracle's arithmetic; true when it is a hit.
+__device__ __forceinline__ bool verify_record(const VerifyParams &P, unsigned long long rec, int &m, int &strand,
+                                              int64_t &gpos, float &f)
+{
+    if (rec == kCandEmpty || (int64_t)(rec >> (kCandMotifBits + 1)) >= P.owned_end) return false;
+    strand = (int)(rec & 1u);
+    m = (int)((rec >> 1) & ((1u << kCandMotifBits) - 1u));
+    gpos = (int64_t)(rec >> (kCandMotifBits + 1));
+    const int L = __ldg(P.lens + m);
+    const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    const uint32_t *mp = P.mask + (gpos >> 5);
+    const uint32_t inv = __funnelshift_r(__ldg(mp), __ldg(mp + 1), (int)(gpos & 31)) & lmask;
+    if (inv) return false;  // a window touching an invalid base is NaN in the oracle, never a hit
+    const uint32_t *wp = P.packed + (gpos >> 4);
+    const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
+    const int sh = (int)(gpos & 15) * 2;
+    const uint64_t bases = (uint64_t)__funnelshift_r(a0, a1, sh) | ((uint64_t)__funnelshift_r(a1, a2, sh) << 32);
+    // Fast path: sum the column-PAIR table (half the loads; the first pair is exactly the oracle's
+    // first two steps).  The pair order differs from the oracle's left-to-right order by at most
+    // guard_eps[m] >= 2 L u sum|entries| in double, so whenever the double sum lies farther than
+    // that from both ends of the rounding interval of its float, the oracle's sum rounds to the
+    // SAME float — the result is bit-exact by construction.  Otherwise (about one candidate in a
+    // million), and for zero / denormal / power-of-two floats, the oracle's loop is replayed.
+    const double *mat2 = P.exact2 + (size_t)(m * 2 + strand) * 256;
+    double s = 0.0;
+    {
+        uint64_t b2 = bases;
+        const int npairs = (L + 1) >> 1;
+        for (int j0 = 0; j0 < npairs; j0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = j0 + k < npairs ? __ldg(mat2 + (j0 + k) * 16 + (int)((b2 >> (4 * k)) & 15u)) : 0.0;
+            b2 >>= 32;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (j0 + k < npairs) s += v[k];
+        }
+    }
+    f = (float)s;
+    bool exact_enough = isinf(s);   // a -inf entry gives -inf in any order (+inf / NaN entries are rejected at upload)
+    if (!exact_enough) {
+        const uint32_t fb = __float_as_uint(f);
+        const uint32_t ex = fb & 0x7F800000u;
+        if (ex != 0u && ex != 0x7F800000u && (fb & 0x007FFFFFu) != 0u) {
+            const double half_ulp = (double)__uint_as_float(ex) * 5.9604644775390625e-8;  // 2^-24 * 2^e
+            exact_enough = half_ulp - fabs(s - (double)f) > __ldg(P.guard_eps + m) * P.guard_scale;
+        }
+    }
+    if (!exact_enough) {
+        const double *mat = P.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
+        s = 0.0;  // left-to-right double sum (the oracle's order)
+        for (int j = 0; j < L; j++) s += __ldg(mat + j * 4 + (int)((bases >> (2 * j)) & 3u));
+        f = (float)s;
+    }
+    return f >= __ldg(P.thr + m);
+}
+
 __global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const VerifyParams P)
 {
     __shared__ uint32_t s_warp_hits[kVerifyThreads / 32];
@@ -631,64 +688,10 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const
     for (unsigned long long base = (unsigned long long)blockIdx.x * kVerifyThreads; base < n;
          base += (unsigned long long)gridDim.x * kVerifyThreads) {
         const unsigned long long i = base + threadIdx.x;
-        bool hit = false;
         int m = 0, strand = 0;
         int64_t gpos = 0;
         float f = 0.f;
-        const unsigned long long rec = i < n ? P.cand[i] : kCandEmpty;
-        if (rec != kCandEmpty && (int64_t)(rec >> (kCandMotifBits + 1)) < P.owned_end) {
-            strand = (int)(rec & 1u);
-            m = (int)((rec >> 1) & ((1u << kCandMotifBits) - 1u));
-            gpos = (int64_t)(rec >> (kCandMotifBits + 1));
-            const int L = __ldg(P.lens + m);
-            const uint32_t lmask = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-            const uint32_t *mp = P.mask + (gpos >> 5);
-            const uint32_t inv = __funnelshift_r(__ldg(mp), __ldg(mp + 1), (int)(gpos & 31)) & lmask;
-            if (!inv) {  // a window touching an invalid base is NaN in the oracle, never a hit
-                const uint32_t *wp = P.packed + (gpos >> 4);
-                const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2);
-                const int sh = (int)(gpos & 15) * 2;
-                uint64_t bases = (uint64_t)__funnelshift_r(a0, a1, sh) | ((uint64_t)__funnelshift_r(a1, a2, sh) << 32);
-                // Fast path: sum the column-PAIR table (half the loads; the first pair is exactly the oracle's
-                // first two steps).  The pair order differs from the oracle's left-to-right order by at most
-                // guard_eps[m] >= 2 L u sum|entries| in double, so whenever the double sum lies farther than
-                // that from both ends of the rounding interval of its float, the oracle's sum rounds to the
-                // SAME float — the result is bit-exact by construction.  Otherwise (about one candidate in a
-                // million), and for zero / denormal / power-of-two floats, the oracle's loop is replayed.
-                const double *mat2 = P.exact2 + (size_t)(m * 2 + strand) * 256;
-                double s = 0.0;
-                {
-                    uint64_t b2 = bases;
-                    const int npairs = (L + 1) >> 1;
-                    for (int j0 = 0; j0 < npairs; j0 += 8) {
-                        double v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; k++) v[k] = j0 + k < npairs ? __ldg(mat2 + (j0 + k) * 16 + (int)((b2 >> (4 * k)) & 15u)) : 0.0;
-                        b2 >>= 32;
-#pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            if (j0 + k < npairs) s += v[k];
-                    }
-                }
-                f = (float)s;
-                bool exact_enough = isinf(s);   // a -inf entry gives -inf in any order (+inf / NaN entries are rejected at upload)
-                if (!exact_enough) {
-                    const uint32_t fb = __float_as_uint(f);
-                    const uint32_t ex = fb & 0x7F800000u;
-                    if (ex != 0u && ex != 0x7F800000u && (fb & 0x007FFFFFu) != 0u) {
-                        const double half_ulp = (double)__uint_as_float(ex) * 5.9604644775390625e-8;  // 2^-24 * 2^e
-                        exact_enough = half_ulp - fabs(s - (double)f) > __ldg(P.guard_eps + m) * P.guard_scale;
-                    }
-                }
-                if (!exact_enough) {
-                    const double *mat = P.exact + ((size_t)(m * 2 + strand) * TFBS_MAX_MOTIF_LEN) * 4;
-                    s = 0.0;  // left-to-right double sum (the oracle's order)
-                    for (int j = 0; j < L; j++) s += __ldg(mat + j * 4 + (int)((bases >> (2 * j)) & 3u));
-                    f = (float)s;
-                }
-                hit = f >= __ldg(P.thr + m);
-            }
-        }
+        const bool hit = verify_record(P, i < n ? P.cand[i] : kCandEmpty, m, strand, gpos, f);
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
         if (lane == 0) s_warp_hits[warp] = (uint32_t)__popc(ballot);
         __syncthreads();
@@ -706,6 +709,107 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const
         if (hit)
             store_hit(P.hits, s_base + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u)), P.cap, gpos + P.pos_offset, strand, m, f);
         __syncthreads();  // s_warp_hits / s_base are rewritten by the next batch
+    }
+}
+
+// ---- direct path: motifs of at most 12 columns at sparse thresholds -----------------------------------
+// For a short motif the set of L-mers that reach the threshold is small (rate x 4^L: 1 678 twelve-mers at a
+// 1e-4 hit rate) and is enumerated on the host, exactly (plan_direct).  Every enumerated L-mer, extended to
+// 12 bases with all possible suffixes, is a key of a hash table in global memory (value = motif, strand);
+// a bitmap over the first 10 bases (2^20 bits = 128 KB, shared memory) screens the positions.  Lanes are
+// POSITIONS here: a thread slices its 12-mer out of the packed words, tests the bitmap (a random, mostly
+// conflict-free 4-byte shared load for 32 positions instead of G warp-wide table loads per base for 128
+// fields) and only on a set bit walks the hash chain.  Matches are candidates like any other: they go to
+// the candidate list and the verify pass re-scores them (they are all hits up to windows with invalid
+// bases).  Takes the three or four cheapest blocks — 8 of 67 table loads per base on the 800-PWM library —
+// off the shared-memory pipe.
+constexpr int kDirectThreads = 1024;
+constexpr int kDirectPerThread = 8;          // CONSECUTIVE positions per thread: two packed words cover their 19 bases
+constexpr int kDirectQueue = 2048;
+constexpr int kDirectBitmapWords = 1 << 15;  // 2^20 bits
+struct DirectParams {
+    const uint32_t *packed;
+    int64_t pos0, pos1;          // window starts scanned by this launch
+    const uint32_t *bitmap;      // [2^15] words: first 10 bases
+    const uint2 *hash;           // {12-mer key, ((motif << 1) | strand) + 1}; .y == 0: empty slot
+    uint32_t hash_mask, hash_shift;
+    VerifyParams V;              // candidate list / hits / counters (V.cand is written here)
+    unsigned long long *cand;
+};
+
+__device__ __noinline__ void direct_overflow(const DirectParams &P, unsigned long long rec)
+{
+    // candidate list full (flood thresholds never take the direct path, so this is a safety net): verify here
+    int m, strand;
+    int64_t gpos;
+    float f;
+    if (verify_record(P.V, rec, m, strand, gpos, f))
+        store_hit(P.V.hits, atomicAdd(P.V.hit_count, 1ull), P.V.cap, gpos + P.V.pos_offset, strand, m, f);
+}
+
+__global__ void __launch_bounds__(kDirectThreads, 1) scan_direct_kernel(const DirectParams P)
+{
+    extern __shared__ uint32_t s_direct[];
+    uint32_t *s_bm = s_direct;                                                                      // [2^15]
+    unsigned long long *s_q = reinterpret_cast<unsigned long long *>(s_direct + kDirectBitmapWords);  // [kDirectQueue]
+    __shared__ uint32_t s_qn;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kDirectBitmapWords / 4; i += kDirectThreads)
+        reinterpret_cast<uint4 *>(s_bm)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bitmap) + i);
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+    constexpr int kSpan = kDirectThreads * kDirectPerThread;
+    static_assert(kDirectPerThread == 8, "a thread's 8 positions + 11 bases must fit two packed words");
+    const int64_t base0 = P.pos0 & ~(int64_t)7;   // spans start on a multiple of 8 bases (pos0 is a tile boundary anyway)
+    const int64_t n_spans = (P.pos1 - base0 + kSpan - 1) / kSpan;
+    for (int64_t span = blockIdx.x; span < n_spans; span += gridDim.x) {
+        const int64_t p0 = base0 + span * kSpan + (int64_t)tid * kDirectPerThread;   // multiple of 8
+        if (p0 < P.pos1) {
+            const uint32_t *wp = P.packed + (p0 >> 4);
+            const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1);
+            const uint64_t w = (((uint64_t)a1 << 32) | a0) >> ((int)(p0 & 15) * 2);   // bases p0 .. p0+23 (or +31)
+            uint32_t pass = 0;
+#pragma unroll
+            for (int r = 0; r < kDirectPerThread; r++) {
+                const uint32_t k10 = (uint32_t)(w >> (2 * r)) & 0xFFFFFu;
+                pass |= ((s_bm[k10 >> 5] >> (k10 & 31u)) & 1u) << r;
+            }
+            while (pass) {
+                const int r = __ffs(pass) - 1;
+                pass &= pass - 1u;
+                const int64_t p = p0 + r;
+                if (p < P.pos0 || p >= P.pos1) continue;
+                const uint32_t key = (uint32_t)(w >> (2 * r)) & 0xFFFFFFu;  // 12 bases
+                for (uint32_t i = (key * 0x9E3779B1u) >> P.hash_shift;; i = (i + 1u) & P.hash_mask) {
+                    const uint2 e = __ldg(P.hash + i);
+                    if (e.y == 0u) break;
+                    if (e.x == key) {
+                        const unsigned long long rec = ((unsigned long long)p << (kCandMotifBits + 1)) | (unsigned long long)(e.y - 1u);
+                        const uint32_t slot = atomicAdd(&s_qn, 1u);
+                        if (slot < (uint32_t)kDirectQueue) s_q[slot] = rec;
+                        else direct_overflow(P, rec);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t qn = min(s_qn, (uint32_t)kDirectQueue);
+        if (qn >= (uint32_t)kDirectQueue / 2 || span + gridDim.x >= n_spans) {  // CTA-uniform
+            if (tid == 0 && qn) {
+                s_base = atomicAdd(P.V.hit_count + kCandCountSlot, (unsigned long long)qn);
+                atomicAdd(P.V.hit_count + 1, (unsigned long long)qn);
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < qn; i += kDirectThreads) {
+                const unsigned long long slot = s_base + i;
+                if (slot < P.V.cand_cap) P.cand[slot] = s_q[i];
+                else direct_overflow(P, s_q[i]);
+            }
+            __syncthreads();
+            if (tid == 0) s_qn = 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -785,9 +889,8 @@ int reserve_candidates(tfbs_ctx *ctx, int64_t cap, unsigned long long *cand_cap)
     return TFBS_OK;
 }
 
-void launch_verify(tfbs_ctx *ctx, const HitsParams &P)
+void fill_verify_params(VerifyParams &V, const HitsParams &P)
 {
-    VerifyParams V;
     V.packed = P.packed;
     V.mask = P.mask;
     V.lens = P.lens;
@@ -807,6 +910,31 @@ void launch_verify(tfbs_ctx *ctx, const HitsParams &P)
     V.cap = P.cap;
     V.owned_end = P.owned_end;
     V.pos_offset = P.pos_offset;
+}
+
+void launch_direct(tfbs_ctx *ctx, const tfbs_pwms *pw, const HitsParams &P, int64_t pos0, int64_t pos1)
+{
+    if (pw->n_direct <= 0 || pos1 <= pos0) return;
+    DirectParams D;
+    D.packed = P.packed;
+    D.pos0 = pos0;
+    D.pos1 = pos1;
+    D.bitmap = pw->direct_bitmap_dev;
+    D.hash = pw->direct_hash_dev;
+    D.hash_mask = pw->direct_hash_mask;
+    D.hash_shift = pw->direct_hash_shift;
+    fill_verify_params(D.V, P);
+    D.cand = P.cand;
+    const size_t smem = (size_t)kDirectBitmapWords * 4 + (size_t)kDirectQueue * 8;
+    cudaFuncSetAttribute(scan_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_direct_kernel<<<(unsigned)ctx->sm_count, kDirectThreads, smem, ctx->stream>>>(D);
+    tfbs_launched(ctx);
+}
+
+void launch_verify(tfbs_ctx *ctx, const HitsParams &P)
+{
+    VerifyParams V;
+    fill_verify_params(V, P);
     verify_candidates_kernel<<<(unsigned)(ctx->sm_count * 8), kVerifyThreads, 0, ctx->stream>>>(V);
     tfbs_launched(ctx);
 }
@@ -1123,12 +1251,156 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int cou
     return kWide;
 }
 
+// ---- direct path planning (host) ------------------------------------------------------------------------
+constexpr int kDirectKeyBases = 12;          // hash key: 12 bases = 24 bits
+constexpr int kDirectPrefixBases = 10;       // bitmap: first 10 bases
+constexpr size_t kDirectMaxEntries = (size_t)2 << 20;   // 2 Mi keys -> 4 Mi slots = 32 MB of hash
+constexpr double kDirectMaxDensity = 0.35;   // bitmap bits set: beyond this the screen stops screening
+
+// Every L-mer whose oracle score reaches the threshold: depth-first over the columns with the
+// best-possible-remainder bound (slack as in fill_block), partial sums in the oracle's left-to-right order
+// so that the leaf test (float)sum >= t IS the oracle's test.  Each hit L-mer becomes 4^(12-L) keys.
+// Returns false when `entries` would exceed `cap` (the caller then gives up the direct path).
+// With entries == nullptr only the keys are counted (*count).
+static bool enumerate_direct_field(const double *mat, int L, float t, uint32_t value, std::vector<uint2> *entries, size_t cap,
+                                   size_t *count)
+{
+    *count = 0;
+    if (std::isnan(t)) return true;
+    double sufbest[TFBS_MAX_MOTIF_LEN + 1];
+    sufbest[L] = 0.0;
+    for (int j = L - 1; j >= 0; j--) {
+        double mx = -INFINITY;
+        for (int b = 0; b < 4; b++) mx = std::max(mx, mat[j * 4 + b]);
+        sufbest[j] = sufbest[j + 1] + mx;
+    }
+    if (!std::isfinite(sufbest[0])) return true;  // a column of -inf only: no window can score
+    const double need = std::isinf(t) ? (double)t
+                                      : (double)t - (std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(sufbest[0]) * 1e-12 + 1e-9);
+    int code[TFBS_MAX_MOTIF_LEN];
+    double part[TFBS_MAX_MOTIF_LEN + 1];
+    part[0] = 0.0;
+    int j = 0;
+    code[0] = 0;
+    const uint32_t n_suffix = 1u << (2 * (kDirectKeyBases - L));
+    for (;;) {
+        if (code[j] == 4) {
+            if (--j < 0) break;
+            code[j]++;
+            continue;
+        }
+        const double sc = part[j] + mat[j * 4 + code[j]];
+        if (!(sc + sufbest[j + 1] >= need)) {
+            code[j]++;
+            continue;
+        }
+        if (j == L - 1) {
+            if ((float)sc >= t) {
+                uint32_t key = 0;
+                for (int i = 0; i < L; i++) key |= (uint32_t)code[i] << (2 * i);
+                *count += n_suffix;
+                if (*count > cap) return false;
+                if (entries)
+                    for (uint32_t u = 0; u < n_suffix; u++) entries->push_back(make_uint2(key | (u << (2 * L)), value));
+            }
+            code[j]++;
+        } else {
+            part[j + 1] = sc;
+            code[++j] = 0;
+        }
+    }
+    return true;
+}
+
+// Decide which motifs (a tail of the length-sorted order: the shortest) take the direct path for this
+// threshold vector and build their bitmap + hash.  Returns the number of direct motifs (0: none).
+// TFBS_HITS_DIRECT=0 switches the path off; forcing a block form (TFBS_HITS_NARROW / _STICKY, A/B runs and
+// tests of the table filter) does too.
+static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32_t> &bitmap, std::vector<uint2> &hash,
+                       uint32_t *hash_shift, int *direct_len, int64_t *n_entries)
+{
+    if (env_int("TFBS_HITS_DIRECT") == 0 || env_int("TFBS_HITS_NARROW") >= 0 || env_int("TFBS_HITS_STICKY") >= 0) return 0;
+    const int M = pw->M;
+    for (int Ld : {12, 10, 8}) {
+        int n = 0;
+        while (n < M && pw->lens_desc[M - 1 - n] <= Ld) n++;
+        // worth a separate pass only if it takes at least one whole table block off the scan
+        if (n < 32) continue;
+        // count first (cheap: no suffix expansion), build only what fits; both passes run on the host's cores
+        cpu_set_t set;
+        const unsigned cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
+        unsigned T = std::max(1u, std::min<unsigned>(std::min(cores, 16u), (unsigned)n));
+        const int forced = env_int("TFBS_PLAN_THREADS");
+        if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
+        std::vector<std::vector<uint2>> part(T);
+        std::vector<size_t> counted(T, 0);
+        std::atomic<bool> ok{true};
+        auto pass = [&](bool build) {
+            std::atomic<int> next{M - n};
+            auto worker = [&](unsigned t) {
+                for (int i = next.fetch_add(1); i < M && ok.load(); i = next.fetch_add(1)) {
+                    const int m = pw->order[i];
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        size_t c = 0;
+                        if (!enumerate_direct_field(pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4,
+                                                    pw->lens[m], thr[m], (((uint32_t)m << 1) | (uint32_t)s2) + 1u,
+                                                    build ? &part[t] : nullptr, kDirectMaxEntries, &c))
+                            ok.store(false);
+                        counted[t] += c;
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < T; t++) pool.emplace_back(worker, t);
+            worker(0);
+            for (auto &th : pool) th.join();
+        };
+        pass(false);
+        size_t total = 0;
+        for (size_t c : counted) total += c;
+        if (!ok.load() || total > kDirectMaxEntries) continue;
+        pass(true);
+        std::vector<uint2> entries;
+        entries.reserve(total);
+        for (auto &v : part) entries.insert(entries.end(), v.begin(), v.end());
+        bitmap.assign(kDirectBitmapWords, 0u);
+        const uint32_t pmask = (1u << (2 * kDirectPrefixBases)) - 1u;
+        for (const uint2 &e : entries) bitmap[(e.x & pmask) >> 5] |= 1u << (e.x & 31u);
+        size_t bits_set = 0;
+        for (uint32_t w : bitmap) bits_set += (size_t)__builtin_popcount(w);
+        if ((double)bits_set > kDirectMaxDensity * (double)(1u << (2 * kDirectPrefixBases))) continue;
+        uint32_t bits = 10;
+        while (((size_t)1 << bits) < 2 * entries.size() + 16) bits++;
+        hash.assign((size_t)1 << bits, make_uint2(0u, 0u));
+        const uint32_t mask = (uint32_t)(((size_t)1 << bits) - 1);
+        for (const uint2 &e : entries) {
+            uint32_t i = (e.x * 0x9E3779B1u) >> (32 - bits);
+            while (hash[i].y != 0u) i = (i + 1u) & mask;
+            hash[i] = e;
+        }
+        *hash_shift = 32 - bits;
+        *direct_len = Ld;
+        *n_entries = (int64_t)entries.size();
+        return n;
+    }
+    return 0;
+}
+
 // Plan the blocks and quantise their tables for a threshold vector; cached per threshold vector.
 int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
 {
-    const int M = pw->M;
-    if (pw->hq_valid && pw->hq_thr.size() == (size_t)M && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * M) == 0)
+    const int Mall = pw->M;
+    if (pw->hq_valid && pw->hq_thr.size() == (size_t)Mall && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * Mall) == 0)
         return TFBS_OK;
+    // the shortest motifs may bypass the table filter altogether (direct path); the blocks below are cut
+    // from the remaining M motifs (the head of the length-sorted order)
+    std::vector<uint32_t> d_bitmap;
+    std::vector<uint2> d_hash;
+    uint32_t d_shift = 0;
+    int d_len = 0;
+    int64_t d_entries = 0;
+    const int n_direct = plan_direct(pw, thr, d_bitmap, d_hash, &d_shift, &d_len, &d_entries);
+    const int M = Mall - n_direct;
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
     int64_t words = 0;   // table words of the blocks emitted so far
@@ -1211,7 +1483,28 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;
     }
-    pw->hq_thr.assign(thr, thr + M);
+    pw->n_direct = n_direct;
+    pw->direct_len = d_len;
+    pw->direct_entries = d_entries;
+    if (n_direct > 0) {
+        if (!pw->direct_bitmap_dev) e = cudaMalloc(&pw->direct_bitmap_dev, (size_t)kDirectBitmapWords * 4);
+        if (e == cudaSuccess && pw->direct_hash_slots_dev < d_hash.size()) {
+            if (pw->direct_hash_dev) cudaFree(pw->direct_hash_dev);
+            pw->direct_hash_dev = nullptr;
+            pw->direct_hash_slots_dev = 0;
+            e = cudaMalloc(&pw->direct_hash_dev, d_hash.size() * sizeof(uint2));
+            if (e == cudaSuccess) pw->direct_hash_slots_dev = d_hash.size();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(pw->direct_bitmap_dev, d_bitmap.data(), (size_t)kDirectBitmapWords * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->direct_hash_dev, d_hash.data(), d_hash.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            tfbs_set_error("tfbs_scan_hits: uploading the direct-path tables failed: %s", cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? TFBS_ERR_NOMEM : TFBS_ERR_CUDA;
+        }
+        pw->direct_hash_mask = (uint32_t)(d_hash.size() - 1);
+        pw->direct_hash_shift = d_shift;
+    }
+    pw->hq_thr.assign(thr, thr + Mall);
     pw->hq_valid = true;
     return TFBS_OK;
 }
@@ -1274,13 +1567,18 @@ extern "C" int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwm
     TFBS_CHECK_CUDA(cudaFuncSetAttribute(scan_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
     tfbs_begin(ctx);
-    scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
-    tfbs_launched(ctx);
+    launch_direct(ctx, pwms, P, 0, n);   // the shortest motifs, when their hit L-mers are few enough to enumerate
+    cudaEventRecord(ctx->ev_direct, ctx->stream);
+    if (grid > 0) {
+        scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
+        tfbs_launched(ctx);
+    }
     cudaEventRecord(ctx->ev_mid, ctx->stream);
     launch_verify(ctx, P);
     rc = tfbs_end(ctx);
     if (rc) return rc;
     cudaEventElapsedTime(&ctx->last_scan_ms, ctx->ev0, ctx->ev_mid);
+    cudaEventElapsedTime(&ctx->last_direct_ms, ctx->ev0, ctx->ev_direct);
     cudaEventElapsedTime(&ctx->last_verify_ms, ctx->ev_mid, ctx->ev1);
     unsigned long long cnt2[3] = {0, 0, 0};
     TFBS_CHECK_CUDA(cudaMemcpyAsync(cnt2, ctx->hit_count.ptr, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1437,8 +1735,11 @@ static int scan_hits_host_impl(tfbs_ctx *ctx, const uint8_t *ascii_host, int64_t
         // work counter (offset 24) and candidate-list length (offset 32) restart for every chunk
         TFBS_CHECK_CUDA(cudaMemsetAsync(P.work_counter, 0, 16, ctx->stream));
         const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count, P.n_tiles * P.n_blocks);
-        scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
-        tfbs_launched(ctx);
+        launch_direct(ctx, pwms, P, b0, std::min<int64_t>(n, t1 * kTilePos));
+        if (grid > 0) {
+            scan_hits_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(P, nullptr);
+            tfbs_launched(ctx);
+        }
         launch_verify(ctx, P);
         TFBS_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned_counts + c, ctx->hit_count.ptr, sizeof(unsigned long long),
                                         cudaMemcpyDeviceToHost, ctx->stream));
@@ -1593,6 +1894,58 @@ extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens
     return TFBS_OK;
 }
 
+// Test hook (host only, no CUDA): plan the DIRECT path for a library and threshold vector and look a
+// sequence up in its bitmap + hash exactly as scan_direct_kernel does.  codes = n bases as 2-bit codes, one
+// per byte (bases past the end count as 0, like the padded device buffer); cand = uint8[n][M][2], set to 1
+// where the 12-mer at position p is a key of (motif m, strand s).  info = {motifs on the direct path, their
+// longest length, keys in the hash, bitmap bits set}.
+extern "C" int tfbs_debug_direct_lookup(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                        const float *thr, const uint8_t *codes, int64_t n, uint8_t *cand, int64_t info[4])
+{
+    if (!logodds || !lens || !thr || !codes || !cand || !info || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1)
+        return TFBS_ERR_INVALID;
+    tfbs_pwms pw;  // host fields only
+    pw.M = M;
+    pw.Lmax = Lmax;
+    pw.lens.assign(lens, lens + M);
+    pw.exact_host.assign((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
+    for (int m = 0; m < M; m++) {
+        if (lens[m] < 1 || lens[m] > Lmax) return TFBS_ERR_INVALID;
+        tfbs_fill_exact(logodds, Lmax, m, lens[m], &pw.exact_host[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4],
+                        &pw.exact_host[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4]);
+    }
+    pw.order.resize(M);
+    for (int m = 0; m < M; m++) pw.order[m] = m;
+    std::stable_sort(pw.order.begin(), pw.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    pw.lens_desc.resize(M);
+    for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
+    std::vector<uint32_t> bitmap;
+    std::vector<uint2> hash;
+    uint32_t shift = 0;
+    int dlen = 0;
+    int64_t entries = 0;
+    const int nd = plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries);
+    memset(cand, 0, (size_t)n * M * 2);
+    info[0] = nd;
+    info[1] = dlen;
+    info[2] = entries;
+    info[3] = 0;
+    if (nd == 0) return TFBS_OK;
+    for (uint32_t w : bitmap) info[3] += __builtin_popcount(w);
+    const uint32_t mask = (uint32_t)(hash.size() - 1);
+    for (int64_t p = 0; p < n; p++) {
+        uint32_t key = 0;
+        for (int i = 0; i < kDirectKeyBases; i++) key |= (uint32_t)(p + i < n ? (codes[p + i] & 3u) : 0u) << (2 * i);
+        const uint32_t k10 = key & 0xFFFFFu;
+        if (!((bitmap[k10 >> 5] >> (k10 & 31u)) & 1u)) continue;
+        for (uint32_t i = (key * 0x9E3779B1u) >> shift;; i = (i + 1u) & mask) {
+            if (hash[i].y == 0u) break;
+            if (hash[i].x == key) cand[((size_t)p * M + ((hash[i].y - 1u) >> 1)) * 2 + ((hash[i].y - 1u) & 1u)] = 1;
+        }
+    }
+    return TFBS_OK;
+}
+
 // Test hook (host only): the blocks a library of the given motif lengths (any order) is cut into when
 // every block of at most `narrow_max_groups` column groups is taken in narrow form (the scan itself
 // decides per block from the thresholds, see tfbs_pwms_hits_blocks).
@@ -1630,6 +1983,18 @@ extern "C" int tfbs_pwms_hits_blocks(const tfbs_pwms *pwms, int32_t *out, int32_
         out[4 * b + 2] = pwms->blk_narrow[b];
         out[4 * b + 3] = pwms->blk_count[b];
     }
+    return TFBS_OK;
+}
+
+// The direct path of the last scan of this library: how many motifs (the shortest ones) bypassed the table
+// filter, the longest of them, and how many 12-mer keys their hash holds; all 0 when the path was not taken.
+extern "C" int tfbs_pwms_hits_direct(const tfbs_pwms *pwms, int32_t *n_motifs, int32_t *max_len, int64_t *keys)
+{
+    if (!pwms || !n_motifs || !max_len || !keys) return TFBS_ERR_INVALID;
+    const bool on = pwms->hq_valid && pwms->n_direct > 0;
+    *n_motifs = on ? pwms->n_direct : 0;
+    *max_len = on ? pwms->direct_len : 0;
+    *keys = on ? pwms->direct_entries : 0;
     return TFBS_OK;
 }
 

@@ -78,6 +78,8 @@ int tfbs_last_scan_candidates(tfbs_ctx *ctx, int64_t *n);
 /* Device time of the two kernels of the most recent tfbs_scan_hits: the filter scan and the exact
  * verify pass over its candidate list (bench.py reports a roofline for each). */
 int tfbs_last_hits_ms(tfbs_ctx *ctx, float *scan_ms, float *verify_ms);
+/* Of that scan time, the part spent in the direct-path kernel (0 when the path was not taken). */
+int tfbs_last_direct_ms(tfbs_ctx *ctx, float *direct_ms);
 /* Region timer: CUDA events recorded on the context's stream; stop synchronises and returns the
  * elapsed device time of everything enqueued in between (kernels and async copies). */
 int tfbs_timer_start(tfbs_ctx *ctx);
@@ -192,6 +194,14 @@ int tfbs_host_unregister(void *ptr);
  * holds (out may be NULL to query *n_blocks).  Diagnostics for bench.py's shared-memory roofline. */
 int tfbs_pwms_hits_blocks(const tfbs_pwms *pwms, int32_t *out, int32_t cap, int32_t *n_blocks);
 
+/* The DIRECT path of the last hits scan: at sparse thresholds the motifs of at most 12 columns are not
+ * filtered through the shared-memory tables; every L-mer that reaches the threshold is enumerated on the
+ * host into a 12-mer hash behind a 10-mer bitmap and the scan looks positions up in it.  n_motifs = how
+ * many motifs took it (the blocks of tfbs_pwms_hits_blocks cover the rest), max_len = the longest of them,
+ * keys = 12-mers in the hash; all 0 when the path was not taken (dense thresholds, very short motifs, or
+ * TFBS_HITS_DIRECT=0). */
+int tfbs_pwms_hits_direct(const tfbs_pwms *pwms, int32_t *n_motifs, int32_t *max_len, int64_t *keys);
+
 /* ---- (3) DNA-shape pentamer lookup -----------------------------------------------------
  * Replaces DNAshapeR getShape()/getDNAShape() (get_DNA_shapes.R:23-25,
  * create_bkg_seqs.py:365-366) and the text parsing + window slicing the reference does on its
@@ -290,6 +300,13 @@ int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_ma
 int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
                            const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand,
                            int32_t *plan, double *expected, int32_t *n_blocks);
+
+/* The DIRECT path of the hits scan planned and looked up on the host (no CUDA): codes = n bases as 2-bit
+ * codes, one per byte; cand = uint8[n][M][2], 1 where the 12-mer at p is an enumerated key of (motif,
+ * strand) — which, for a window of valid bases inside the sequence, is exactly "the oracle reports a hit".
+ * info = {motifs on the direct path, their longest length, keys, bitmap bits set}. */
+int tfbs_debug_direct_lookup(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                             const float *thr, const uint8_t *codes, int64_t n, uint8_t *cand, int64_t info[4]);
 
 #ifdef __cplusplus
 }

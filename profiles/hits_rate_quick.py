@@ -26,5 +26,5 @@ for narrow, env in MODES.items():
             ms.append(ctx.last_kernel_ms())
         plan = lib.hits_blocks()
         print(f"{narrow} rate {rate}: {min(ms):.2f} ms, hits {h}, candidates {ctx.last_scan_candidates()}, "
-              f"blocks {len(plan)} (narrow groups {sorted(b[0] + b[1] for b in plan if b[2] == 1)}, sticky groups {sorted(b[0] + b[1] for b in plan if b[2] == 2)})", flush=True)
+              f"direct {lib.hits_direct()}, blocks {len(plan)} (narrow groups {sorted(b[0] + b[1] for b in plan if b[2] == 1)}, sticky groups {sorted(b[0] + b[1] for b in plan if b[2] == 2)})", flush=True)
     lib.close()

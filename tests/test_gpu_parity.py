@@ -795,22 +795,23 @@ def test_hits_narrow_blocks_equal_wide_blocks_and_oracle(ctx, kind, monkeypatch)
         lib = ctx.upload_pwms(logodds, lens)
         assert lib.hits_blocks() == []
         hits = ctx.scan_hits(enc, lib, thr, cap=1 << 20, sort=True)
-        results[narrow] = (hits.copy(), ctx.last_scan_candidates(), lib.hits_blocks())
+        results[narrow] = (hits.copy(), ctx.last_scan_candidates(), lib.hits_blocks(), lib.hits_direct()[0])
         lib.close()
     enc.close()
-    hits, cand_narrow, blocks_narrow = results["9"]
-    wide, cand_wide, blocks_wide = results["0"]
-    auto, cand_auto, blocks_auto = results[None]
+    hits, cand_narrow, blocks_narrow, nd_narrow = results["9"]
+    wide, cand_wide, blocks_wide, nd_wide = results["0"]
+    auto, cand_auto, blocks_auto, nd_auto = results[None]
+    assert nd_narrow == 0 and nd_wide == 0      # forcing a block form keeps every motif on the table filter
     assert blocks_narrow == _lib.hits_block_plan(lens, 9) and [b[2] for b in blocks_narrow] == [1, 1, 0]
     assert blocks_wide == _lib.hits_block_plan(lens, 0) and len(blocks_wide) == (M + 31) // 32
-    assert sum(b[3] for b in blocks_auto) == M
+    assert sum(b[3] for b in blocks_auto) == M - nd_auto   # the direct path may have taken the shortest motifs
     assert hits.size == cnt and cnt > 0
     gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
     assert np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
     assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand)
     assert np.array_equal(hits["score"], score)
     assert np.array_equal(hits, wide) and np.array_equal(hits, auto)
-    sticky, cand_sticky, blocks_sticky = results["sticky"]
+    sticky, cand_sticky, blocks_sticky, _ = results["sticky"]
     assert [b[2] for b in blocks_sticky] == [2, 2, 0] and np.array_equal(hits, sticky)
     if kind == "flood":
         # everything is a candidate: the cost model must not pick the coarser filter
@@ -937,6 +938,37 @@ def test_verify_pass_fast_and_oracle_order_paths_agree(ctx, guard_scale, monkeyp
     lib.close()
 
 
+@pytest.mark.parametrize("n,chunks", [(300_000, 0), (300_000, 3), (1_000, 0)])
+def test_hits_direct_path_equals_table_filter_and_oracle(ctx, n, chunks, monkeypatch):
+    """A/B of the direct path (enumerated 12-mer hash for motifs of <= 12 columns) against the table filter
+    (TFBS_HITS_DIRECT=0) and the oracle: same hits, bit for bit, through the resident and the pipelined
+    host entry points; N runs, lower case and the sequence end included."""
+    logodds, lens = synth.pwm_library(39, 300, 6, 30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-4, gc=0.41, seed=39, sample=50_000)
+    seq = synth.genome(39, 12_345_678, n)
+    seq[n // 2: n // 2 + 40] = ord("N")
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    got = {}
+    for direct in ("1", "0"):
+        monkeypatch.setenv("TFBS_HITS_DIRECT", direct)
+        lib = ctx.upload_pwms(logodds, lens)
+        if chunks:
+            out = np.empty(cnt + 16, dtype=_lib.HIT_DTYPE)
+            hits = ctx.scan_hits_host(seq, ctx.alloc_seq(n), lib, thr, out, chunks=chunks, sort=True).copy()
+        else:
+            enc = ctx.encode(seq)
+            hits = ctx.scan_hits(enc, lib, thr, cap=cnt + 16, sort=True)
+            enc.close()
+        got[direct] = (hits, lib.hits_direct()[0], sum(b[3] for b in lib.hits_blocks()))
+        lib.close()
+    assert got["1"][1] == int((lens <= 12).sum()) > 32 and got["1"][2] == 300 - got["1"][1]
+    assert got["0"][1] == 0 and got["0"][2] == 300
+    for hits, _, _ in got.values():
+        gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+        assert hits.size == cnt and np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
+        assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand) and np.array_equal(hits["score"], score)
+
+
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
     """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
     narrow blocks for the short motifs; the plan follows the thresholds of each call."""
@@ -951,8 +983,12 @@ def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypat
     dense = synth.thresholds_for_rate(logodds, lens, rate=3e-2, sample=20_000)
     ctx.scan_hits(enc, lib, dense, cap=1 << 22, sort=False)
     plan_dense = lib.hits_blocks()
+    assert lib.hits_direct()[0] == 0 and sum(b[3] for b in plan_dense) == 200   # dense thresholds: tables only
     h3 = ctx.scan_hits(enc, lib, sparse, sort=True)  # back to the first thresholds: same plan, same hits
     assert lib.hits_blocks() == plan_sparse and np.array_equal(h1, h3)
+    nd, dlen, keys = lib.hits_direct()
+    assert nd == int((lens <= 12).sum()) and dlen == 12 and keys > 0   # sparse thresholds: the short motifs go direct
+    assert sum(b[3] for b in plan_sparse) == 200 - nd
     assert any(b[2] for b in plan_sparse)
     assert sum(1 for b in plan_dense if b[2]) < sum(1 for b in plan_sparse if b[2])
     for a, b, narrow, count in plan_sparse:

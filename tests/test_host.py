@@ -666,3 +666,52 @@ def test_pair_sum_rounding_guard_is_sufficient():
         accepted += int(accept.sum())
         total += n
     assert accepted > 0.9999 * total
+
+
+# ---- hits scan, direct path: enumerated 12-mer hash for the shortest motifs ---------------------------
+@pytest.mark.parametrize("rate", [1e-4, 1e-3])
+def test_direct_path_lookup_equals_the_oracle_hits(rate, monkeypatch):
+    """At sparse thresholds the motifs of at most 12 columns bypass the table filter: every L-mer whose
+    oracle score reaches the threshold is enumerated into a hash of 12-mers (scan_direct_kernel looks
+    positions up in it).  The host replay of plan + lookup must flag EXACTLY the oracle's hits of those
+    motifs (windows fully inside the sequence), on both strands, and leave the longer motifs alone."""
+    from oracle import pssm_oracle as po
+
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(39, 200, 6, 30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=rate, gc=0.41, seed=39, sample=50_000)
+    seq = synth.genome(39, 0, 400_000, gc=0.41, n_runs=False, lowercase=False)
+    codes = np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), seq).astype(np.uint8)
+    cand, info = _lib.direct_lookup_host(logodds, lens, thr, codes)
+    n_short = int((lens <= info["max_len"]).sum()) if info["motifs"] else 0
+    if rate == 1e-4:
+        assert info["max_len"] == 12 and info["motifs"] == int((lens <= 12).sum()) >= 32
+        assert info["bitmap_bits"] < 0.35 * 2**20
+    assert info["motifs"] == n_short
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    want = np.zeros_like(cand)
+    short = lens[mot] <= info["max_len"] if info["motifs"] else np.zeros(cnt, dtype=bool)
+    want[pos[short], mot[short], strand[short]] = 1
+    inside = np.arange(seq.size)[:, None] + lens[None, :] <= seq.size       # windows that fit
+    assert np.array_equal(cand[inside], want[inside])
+    assert cand[:, lens > max(info["max_len"], 0), :].sum() == 0
+    if rate == 1e-4:
+        assert want.sum() > 1000
+
+
+def test_direct_path_is_not_taken_when_it_cannot_pay(monkeypatch):
+    """Flood thresholds, very short motifs (4^(12-L) keys per hit L-mer) and the A/B switches keep every
+    motif on the table filter."""
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(5, 64, 6, 12)
+    codes = np.zeros(64, dtype=np.uint8)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=1e-4, sample=20_000)
+    assert _lib.direct_lookup_host(logodds, lens, thr, codes)[1]["motifs"] == 64
+    assert _lib.direct_lookup_host(logodds, lens, np.full(64, -1e30, np.float32), codes)[1]["motifs"] == 0
+    assert _lib.direct_lookup_host(logodds, lens, np.full(64, np.nan, np.float32), codes)[1]["keys"] == 0
+    tiny, tl = synth.pwm_library(6, 64, 1, 3)
+    assert _lib.direct_lookup_host(tiny, tl, np.zeros(64, np.float32), codes)[1]["motifs"] == 0
+    monkeypatch.setenv("TFBS_HITS_DIRECT", "0")
+    assert _lib.direct_lookup_host(logodds, lens, thr, codes)[1]["motifs"] == 0
