@@ -723,6 +723,8 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_candidates_kernel(const
 // the candidate list and the verify pass re-scores them (they are all hits up to windows with invalid
 // bases).  Takes the three or four cheapest blocks — 8 of 67 table loads per base on the 800-PWM library —
 // off the shared-memory pipe.
+constexpr int kDirectKeyBases = 12;          // hash key: 12 bases = 24 bits
+constexpr int kDirectOffBits = 2;            // window offset inside the motif (motifs of 13 / 14 columns)
 constexpr int kDirectThreads = 1024;
 constexpr int kDirectPerThread = 8;          // CONSECUTIVE positions per thread: two packed words cover their 19 bases
 constexpr int kDirectQueue = 2048;
@@ -762,10 +764,12 @@ __global__ void __launch_bounds__(kDirectThreads, 1) scan_direct_kernel(const Di
     constexpr int kSpan = kDirectThreads * kDirectPerThread;
     static_assert(kDirectPerThread == 8, "a thread's 8 positions + 11 bases must fit two packed words");
     const int64_t base0 = P.pos0 & ~(int64_t)7;   // spans start on a multiple of 8 bases (pos0 is a tile boundary anyway)
-    const int64_t n_spans = (P.pos1 - base0 + kSpan - 1) / kSpan;
+    // keys sit up to 3 bases after the window start they stand for: look 8 positions past the range
+    const int64_t q_end = P.pos1 + 8;
+    const int64_t n_spans = (q_end - base0 + kSpan - 1) / kSpan;
     for (int64_t span = blockIdx.x; span < n_spans; span += gridDim.x) {
         const int64_t p0 = base0 + span * kSpan + (int64_t)tid * kDirectPerThread;   // multiple of 8
-        if (p0 < P.pos1) {
+        if (p0 < q_end) {
             const uint32_t *wp = P.packed + (p0 >> 4);
             const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1);
             const uint64_t w = (((uint64_t)a1 << 32) | a0) >> ((int)(p0 & 15) * 2);   // bases p0 .. p0+23 (or +31)
@@ -778,14 +782,16 @@ __global__ void __launch_bounds__(kDirectThreads, 1) scan_direct_kernel(const Di
             while (pass) {
                 const int r = __ffs(pass) - 1;
                 pass &= pass - 1u;
-                const int64_t p = p0 + r;
-                if (p < P.pos0 || p >= P.pos1) continue;
+                const int64_t q = p0 + r;
                 const uint32_t key = (uint32_t)(w >> (2 * r)) & 0xFFFFFFu;  // 12 bases
                 for (uint32_t i = (key * 0x9E3779B1u) >> P.hash_shift;; i = (i + 1u) & P.hash_mask) {
                     const uint2 e = __ldg(P.hash + i);
                     if (e.y == 0u) break;
                     if (e.x == key) {
-                        const unsigned long long rec = ((unsigned long long)p << (kCandMotifBits + 1)) | (unsigned long long)(e.y - 1u);
+                        const uint32_t v = e.y - 1u;
+                        const int64_t p = q - (int64_t)(v & ((1u << kDirectOffBits) - 1u));   // window start
+                        if (p < P.pos0 || p >= P.pos1) continue;
+                        const unsigned long long rec = ((unsigned long long)p << (kCandMotifBits + 1)) | (unsigned long long)(v >> kDirectOffBits);
                         const uint32_t slot = atomicAdd(&s_qn, 1u);
                         if (slot < (uint32_t)kDirectQueue) s_q[slot] = rec;
                         else direct_overflow(P, rec);
@@ -1252,56 +1258,63 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int cou
 }
 
 // ---- direct path planning (host) ------------------------------------------------------------------------
-constexpr int kDirectKeyBases = 12;          // hash key: 12 bases = 24 bits
+constexpr int kDirectMaxLen = 14;            // longest motif the path may take (windows of 12 of its columns)
 constexpr int kDirectPrefixBases = 10;       // bitmap: first 10 bases
-constexpr size_t kDirectMaxEntries = (size_t)2 << 20;   // 2 Mi keys -> 4 Mi slots = 32 MB of hash
-constexpr double kDirectMaxDensity = 0.35;   // bitmap bits set: beyond this the screen stops screening
+constexpr size_t kDirectMaxEntries = (size_t)3 << 20;   // 3 Mi keys -> 8 Mi slots = 64 MB of hash
+constexpr double kDirectMaxDensity = 0.5;    // bitmap bits set: beyond this the screen stops screening (A/B on B200: 0.35 -> 0.5 gains 0.65 ms)
 
-// Every L-mer whose oracle score reaches the threshold: depth-first over the columns with the
-// best-possible-remainder bound (slack as in fill_block), partial sums in the oracle's left-to-right order
-// so that the leaf test (float)sum >= t IS the oracle's test.  Each hit L-mer becomes 4^(12-L) keys.
-// Returns false when `entries` would exceed `cap` (the caller then gives up the direct path).
-// With entries == nullptr only the keys are counted (*count).
-static bool enumerate_direct_field(const double *mat, int L, float t, uint32_t value, std::vector<uint2> *entries, size_t cap,
-                                   size_t *count)
+// Keys of one (motif, strand) field.  L <= 12: every L-mer whose oracle score reaches the threshold —
+// depth-first over the columns with the best-possible-remainder bound (slack as in fill_block), partial sums
+// in the oracle's left-to-right order so that the leaf test (float)sum >= t IS the oracle's test; each hit
+// L-mer becomes 4^(12-L) keys.  L = 13 or 14: the 12-mers at columns off .. off+11 that can still reach the
+// threshold when every column outside the window scores its best (a superset of the hits: the verify pass
+// rejects the rest); the key is then taken `off` bases after the window start.
+// With entries == nullptr only the keys are counted (*count).  Returns false when more than `cap` keys.
+static bool enumerate_direct_field(const double *mat, int L, int off, float t, uint32_t value, std::vector<uint2> *entries,
+                                   size_t cap, size_t *count)
 {
     *count = 0;
     if (std::isnan(t)) return true;
-    double sufbest[TFBS_MAX_MOTIF_LEN + 1];
-    sufbest[L] = 0.0;
-    for (int j = L - 1; j >= 0; j--) {
-        double mx = -INFINITY;
-        for (int b = 0; b < 4; b++) mx = std::max(mx, mat[j * 4 + b]);
-        sufbest[j] = sufbest[j + 1] + mx;
+    const int W = std::min(L, kDirectKeyBases);   // window columns off .. off+W-1
+    double colmax[TFBS_MAX_MOTIF_LEN], best = 0.0, outside = 0.0;
+    for (int j = 0; j < L; j++) {
+        colmax[j] = -INFINITY;
+        for (int b = 0; b < 4; b++) colmax[j] = std::max(colmax[j], mat[j * 4 + b]);
+        best += colmax[j];
+        if (j < off || j >= off + W) outside += colmax[j];
     }
-    if (!std::isfinite(sufbest[0])) return true;  // a column of -inf only: no window can score
+    if (!std::isfinite(best)) return true;  // a column of -inf only: no window can score
+    double sufbest[kDirectKeyBases + 1];    // best of window columns j.. plus everything outside the window
+    sufbest[W] = outside;
+    for (int j = W - 1; j >= 0; j--) sufbest[j] = sufbest[j + 1] + colmax[off + j];
     const double need = std::isinf(t) ? (double)t
-                                      : (double)t - (std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(sufbest[0]) * 1e-12 + 1e-9);
-    int code[TFBS_MAX_MOTIF_LEN];
-    double part[TFBS_MAX_MOTIF_LEN + 1];
+                                      : (double)t - (std::fabs((double)t) * std::ldexp(1.0, -22) + std::fabs(best) * 1e-12 + 1e-9);
+    const bool exact_leaf = W == L;
+    int code[kDirectKeyBases];
+    double part[kDirectKeyBases + 1];
     part[0] = 0.0;
     int j = 0;
     code[0] = 0;
-    const uint32_t n_suffix = 1u << (2 * (kDirectKeyBases - L));
+    const uint32_t n_suffix = 1u << (2 * (kDirectKeyBases - W));
     for (;;) {
         if (code[j] == 4) {
             if (--j < 0) break;
             code[j]++;
             continue;
         }
-        const double sc = part[j] + mat[j * 4 + code[j]];
+        const double sc = part[j] + mat[(off + j) * 4 + code[j]];
         if (!(sc + sufbest[j + 1] >= need)) {
             code[j]++;
             continue;
         }
-        if (j == L - 1) {
-            if ((float)sc >= t) {
+        if (j == W - 1) {
+            if (!exact_leaf || (float)sc >= t) {
                 uint32_t key = 0;
-                for (int i = 0; i < L; i++) key |= (uint32_t)code[i] << (2 * i);
+                for (int i = 0; i < W; i++) key |= (uint32_t)code[i] << (2 * i);
                 *count += n_suffix;
                 if (*count > cap) return false;
                 if (entries)
-                    for (uint32_t u = 0; u < n_suffix; u++) entries->push_back(make_uint2(key | (u << (2 * L)), value));
+                    for (uint32_t u = 0; u < n_suffix; u++) entries->push_back(make_uint2(key | (u << (2 * W)), value));
             }
             code[j]++;
         } else {
@@ -1321,7 +1334,7 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
 {
     if (env_int("TFBS_HITS_DIRECT") == 0 || env_int("TFBS_HITS_NARROW") >= 0 || env_int("TFBS_HITS_STICKY") >= 0) return 0;
     const int M = pw->M;
-    for (int Ld : {12, 10, 8}) {
+    for (int Ld : {kDirectMaxLen, 12, 10, 8}) {
         int n = 0;
         while (n < M && pw->lens_desc[M - 1 - n] <= Ld) n++;
         // worth a separate pass only if it takes at least one whole table block off the scan
@@ -1334,18 +1347,33 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
         if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
         std::vector<std::vector<uint2>> part(T);
         std::vector<size_t> counted(T, 0);
+        std::vector<uint8_t> best_off((size_t)M * 2, 0);   // window offset chosen for every field (count pass)
         std::atomic<bool> ok{true};
         auto pass = [&](bool build) {
             std::atomic<int> next{M - n};
             auto worker = [&](unsigned t) {
                 for (int i = next.fetch_add(1); i < M && ok.load(); i = next.fetch_add(1)) {
-                    const int m = pw->order[i];
+                    const int m = pw->order[i], L = pw->lens[m];
                     for (int s2 = 0; s2 < 2; s2++) {
+                        const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4;
                         size_t c = 0;
-                        if (!enumerate_direct_field(pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4,
-                                                    pw->lens[m], thr[m], (((uint32_t)m << 1) | (uint32_t)s2) + 1u,
-                                                    build ? &part[t] : nullptr, kDirectMaxEntries, &c))
-                            ok.store(false);
+                        if (!build) {
+                            // motifs longer than the key: the 12-column window that passes the fewest 12-mers
+                            size_t best_c = SIZE_MAX;
+                            for (int off = 0; off + std::min(L, kDirectKeyBases) <= L; off++) {
+                                size_t c2 = 0;
+                                if (enumerate_direct_field(mat, L, off, thr[m], 0u, nullptr, kDirectMaxEntries, &c2) && c2 < best_c) {
+                                    best_c = c2;
+                                    best_off[(size_t)m * 2 + s2] = (uint8_t)off;
+                                }
+                            }
+                            if (best_c == SIZE_MAX) ok.store(false);
+                            else c = best_c;
+                        } else {
+                            const int off = best_off[(size_t)m * 2 + s2];
+                            const uint32_t value = ((((uint32_t)m << 1) | (uint32_t)s2) << kDirectOffBits | (uint32_t)off) + 1u;
+                            if (!enumerate_direct_field(mat, L, off, thr[m], value, &part[t], kDirectMaxEntries, &c)) ok.store(false);
+                        }
                         counted[t] += c;
                     }
                 }
@@ -1359,6 +1387,7 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
         size_t total = 0;
         for (size_t c : counted) total += c;
         if (!ok.load() || total > kDirectMaxEntries) continue;
+        std::fill(counted.begin(), counted.end(), (size_t)0);
         pass(true);
         std::vector<uint2> entries;
         entries.reserve(total);
@@ -1368,7 +1397,9 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
         for (const uint2 &e : entries) bitmap[(e.x & pmask) >> 5] |= 1u << (e.x & 31u);
         size_t bits_set = 0;
         for (uint32_t w : bitmap) bits_set += (size_t)__builtin_popcount(w);
-        if ((double)bits_set > kDirectMaxDensity * (double)(1u << (2 * kDirectPrefixBases))) continue;
+        double max_density = kDirectMaxDensity;
+        if (const char *env = getenv("TFBS_DIRECT_DENSITY")) max_density = atof(env);   // A/B measurements
+        if ((double)bits_set > max_density * (double)(1u << (2 * kDirectPrefixBases))) continue;
         uint32_t bits = 10;
         while (((size_t)1 << bits) < 2 * entries.size() + 16) bits++;
         hash.assign((size_t)1 << bits, make_uint2(0u, 0u));
@@ -1940,7 +1971,11 @@ extern "C" int tfbs_debug_direct_lookup(const double *logodds, const int32_t *le
         if (!((bitmap[k10 >> 5] >> (k10 & 31u)) & 1u)) continue;
         for (uint32_t i = (key * 0x9E3779B1u) >> shift;; i = (i + 1u) & mask) {
             if (hash[i].y == 0u) break;
-            if (hash[i].x == key) cand[((size_t)p * M + ((hash[i].y - 1u) >> 1)) * 2 + ((hash[i].y - 1u) & 1u)] = 1;
+            if (hash[i].x == key) {
+                const uint32_t v = hash[i].y - 1u;
+                const int64_t start = p - (int64_t)(v & ((1u << kDirectOffBits) - 1u));
+                if (start >= 0) cand[((size_t)start * M + (v >> (kDirectOffBits + 1))) * 2 + ((v >> kDirectOffBits) & 1u)] = 1;
+            }
         }
     }
     return TFBS_OK;
