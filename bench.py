@@ -561,7 +561,7 @@ def run_ours(args):
                                               "best of 3, measured in this run",
                          "loads_per_base": int(sum(a + b for a, b, _, _ in blocks)),
                          "direct_path": {"motifs": direct[0], "max_len": direct[1], "keys": direct[2],
-                                         "note": "motifs of <= 12 columns looked up in an enumerated 12-mer hash "
+                                         "note": "motifs of <= max_len columns looked up in an enumerated 12-mer hash "
                                                  "(scan_direct_kernel); they cost no table loads"},
                          "blocks": {"wide_32_motifs": sum(1 for b in blocks if b[2] == 0),
                                     "narrow_64_motifs": sum(1 for b in blocks if b[2] == 1),
