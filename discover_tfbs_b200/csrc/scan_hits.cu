@@ -727,7 +727,8 @@ constexpr int kDirectKeyBases = 12;          // hash key: 12 bases = 24 bits
 constexpr int kDirectOffBits = 2;            // window offset inside the motif (motifs of 13 / 14 columns)
 constexpr int kDirectThreads = 1024;
 constexpr int kDirectPerThread = 8;          // CONSECUTIVE positions per thread: two packed words cover their 19 bases
-constexpr int kDirectQueue = 2048;
+constexpr int kDirectQueue = 4096;
+constexpr int kDirectSpansPerCheck = 4;      // spans between two looks at the queue (one CTA barrier each)
 constexpr int kDirectBitmapWords = 1 << 15;  // 2^20 bits
 struct DirectParams {
     const uint32_t *packed;
@@ -767,6 +768,7 @@ __global__ void __launch_bounds__(kDirectThreads, 1) scan_direct_kernel(const Di
     // keys sit up to 3 bases after the window start they stand for: look 8 positions past the range
     const int64_t q_end = P.pos1 + 8;
     const int64_t n_spans = (q_end - base0 + kSpan - 1) / kSpan;
+    int since_check = 0;
     for (int64_t span = blockIdx.x; span < n_spans; span += gridDim.x) {
         const int64_t p0 = base0 + span * kSpan + (int64_t)tid * kDirectPerThread;   // multiple of 8
         if (p0 < q_end) {
@@ -799,9 +801,13 @@ __global__ void __launch_bounds__(kDirectThreads, 1) scan_direct_kernel(const Di
                 }
             }
         }
+        // the queue is looked at every kDirectSpansPerCheck spans and after the last one (CTA-uniform)
+        const bool last = span + gridDim.x >= n_spans;
+        if (++since_check < kDirectSpansPerCheck && !last) continue;
+        since_check = 0;
         __syncthreads();
         const uint32_t qn = min(s_qn, (uint32_t)kDirectQueue);
-        if (qn >= (uint32_t)kDirectQueue / 2 || span + gridDim.x >= n_spans) {  // CTA-uniform
+        if (qn >= (uint32_t)kDirectQueue / 2 || last) {
             if (tid == 0 && qn) {
                 s_base = atomicAdd(P.V.hit_count + kCandCountSlot, (unsigned long long)qn);
                 atomicAdd(P.V.hit_count + 1, (unsigned long long)qn);

@@ -154,12 +154,14 @@ int tfbs_scan_dense(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, f
  * bit-exact with max / first argmax of the oracle's calculate().  Only S*M*2 floats cross PCIe instead of the [M][n] dense arrays. */
 int tfbs_scan_best(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const int64_t *rec_start,
                    const int64_t *rec_len, int64_t S, float *best_host, int32_t *pos_host);
-/* Hits mode: every (motif, start, strand) with (float)score >= thr[motif].  A packed
- * fixed-point filter with a rigorous upper bound selects candidates; each candidate is then
- * re-scored left to right in double and cast to float, so hit sets and scores are bit-exact
- * with the oracle.  Order of `out` is unspecified unless `sorted` is non-zero (then ascending
- * (motif, pos, strand)).  out_host may be NULL (hits stay on device).  If more than `cap` hits
- * exist the call returns TFBS_ERR_OVERFLOW with *n_hits = the number found. */
+/* Hits mode: every (motif, start, strand) with (float)score >= thr[motif].  Candidates come from a packed
+ * fixed-point filter over shared-memory k-mer tables with a rigorous upper bound (and, at sparse thresholds,
+ * from an enumerated 12-mer hash for the motifs of at most 14 columns); a second kernel re-scores every
+ * candidate in double — in the oracle's left-to-right order, or in column pairs when a rounding guard proves
+ * that both orders round to the same float — so hit sets and scores are bit-exact with the oracle.  Order
+ * of `out` is unspecified unless `sorted` is non-zero (then ascending (motif, pos, strand)).  out_host may
+ * be NULL (hits stay on device).  If more than `cap` hits exist the call returns TFBS_ERR_OVERFLOW with
+ * *n_hits = the number found. */
 int tfbs_scan_hits(tfbs_ctx *ctx, const tfbs_seq *seq, const tfbs_pwms *pwms, const float *thr,
                    tfbs_hit *out_host, int64_t cap, int32_t sorted, int64_t *n_hits);
 
