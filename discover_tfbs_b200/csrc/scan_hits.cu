@@ -150,7 +150,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     uint32_t done;
     uint32_t spins = 0;
     do {
-        if (++spins == (1u << 24)) __trap();  // a lost arrival must fail the launch, not hang the GPU
+        if (++spins == (1u << 28)) __trap();  // a lost arrival must fail the launch (after tens of seconds), not hang the GPU
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
