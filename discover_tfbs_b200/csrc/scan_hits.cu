@@ -1511,11 +1511,14 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         nb++;
     });
     pw->n_blocks = nb;
-    cudaError_t e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), (size_t)words * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), (size_t)nb * 32 * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_AB_dev, blk_AB.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_lut_off_dev, pw->blk_lut_off.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(pw->blk_motif_dev, pw->blk_motif.data(), (size_t)nb * TFBS_BLOCK_SLOTS * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaSuccess;
+    if (nb > 0) {  // (no table block at all when every motif took the direct path)
+        e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), (size_t)words * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), (size_t)nb * 32 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->blk_AB_dev, blk_AB.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->blk_lut_off_dev, pw->blk_lut_off.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->blk_motif_dev, pw->blk_motif.data(), (size_t)nb * TFBS_BLOCK_SLOTS * 4, cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;

@@ -970,6 +970,29 @@ def test_hits_direct_path_equals_table_filter_and_oracle(ctx, n, chunks, monkeyp
         assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand) and np.array_equal(hits["score"], score)
 
 
+def test_hits_library_of_short_motifs_only_runs_without_a_table_block(ctx, monkeypatch):
+    """64 motifs of 6 - 12 columns at a sparse threshold: every motif takes the direct path, the table filter
+    has no block to scan; hits equal the oracle's through the resident and the pipelined entry points."""
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(5, 64, 6, 12)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=1e-4, sample=50_000)
+    seq = synth.genome(5, 777, 500_000)
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    enc = ctx.encode(seq)
+    lib = ctx.upload_pwms(logodds, lens)
+    hits = ctx.scan_hits(enc, lib, thr, cap=cnt + 16, sort=True)
+    assert lib.hits_direct()[0] == 64 and lib.hits_blocks() == []
+    out = np.empty(cnt + 16, dtype=_lib.HIT_DTYPE)
+    host = ctx.scan_hits_host(seq, ctx.alloc_seq(seq.size), lib, thr, out, chunks=4, sort=True)
+    for h in (hits, host):
+        gpos = np.where(h["pos"] < 0, ~h["pos"], h["pos"])
+        assert cnt > 1000 and h.size == cnt and np.array_equal(gpos, pos) and np.array_equal(h["motif"], mot)
+        assert np.array_equal((h["pos"] < 0).astype(np.int32), strand) and np.array_equal(h["score"], score)
+    enc.close()
+    lib.close()
+
+
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
     """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
     narrow blocks for the short motifs; the plan follows the thresholds of each call."""
