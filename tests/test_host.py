@@ -718,3 +718,37 @@ def test_direct_path_is_not_taken_when_it_cannot_pay(monkeypatch):
     assert _lib.direct_lookup_host(tiny, tl, np.zeros(64, np.float32), codes)[1]["motifs"] == 0
     monkeypatch.setenv("TFBS_HITS_DIRECT", "0")
     assert _lib.direct_lookup_host(logodds, lens, thr, codes)[1]["motifs"] == 0
+
+
+# ---- bench.py contract (CPU side) ---------------------------------------------------------------------
+def test_bench_reference_arm_prints_one_json_line_with_all_host_cores():
+    """`bench.py --impl reference`: ONE JSON line on stdout with the contract's keys; the CPU arm takes its
+    thread count from sched_getaffinity even when OMP_NUM_THREADS=1 (what torch.distributed.run exports)."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--motifs", "24"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert "10000000 bp" in d["cpu_baseline"]["sample"]                 # >= 10 Mb per step (SURVEY.md §8d)
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu():
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--motifs", "8",
+                          "--genome-mb", "1", "--no-extras"], capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and out.stdout.strip() == ""
+    assert "no CUDA device" in out.stderr or "libtfbs_cuda" in out.stderr
