@@ -79,29 +79,55 @@ def merge_shard_hits(per_shard: list) -> np.ndarray:
     return allh[order]
 
 
-def concat_sorted_shards(per_shard: list, n_motifs: int) -> np.ndarray:
+def concat_sorted_shards(per_shard: list, n_motifs: int, out: np.ndarray = None, threads: int = 8) -> np.ndarray:
     """Whole-genome (motif, pos, strand) order from per-shard arrays that are each in that order and
     hold global positions: shards are position-ordered, so for every motif the shard pieces are simply
-    laid end to end — an ordered concatenation, no comparison sort."""
+    laid end to end — an ordered concatenation, no comparison sort.  The block copies of disjoint motif
+    ranges run on `threads` host threads (NumPy releases the GIL while it copies); `out` may be a
+    preallocated HIT_DTYPE array of at least the total size (saves the page faults of a fresh one)."""
     if not per_shard:
         return np.zeros(0, dtype=_lib.HIT_DTYPE)
-    if len(per_shard) == 1:
+    if len(per_shard) == 1 and out is None:
         return per_shard[0]
-    bounds = [np.searchsorted(h["motif"], np.arange(n_motifs + 1)) for h in per_shard]  # [shard][motif] -> row
-    counts = np.stack([np.diff(b) for b in bounds])                   # [shard][motif]
-    out = np.empty(int(counts.sum()), dtype=_lib.HIT_DTYPE)
-    # motif by motif, the shard pieces are laid end to end: n_motifs x n_shards contiguous block copies
+    bounds = np.stack([np.searchsorted(h["motif"], np.arange(n_motifs + 1)) for h in per_shard])  # [shard][motif] -> row
+    counts = np.diff(bounds, axis=1)                                  # [shard][motif]
+    total = int(counts.sum())
+    if out is None:
+        out = np.empty(total, dtype=_lib.HIT_DTYPE)
+    elif out.size < total or out.dtype != _lib.HIT_DTYPE:
+        raise ValueError(f"out must be a HIT_DTYPE array of at least {total} entries")
+    out = out[:total]
+    # destination of the first hit of motif m: everything of the motifs before it
+    motif_base = np.concatenate([[0], np.cumsum(counts.sum(axis=0))])
     # (copied as plain 2 x uint64 rows: slice assignment of a structured dtype goes field by field)
     raw_out = out.view(np.uint64).reshape(-1, 2)
     raw_in = [np.ascontiguousarray(h).view(np.uint64).reshape(-1, 2) for h in per_shard]
-    at = 0
-    for m in range(n_motifs):
-        for k in range(len(per_shard)):
-            c = int(counts[k][m])
-            if c:
-                lo = int(bounds[k][m])
-                raw_out[at: at + c] = raw_in[k][lo: lo + c]
-                at += c
+
+    def copy_motifs(m0, m1):
+        for m in range(m0, m1):
+            at = int(motif_base[m])
+            for k in range(len(per_shard)):
+                c = int(counts[k][m])
+                if c:
+                    lo = int(bounds[k][m])
+                    raw_out[at: at + c] = raw_in[k][lo: lo + c]
+                    at += c
+
+    threads = max(1, min(int(threads), n_motifs))
+    if threads == 1 or total < (1 << 20):
+        copy_motifs(0, n_motifs)
+    else:
+        import threading
+
+        # motif ranges of about equal numbers of hits
+        cuts = np.searchsorted(motif_base, np.linspace(0, total, threads + 1)[1:-1]).tolist()
+        edges = [0] + [min(max(int(c), 0), n_motifs) for c in cuts] + [n_motifs]
+        pool = [threading.Thread(target=copy_motifs, args=(edges[i], edges[i + 1])) for i in range(threads)
+                if edges[i + 1] > edges[i]]
+        for t in pool:
+            t.start()
+        for t in pool:
+            t.join()
     return out
 
 

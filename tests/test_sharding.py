@@ -65,6 +65,22 @@ def test_ordered_concatenation_of_sorted_shards_equals_global_sort():
         assert np.array_equal(got, sharding.merge_shard_hits(parts))
     empty = np.zeros(0, dtype=_lib.HIT_DTYPE)
     assert sharding.concat_sorted_shards([empty, empty], len(lens)).size == 0
+    # threaded copies into a preallocated output give the same array
+    rng = np.random.default_rng(1)
+    big = []
+    for k in range(3):
+        h = np.zeros(700_000, dtype=_lib.HIT_DTYPE)
+        h["motif"] = np.sort(rng.integers(0, 50, size=h.size))
+        h["pos"] = np.arange(h.size) + k * 10**7
+        h["score"] = rng.random(h.size)
+        big.append(h)
+    want = sharding.merge_shard_hits(big)
+    buf = np.empty(want.size + 5, dtype=_lib.HIT_DTYPE)
+    got = sharding.concat_sorted_shards(big, 50, out=buf, threads=4)
+    assert got.base is not None and np.array_equal(got, want)
+    assert np.array_equal(sharding.concat_sorted_shards(big, 50, threads=1), want)
+    with pytest.raises(ValueError):
+        sharding.concat_sorted_shards(big, 50, out=buf[:10])
 
 
 @pytest.mark.parametrize("n,k", [(0, 3), (1, 4), (55_000, 8), (7, 7), (10, 3)])
