@@ -77,6 +77,7 @@ _PROTOTYPES = {
     "tfbs_pwms_hits_direct": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
     "tfbs_debug_direct_lookup": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "tfbs_debug_direct_motifs": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
 }
 
@@ -181,6 +182,17 @@ def direct_lookup_host(logodds, lens, thr, codes):
     info = np.zeros(4, dtype=np.int64)
     _check(load().tfbs_debug_direct_lookup(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), _ptr(cd), int(cd.size), _ptr(out), _ptr(info)))
     return out, {"motifs": int(info[0]), "max_len": int(info[1]), "keys": int(info[2]), "bitmap_bits": int(info[3])}
+
+
+def direct_motifs_host(logodds, lens, thr) -> np.ndarray:
+    """Which motifs the hits scan's direct path takes for a threshold vector (test hook, no GPU): bool[M]."""
+    lo = np.ascontiguousarray(logodds, dtype=np.float64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    th = np.ascontiguousarray(thr, dtype=np.float32)
+    M, Lmax = int(lo.shape[0]), int(lo.shape[1])
+    out = np.zeros(M, dtype=np.uint8)
+    _check(load().tfbs_debug_direct_motifs(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), _ptr(out)))
+    return out.astype(bool)
 
 
 def device_count() -> int:

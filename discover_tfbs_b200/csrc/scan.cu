@@ -370,13 +370,17 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     for (int i = 0; i < M; i++) p->lens_desc[i] = lens[p->order[i]];
     p->n_blocks = 0;
     p->n_blocks_max = (M + 31) / 32;
-    int64_t words = 0;
-    for (int i = 0; i < M; i += 32) {
+    // (A per-threshold plan leaves some short motifs to the direct path, so block i may start at a motif
+    // SHORTER than lens_desc[32 i]; the table of a shorter motif can be the larger one — 24 columns take
+    // 6 x 32 KB, 25 columns 5 x 32 + 2 x 8 KB — hence the running maximum over all lengths up to it.)
+    int64_t words = 0, words_upto[TFBS_MAX_MOTIF_LEN + 1] = {0};
+    for (int L = 1; L <= TFBS_MAX_MOTIF_LEN; L++) {
         int A = 0, B = 1;
-        tfbs_hits_group_plan(p->lens_desc[i], &A, &B);
-        words += (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32;
-        p->hits_lut_bytes = std::max(p->hits_lut_bytes, (size_t)A * 32768 + (size_t)B * 8192);
+        tfbs_hits_group_plan(L, &A, &B);
+        words_upto[L] = std::max(words_upto[L - 1], (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32);
     }
+    for (int i = 0; i < M; i += 32) words += words_upto[p->lens_desc[i]];
+    p->hits_lut_bytes = (size_t)words_upto[p->lens_desc[0]] * 4;
     p->exact_host = exact;
     p->hq_lut_words = words;
 

@@ -1222,16 +1222,17 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
     return narrow ? expected : 0.0;
 }
 
-// Form of the block made of motifs order[first, first + count) (count > 32): forced from the
+// Form of the block made of motifs order[first, first + count) (count > 32; `order` = the motifs on the table
+// filter for this threshold vector, longest first, lens_desc their lengths): forced from the
 // environment, else the cheapest by the cost model.  The candidate forms are built in place in
 // lut / kinit; on return they hold the tables of the chosen form unless that is kWide (the caller
 // builds the wide table of the first 32 motifs).  *expected = candidates per window start the chosen
 // narrow / sticky form is expected to pass (0 for kWide).
-static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int count, int A, int B, uint32_t *lut,
-                       uint32_t *kinit, double *expected)
+static int choose_form(const tfbs_pwms *pw, const float *thr, const int32_t *order, const int32_t *lens_desc, int first,
+                       int count, int A, int B, uint32_t *lut, uint32_t *kinit, double *expected)
 {
     const int G = A + B;
-    const int32_t *motifs = pw->order.data() + first;
+    const int32_t *motifs = order + first;
     const int force_narrow = env_int("TFBS_HITS_NARROW"), force_sticky = env_int("TFBS_HITS_STICKY");
     *expected = 0.0;
     if (force_narrow >= 0 || force_sticky >= 0) {
@@ -1243,7 +1244,7 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int cou
     }
     // groups of the second of the two wide blocks a narrow block replaces
     int A2 = 0, B2 = 1;
-    tfbs_hits_group_plan(pw->lens_desc[first + 32], &A2, &B2);
+    tfbs_hits_group_plan(lens_desc[first + 32], &A2, &B2);
     const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
     // the sticky filter (>= 117 steps) also estimates the candidates of the wide form: measured,
     // it passes about 1.5x as many
@@ -1267,6 +1268,7 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, int first, int cou
 constexpr int kDirectMaxLen = 14;            // longest motif the path may take (windows of 12 of its columns)
 constexpr int kDirectPrefixBases = 10;       // bitmap: first 10 bases
 constexpr size_t kDirectMaxEntries = (size_t)3 << 20;   // 3 Mi keys -> 8 Mi slots = 64 MB of hash
+constexpr size_t kDirectMotifMaxEntries = kDirectMaxEntries / 32;   // keys of ONE motif (both strands); more: it stays on the tables
 constexpr double kDirectMaxDensity = 0.5;    // bitmap bits set: beyond this the screen stops screening (A/B on B200: 0.35 -> 0.5 gains 0.65 ms)
 
 // Keys of one (motif, strand) field.  L <= 12: every L-mer whose oracle score reaches the threshold —
@@ -1331,69 +1333,91 @@ static bool enumerate_direct_field(const double *mat, int L, int off, float t, u
     return true;
 }
 
-// Decide which motifs (a tail of the length-sorted order: the shortest) take the direct path for this
-// threshold vector and build their bitmap + hash.  Returns the number of direct motifs (0: none).
+// Decide which motifs take the direct path for this threshold vector and build their bitmap + hash.
+// Candidates are the motifs of at most Ld columns, Ld = 14, 12, 10, 8: the first set whose keys number at most
+// kDirectMaxEntries and whose bitmap stays sparse enough is taken whole.  If no whole set fits, the choice is
+// made PER MOTIF: a motif whose own keys number more than kDirectMotifMaxEntries (a loose, flood or -inf
+// threshold) stays on the table filter without taking the rest of the library with it — with "80 % of the
+// best score" thresholds the 6-column motifs pass a percent of all windows while the 12-column ones pass 1e-5
+// of them.  is_direct[m] = 1 for the motifs taken.  Returns their number (0: none).
 // TFBS_HITS_DIRECT=0 switches the path off; forcing a block form (TFBS_HITS_NARROW / _STICKY, A/B runs and
 // tests of the table filter) does too.
 static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32_t> &bitmap, std::vector<uint2> &hash,
-                       uint32_t *hash_shift, int *direct_len, int64_t *n_entries)
+                       uint32_t *hash_shift, int *direct_len, int64_t *n_entries, std::vector<uint8_t> &is_direct)
 {
-    if (env_int("TFBS_HITS_DIRECT") == 0 || env_int("TFBS_HITS_NARROW") >= 0 || env_int("TFBS_HITS_STICKY") >= 0) return 0;
     const int M = pw->M;
-    for (int Ld : {kDirectMaxLen, 12, 10, 8}) {
-        int n = 0;
-        while (n < M && pw->lens_desc[M - 1 - n] <= Ld) n++;
-        // worth a separate pass only if it takes at least one whole table block off the scan
-        if (n < 32) continue;
-        // count first (cheap: no suffix expansion), build only what fits; both passes run on the host's cores
-        cpu_set_t set;
-        const unsigned cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
-        unsigned T = std::max(1u, std::min<unsigned>(std::min(cores, 16u), (unsigned)n));
-        const int forced = env_int("TFBS_PLAN_THREADS");
-        if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
-        std::vector<std::vector<uint2>> part(T);
-        std::vector<size_t> counted(T, 0);
-        std::vector<uint8_t> best_off((size_t)M * 2, 0);   // window offset chosen for every field (count pass)
-        std::atomic<bool> ok{true};
-        auto pass = [&](bool build) {
-            std::atomic<int> next{M - n};
-            auto worker = [&](unsigned t) {
-                for (int i = next.fetch_add(1); i < M && ok.load(); i = next.fetch_add(1)) {
-                    const int m = pw->order[i], L = pw->lens[m];
-                    for (int s2 = 0; s2 < 2; s2++) {
-                        const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4;
-                        size_t c = 0;
-                        if (!build) {
-                            // motifs longer than the key: the 12-column window that passes the fewest 12-mers
-                            size_t best_c = SIZE_MAX;
-                            for (int off = 0; off + std::min(L, kDirectKeyBases) <= L; off++) {
-                                size_t c2 = 0;
-                                if (enumerate_direct_field(mat, L, off, thr[m], 0u, nullptr, kDirectMaxEntries, &c2) && c2 < best_c) {
-                                    best_c = c2;
-                                    best_off[(size_t)m * 2 + s2] = (uint8_t)off;
-                                }
+    is_direct.assign((size_t)M, 0);
+    if (env_int("TFBS_HITS_DIRECT") == 0 || env_int("TFBS_HITS_NARROW") >= 0 || env_int("TFBS_HITS_STICKY") >= 0) return 0;
+    int n_max = 0;   // motifs of at most kDirectMaxLen columns: the tail of the length-sorted order
+    while (n_max < M && pw->lens_desc[M - 1 - n_max] <= kDirectMaxLen) n_max++;
+    // worth a separate pass only if it takes at least one whole table block off the scan
+    if (n_max < 32) return 0;
+    cpu_set_t set;
+    const unsigned cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
+    unsigned T = std::max(1u, std::min<unsigned>(std::min(cores, 16u), (unsigned)n_max));
+    const int forced = env_int("TFBS_PLAN_THREADS");
+    if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
+    constexpr size_t kTooMany = SIZE_MAX;
+    std::vector<uint8_t> best_off((size_t)M * 2, 0);   // window offset chosen for every field (count pass)
+    std::vector<size_t> keys((size_t)M, kTooMany);     // keys of both strands of a motif (count pass)
+    std::vector<int32_t> taken;                        // motifs of the set being tried
+    std::vector<std::vector<uint2>> part(T);
+    // both passes run on the host's cores: count first (cheap: no suffix expansion), build only what fits
+    auto pass = [&](bool build) {
+        std::atomic<int> next{build ? 0 : M - n_max};
+        const int end = build ? (int)taken.size() : M;
+        auto worker = [&](unsigned t) {
+            for (int i = next.fetch_add(1); i < end; i = next.fetch_add(1)) {
+                const int m = build ? taken[(size_t)i] : pw->order[i], L = pw->lens[m];
+                size_t km = 0;
+                for (int s2 = 0; s2 < 2 && km != kTooMany; s2++) {
+                    const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4;
+                    if (!build) {
+                        // motifs longer than the key: the 12-column window that passes the fewest 12-mers
+                        size_t best_c = kTooMany;
+                        for (int off = 0; off + std::min(L, kDirectKeyBases) <= L; off++) {
+                            size_t c2 = 0;
+                            if (enumerate_direct_field(mat, L, off, thr[m], 0u, nullptr, kDirectMaxEntries, &c2) && c2 < best_c) {
+                                best_c = c2;
+                                best_off[(size_t)m * 2 + s2] = (uint8_t)off;
                             }
-                            if (best_c == SIZE_MAX) ok.store(false);
-                            else c = best_c;
-                        } else {
-                            const int off = best_off[(size_t)m * 2 + s2];
-                            const uint32_t value = ((((uint32_t)m << 1) | (uint32_t)s2) << kDirectOffBits | (uint32_t)off) + 1u;
-                            if (!enumerate_direct_field(mat, L, off, thr[m], value, &part[t], kDirectMaxEntries, &c)) ok.store(false);
                         }
-                        counted[t] += c;
+                        km = best_c == kTooMany ? kTooMany : km + best_c;
+                    } else {
+                        const int off = best_off[(size_t)m * 2 + s2];
+                        const uint32_t value = ((((uint32_t)m << 1) | (uint32_t)s2) << kDirectOffBits | (uint32_t)off) + 1u;
+                        size_t c = 0;
+                        enumerate_direct_field(mat, L, off, thr[m], value, &part[t], kDirectMaxEntries, &c);
                     }
                 }
-            };
-            std::vector<std::thread> pool;
-            for (unsigned t = 1; t < T; t++) pool.emplace_back(worker, t);
-            worker(0);
-            for (auto &th : pool) th.join();
+                if (!build) keys[(size_t)m] = km;
+            }
         };
-        pass(false);
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T; t++) pool.emplace_back(worker, t);
+        worker(0);
+        for (auto &th : pool) th.join();
+    };
+    pass(false);
+    // One attempt: the motifs of at most Ld columns — all of them, or (per_motif) those with few enough keys.
+    auto attempt = [&](int Ld, bool per_motif) -> int {
+        int n = 0;
+        while (n < M && pw->lens_desc[M - 1 - n] <= Ld) n++;
+        taken.clear();
         size_t total = 0;
-        for (size_t c : counted) total += c;
-        if (!ok.load() || total > kDirectMaxEntries) continue;
-        std::fill(counted.begin(), counted.end(), (size_t)0);
+        for (int i = M - n; i < M; i++) {
+            const int m = pw->order[i];
+            const size_t km = keys[(size_t)m];
+            if (per_motif ? km > kDirectMotifMaxEntries : km == kTooMany) {
+                if (per_motif) continue;
+                return 0;
+            }
+            taken.push_back(m);
+            total += km;
+        }
+        if (per_motif && (int)taken.size() == n) return 0;   // nothing left out: the whole set was tried already
+        if ((int)taken.size() < 32 || total > kDirectMaxEntries) return 0;
+        for (auto &v : part) v.clear();
         pass(true);
         std::vector<uint2> entries;
         entries.reserve(total);
@@ -1405,7 +1429,7 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
         for (uint32_t w : bitmap) bits_set += (size_t)__builtin_popcount(w);
         double max_density = kDirectMaxDensity;
         if (const char *env = getenv("TFBS_DIRECT_DENSITY")) max_density = atof(env);   // A/B measurements
-        if ((double)bits_set > max_density * (double)(1u << (2 * kDirectPrefixBases))) continue;
+        if ((double)bits_set > max_density * (double)(1u << (2 * kDirectPrefixBases))) return 0;
         uint32_t bits = 10;
         while (((size_t)1 << bits) < 2 * entries.size() + 16) bits++;
         hash.assign((size_t)1 << bits, make_uint2(0u, 0u));
@@ -1416,11 +1440,34 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
             hash[i] = e;
         }
         *hash_shift = 32 - bits;
-        *direct_len = Ld;
+        *direct_len = 0;
+        for (int m : taken) {
+            is_direct[(size_t)m] = 1;
+            *direct_len = std::max(*direct_len, (int)pw->lens[m]);
+        }
         *n_entries = (int64_t)entries.size();
-        return n;
-    }
+        return (int)taken.size();
+    };
+    for (bool per_motif : {false, true})
+        for (int Ld : {kDirectMaxLen, 12, 10, 8})
+            if (const int n = attempt(Ld, per_motif)) return n;
     return 0;
+}
+
+// The motifs the table filter keeps for a threshold vector: the length-sorted order without the motifs on
+// the direct path (still longest first, so block i of this order is no longer than block i of the whole
+// library and the device arrays sized at upload are large enough).
+static void table_order(const tfbs_pwms *pw, const std::vector<uint8_t> &is_direct, std::vector<int32_t> &order,
+                        std::vector<int32_t> &lens_desc)
+{
+    order.clear();
+    lens_desc.clear();
+    for (int i = 0; i < pw->M; i++) {
+        const int m = pw->order[i];
+        if (is_direct[(size_t)m]) continue;
+        order.push_back(m);
+        lens_desc.push_back(pw->lens[m]);
+    }
 }
 
 // Plan the blocks and quantise their tables for a threshold vector; cached per threshold vector.
@@ -1429,20 +1476,24 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     const int Mall = pw->M;
     if (pw->hq_valid && pw->hq_thr.size() == (size_t)Mall && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * Mall) == 0)
         return TFBS_OK;
-    // the shortest motifs may bypass the table filter altogether (direct path); the blocks below are cut
-    // from the remaining M motifs (the head of the length-sorted order)
+    pw->hq_valid = false;   // the device tables are overwritten from here on
+    // short motifs may bypass the table filter altogether (direct path); the blocks below are cut from the
+    // remaining M motifs
     std::vector<uint32_t> d_bitmap;
     std::vector<uint2> d_hash;
     uint32_t d_shift = 0;
     int d_len = 0;
     int64_t d_entries = 0;
-    const int n_direct = plan_direct(pw, thr, d_bitmap, d_hash, &d_shift, &d_len, &d_entries);
+    std::vector<uint8_t> is_direct;
+    const int n_direct = plan_direct(pw, thr, d_bitmap, d_hash, &d_shift, &d_len, &d_entries, is_direct);
     const int M = Mall - n_direct;
+    std::vector<int32_t> t_order, t_lens;   // the motifs left on the table filter, longest first
+    table_order(pw, is_direct, t_order, t_lens);
     std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
     std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
     int64_t words = 0;   // table words of the blocks emitted so far
     int nb = 0;
-    const int32_t *order = pw->order.data();
+    const int32_t *order = t_order.data();
     // The form of a block depends only on where it starts, and every block starts at a multiple of 32
     // motifs: the forms (and tables) of all possible starts are worked out speculatively on the host's
     // cores, then the sequential cut below picks the ones it reaches.  (Planning the 800-PWM library
@@ -1455,7 +1506,7 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     std::vector<int> starts;
     for (int i = 0; i < M; i += 32) {
         Spec &S = spec[(size_t)i / 32];
-        tfbs_hits_group_plan(pw->lens_desc[i], &S.A, &S.B);
+        tfbs_hits_group_plan(t_lens[(size_t)i], &S.A, &S.B);
         S.count = std::min(M - i, 64);
         if (S.A + S.B <= TFBS_NARROW_MAX_GROUPS && M - i > 32) starts.push_back(i);
     }
@@ -1472,7 +1523,7 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
                 S.lut.assign((size_t)S.A * 8192 + (size_t)S.B * 2048, 0u);
                 S.kinit.assign(32, kPoison);
                 double expected;
-                S.form = choose_form(pw, thr, starts[k], S.count, S.A, S.B, S.lut.data(), S.kinit.data(), &expected);
+                S.form = choose_form(pw, thr, order, t_lens.data(), starts[k], S.count, S.A, S.B, S.lut.data(), S.kinit.data(), &expected);
             }
         };
         std::vector<std::thread> pool;
@@ -1481,9 +1532,12 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         for (auto &th : pool) th.join();
     }
     // a narrow / sticky block's tables were built by choose_form above, a wide one is built by emit below
+    bool fits = true;   // the device arrays were sized at upload for any plan (scan.cu); checked all the same
     auto accept = [&](int first, int count, int A, int B) -> int {
         const Spec &S = spec[(size_t)first / 32];
         (void)count; (void)A; (void)B;
+        fits = fits && nb < pw->n_blocks_max && words + (int64_t)S.A * 8192 + (int64_t)S.B * 2048 <= pw->hq_lut_words;
+        if (!fits) return (int)kWide;
         if (S.form != kWide) {
             std::copy(S.lut.begin(), S.lut.end(), qlut.begin() + words);
             std::copy(S.kinit.begin(), S.kinit.end(), kinit.begin() + (size_t)nb * 32);
@@ -1497,7 +1551,9 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     pw->blk_lut_off.clear();
     pw->blk_motif.assign((size_t)pw->n_blocks_max * TFBS_BLOCK_SLOTS, -1);
     std::vector<int32_t> blk_AB;
-    cut_blocks(pw->lens_desc.data(), M, accept, [&](const tfbs_hits_block &K) {
+    cut_blocks(t_lens.data(), M, accept, [&](const tfbs_hits_block &K) {
+        fits = fits && nb < pw->n_blocks_max && words + (int64_t)K.A * 8192 + (int64_t)K.B * 2048 <= pw->hq_lut_words;
+        if (!fits) return;
         if (K.narrow == kWide)
             fill_block(pw, thr, order + K.first, K.count, K.A, K.B, kWide, qlut.data() + words, kinit.data() + (size_t)nb * 32);
         for (int l = 0; l < K.count; l++) pw->blk_motif[(size_t)nb * TFBS_BLOCK_SLOTS + l] = order[K.first + l];
@@ -1510,6 +1566,11 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         words += (int64_t)K.A * 8192 + (int64_t)K.B * 2048;
         nb++;
     });
+    if (!fits) {
+        pw->hq_valid = false;
+        tfbs_set_error("tfbs_scan_hits: the block plan does not fit the tables sized at upload (%d blocks, %lld words)", nb, (long long)words);
+        return TFBS_ERR_INVALID;
+    }
     pw->n_blocks = nb;
     cudaError_t e = cudaSuccess;
     if (nb > 0) {  // (no table block at all when every motif took the direct path)
@@ -1849,24 +1910,9 @@ extern "C" int tfbs_scan_hits_host_shard(tfbs_ctx *ctx, const uint8_t *ascii_hos
     return scan_hits_host_impl(ctx, ascii_host, n, seq, pwms, thr, out_host, cap, chunks, sorted, owned, shard_start, n_hits);
 }
 
-// Test hook (host only, no CUDA): run the candidate FILTER of the hits kernel on the host, with the
-// kernel's own tables (fill_block) and its 32-bit field arithmetic, so the CPU test-suite can check
-// that {candidates} is a superset of {hits} for every block form — in particular that fields never
-// carry (wide, narrow) and that the carry slack of sticky fields is sufficient.
-//   form 0: wide blocks only; 1: narrow wherever more than 32 motifs are left; 2: as 1, but sticky
-//   from TFBS_STICKY_MIN_GROUPS groups on; 3: what a scan would use (cost model / environment).
-//   plan (optional): int32[blocks][4] = {A, B, form, motifs}, n_blocks; expected (optional):
-//   double[blocks] = candidates per window start the builder expects of a narrow / sticky block.
-//   codes: n bases as 2-bit codes, one per byte (bases past the end count as 0, as in the padded device buffer)
-//   cand:  uint8[n][M][2], set to 1 where the filter passes window start p of motif m on strand s
-extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
-                                      const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand,
-                                      int32_t *plan, double *expected, int32_t *n_blocks)
+// Host-only library for the test hooks below: the fields the planning code reads, no device memory.
+static int host_library(tfbs_pwms &pw, const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax)
 {
-    if (!logodds || !lens || !thr || !codes || !cand || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1 ||
-        form < 0 || form > 3)
-        return TFBS_ERR_INVALID;
-    tfbs_pwms pw;  // host fields only
     pw.M = M;
     pw.Lmax = Lmax;
     pw.lens.assign(lens, lens + M);
@@ -1881,21 +1927,57 @@ extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens
     std::stable_sort(pw.order.begin(), pw.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
     pw.lens_desc.resize(M);
     for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
+    return TFBS_OK;
+}
+
+// Test hook (host only, no CUDA): run the candidate FILTER of the hits kernel on the host, with the
+// kernel's own tables (fill_block) and its 32-bit field arithmetic, so the CPU test-suite can check
+// that {candidates} is a superset of {hits} for every block form — in particular that fields never
+// carry (wide, narrow) and that the carry slack of sticky fields is sufficient.
+//   form 0: wide blocks only; 1: narrow wherever more than 32 motifs are left; 2: as 1, but sticky
+//   from TFBS_STICKY_MIN_GROUPS groups on; 3: what a scan would use (cost model / environment) with every
+//   motif on the tables; 4: the table side of the plan a scan really uses (the motifs on the direct path
+//   are left out and get no candidates here).
+//   plan (optional): int32[blocks][4] = {A, B, form, motifs}, n_blocks; expected (optional):
+//   double[blocks] = candidates per window start the builder expects of a narrow / sticky block.
+//   codes: n bases as 2-bit codes, one per byte (bases past the end count as 0, as in the padded device buffer)
+//   cand:  uint8[n][M][2], set to 1 where the filter passes window start p of motif m on strand s
+extern "C" int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                      const float *thr, int32_t form, const uint8_t *codes, int64_t n, uint8_t *cand,
+                                      int32_t *plan, double *expected, int32_t *n_blocks)
+{
+    if (!logodds || !lens || !thr || !codes || !cand || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1 ||
+        form < 0 || form > 4)
+        return TFBS_ERR_INVALID;
+    tfbs_pwms pw;  // host fields only
+    if (host_library(pw, logodds, lens, M, Lmax)) return TFBS_ERR_INVALID;
     memset(cand, 0, (size_t)n * M * 2);
     std::vector<uint32_t> lut((size_t)6 * 8192 + (size_t)kMaxG * 2048), kinit(32);
     auto base = [&](int64_t i) -> uint32_t { return i < n ? (codes[i] & 3u) : 0u; };
+    // form 4: the table side of the plan a scan really uses — the motifs the direct path took are left out
+    std::vector<int32_t> t_order = pw.order, t_lens = pw.lens_desc;
+    if (form == 4) {
+        std::vector<uint32_t> bitmap;
+        std::vector<uint2> hash;
+        std::vector<uint8_t> is_direct;
+        uint32_t shift = 0;
+        int dlen = 0;
+        int64_t entries = 0;
+        plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries, is_direct);
+        table_order(&pw, is_direct, t_order, t_lens);
+    }
     int nb = 0;
     double exp_block = 0.0;
     cut_blocks(
-        pw.lens_desc.data(), M,
+        t_lens.data(), (int)t_order.size(),
         [&](int first, int count, int A, int B) {
             exp_block = 0.0;
-            if (form == 3) return choose_form(&pw, thr, first, count, A, B, lut.data(), kinit.data(), &exp_block);
+            if (form >= 3) return choose_form(&pw, thr, t_order.data(), t_lens.data(), first, count, A, B, lut.data(), kinit.data(), &exp_block);
             return form == 0 ? (int)kWide : (form == 2 && A + B >= TFBS_STICKY_MIN_GROUPS ? (int)kSticky : (int)kNarrow);
         },
         [&](const tfbs_hits_block &K) {
             const int G = K.A + K.B;
-            const int32_t *motifs = pw.order.data() + K.first;
+            const int32_t *motifs = t_order.data() + K.first;
             const double e = fill_block(&pw, thr, motifs, K.count, K.A, K.B, K.narrow, lut.data(), kinit.data());
             if (plan) {
                 plan[4 * nb + 0] = K.A;
@@ -1945,26 +2027,14 @@ extern "C" int tfbs_debug_direct_lookup(const double *logodds, const int32_t *le
     if (!logodds || !lens || !thr || !codes || !cand || !info || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN || n < 1)
         return TFBS_ERR_INVALID;
     tfbs_pwms pw;  // host fields only
-    pw.M = M;
-    pw.Lmax = Lmax;
-    pw.lens.assign(lens, lens + M);
-    pw.exact_host.assign((size_t)M * 2 * TFBS_MAX_MOTIF_LEN * 4, 0.0);
-    for (int m = 0; m < M; m++) {
-        if (lens[m] < 1 || lens[m] > Lmax) return TFBS_ERR_INVALID;
-        tfbs_fill_exact(logodds, Lmax, m, lens[m], &pw.exact_host[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4],
-                        &pw.exact_host[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4]);
-    }
-    pw.order.resize(M);
-    for (int m = 0; m < M; m++) pw.order[m] = m;
-    std::stable_sort(pw.order.begin(), pw.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-    pw.lens_desc.resize(M);
-    for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
+    if (host_library(pw, logodds, lens, M, Lmax)) return TFBS_ERR_INVALID;
     std::vector<uint32_t> bitmap;
     std::vector<uint2> hash;
     uint32_t shift = 0;
     int dlen = 0;
     int64_t entries = 0;
-    const int nd = plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries);
+    std::vector<uint8_t> is_direct;
+    const int nd = plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries, is_direct);
     memset(cand, 0, (size_t)n * M * 2);
     info[0] = nd;
     info[1] = dlen;
@@ -1987,6 +2057,25 @@ extern "C" int tfbs_debug_direct_lookup(const double *logodds, const int32_t *le
             }
         }
     }
+    return TFBS_OK;
+}
+
+// Test hook (host only, no CUDA): which motifs the direct path takes for a threshold vector (is_direct[M]);
+// the choice is made per motif, so one loose threshold does not keep the rest of the library on the tables.
+extern "C" int tfbs_debug_direct_motifs(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                        const float *thr, uint8_t *is_direct)
+{
+    if (!logodds || !lens || !thr || !is_direct || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN) return TFBS_ERR_INVALID;
+    tfbs_pwms pw;  // host fields only
+    if (host_library(pw, logodds, lens, M, Lmax)) return TFBS_ERR_INVALID;
+    std::vector<uint32_t> bitmap;
+    std::vector<uint2> hash;
+    std::vector<uint8_t> flags;
+    uint32_t shift = 0;
+    int dlen = 0;
+    int64_t entries = 0;
+    plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries, flags);
+    std::copy(flags.begin(), flags.end(), is_direct);
     return TFBS_OK;
 }
 

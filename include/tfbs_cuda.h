@@ -196,12 +196,12 @@ int tfbs_host_unregister(void *ptr);
  * holds (out may be NULL to query *n_blocks).  Diagnostics for bench.py's shared-memory roofline. */
 int tfbs_pwms_hits_blocks(const tfbs_pwms *pwms, int32_t *out, int32_t cap, int32_t *n_blocks);
 
-/* The DIRECT path of the last hits scan: at sparse thresholds the motifs of at most 12 columns are not
+/* The DIRECT path of the last hits scan: at sparse thresholds the motifs of at most 14 columns are not
  * filtered through the shared-memory tables; every L-mer that reaches the threshold is enumerated on the
- * host into a 12-mer hash behind a 10-mer bitmap and the scan looks positions up in it.  n_motifs = how
- * many motifs took it (the blocks of tfbs_pwms_hits_blocks cover the rest), max_len = the longest of them,
- * keys = 12-mers in the hash; all 0 when the path was not taken (dense thresholds, very short motifs, or
- * TFBS_HITS_DIRECT=0). */
+ * host into a 12-mer hash behind a 10-mer bitmap and the scan looks positions up in it.  Chosen per motif
+ * and per threshold vector.  n_motifs = how many motifs took it (the blocks of tfbs_pwms_hits_blocks cover
+ * the rest), max_len = the longest of them, keys = 12-mers in the hash; all 0 when the path was not taken
+ * (dense thresholds, very short motifs, fewer than 32 eligible motifs, or TFBS_HITS_DIRECT=0). */
 int tfbs_pwms_hits_direct(const tfbs_pwms *pwms, int32_t *n_motifs, int32_t *max_len, int64_t *keys);
 
 /* ---- (3) DNA-shape pentamer lookup -----------------------------------------------------
@@ -293,7 +293,8 @@ int tfbs_debug_hits_block_plan(const int32_t *lens, int32_t M, int32_t narrow_ma
 
 /* The candidate FILTER of the hits kernel run on the host with the kernel's own tables and 32-bit
  * field arithmetic (no CUDA): form 0 = wide blocks, 1 = narrow, 2 = narrow + sticky, 3 = the plan a
- * scan would use (cost model).  codes = n bases as 2-bit codes, one per byte; cand = uint8[n][M][2],
+ * scan would use (cost model) with every motif on the tables, 4 = the table side of the plan a scan
+ * really uses (motifs on the direct path are left out and get no candidates here).  codes = n bases as 2-bit codes, one per byte; cand = uint8[n][M][2],
  * 1 where window start p of motif m passes on strand s.  Optional outputs: plan = int32[blocks][4]
  * {A, B, form, motifs} (room for M blocks), expected = double[blocks] candidates per window start the
  * table builder predicts for a narrow / sticky block, n_blocks.  Lets the CPU suite check that the
@@ -309,6 +310,11 @@ int tfbs_debug_hits_filter(const double *logodds, const int32_t *lens, int32_t M
  * info = {motifs on the direct path, their longest length, keys, bitmap bits set}. */
 int tfbs_debug_direct_lookup(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
                              const float *thr, const uint8_t *codes, int64_t n, uint8_t *cand, int64_t info[4]);
+/* Which motifs the direct path takes for a threshold vector: is_direct[M] (0 / 1).  The choice is made per
+ * motif — one whose own 12-mer keys are too many (loose or -inf threshold, very short motif) stays on the
+ * table filter and the rest of the library still takes the path. */
+int tfbs_debug_direct_motifs(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                             const float *thr, uint8_t *is_direct);
 
 #ifdef __cplusplus
 }

@@ -993,6 +993,43 @@ def test_hits_library_of_short_motifs_only_runs_without_a_table_block(ctx, monke
     lib.close()
 
 
+@pytest.mark.parametrize("chunks", [0, 3])
+def test_hits_direct_path_is_chosen_per_motif(ctx, chunks, monkeypatch):
+    """Heterogeneous thresholds: most of the library at a sparse rate, every 5th short motif at a dense one,
+    one at -inf (every window a hit).  The loose motifs stay on the table filter (their 12-mer keys are too
+    many), the other short motifs still take the direct path; the short motifs left behind join the tail of
+    the table order.  Hits equal the oracle's bit for bit, and the library's plan equals the host replay."""
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(39, 300, 6, 30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=2e-4, gc=0.41, seed=39, sample=50_000)
+    loose = synth.thresholds_for_rate(logodds, lens, rate=2e-2, gc=0.41, seed=40, sample=20_000)
+    short = np.flatnonzero(lens <= 14)
+    thr[short[::5]] = loose[short[::5]]
+    thr[short[1]] = -np.inf
+    n = 200_000
+    seq = synth.genome(39, 2_345_678, n)
+    seq[n // 3: n // 3 + 25] = ord("N")
+    want_direct = _lib.direct_motifs_host(logodds, lens, thr)
+    assert 32 <= want_direct.sum() < short.size and not want_direct[short[::5]].any() and not want_direct[short[1]]
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    lib = ctx.upload_pwms(logodds, lens)
+    if chunks:
+        out = np.empty(cnt + 16, dtype=_lib.HIT_DTYPE)
+        hits = ctx.scan_hits_host(seq, ctx.alloc_seq(n), lib, thr, out, chunks=chunks, sort=True).copy()
+    else:
+        enc = ctx.encode(seq)
+        hits = ctx.scan_hits(enc, lib, thr, cap=cnt + 16, sort=True)
+        enc.close()
+    n_direct, max_len, keys = lib.hits_direct()
+    assert n_direct == int(want_direct.sum()) and max_len == int(lens[want_direct].max()) and keys > 0
+    assert sum(b[3] for b in lib.hits_blocks()) == 300 - n_direct
+    gpos = np.where(hits["pos"] < 0, ~hits["pos"], hits["pos"])
+    assert hits.size == cnt and np.array_equal(gpos, pos) and np.array_equal(hits["motif"], mot)
+    assert np.array_equal((hits["pos"] < 0).astype(np.int32), strand) and np.array_equal(hits["score"], score)
+    lib.close()
+
+
 def test_hits_cost_model_picks_narrow_blocks_at_sparse_thresholds(ctx, monkeypatch):
     """At the hit densities a genome scan runs at (1e-4 per window and strand) the default plan uses
     narrow blocks for the short motifs; the plan follows the thresholds of each call."""

@@ -720,6 +720,59 @@ def test_direct_path_is_not_taken_when_it_cannot_pay(monkeypatch):
     assert _lib.direct_lookup_host(logodds, lens, thr, codes)[1]["motifs"] == 0
 
 
+def test_direct_path_is_chosen_per_motif(monkeypatch):
+    """One loose threshold must not keep the rest of the library off the direct path: a motif whose own keys
+    are too many (dense rate, -inf threshold) stays on the table filter, the others still go direct.  The
+    union of the two sides covers every oracle hit; the table side (form 4) passes nothing for direct motifs."""
+    from oracle import pssm_oracle as po
+
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(39, 200, 6, 30)
+    thr = synth.thresholds_for_rate(logodds, lens, rate=1e-4, gc=0.41, seed=39, sample=50_000)
+    homogeneous = _lib.direct_motifs_host(logodds, lens, thr)
+    assert np.array_equal(homogeneous, lens <= 14)            # sparse everywhere: every motif of <= 14 columns
+    loose = synth.thresholds_for_rate(logodds, lens, rate=2e-2, gc=0.41, seed=40, sample=20_000)
+    short = np.flatnonzero(lens <= 14)
+    thr[short[::4]] = loose[short[::4]]
+    thr[short[1]] = -np.inf
+    thr[short[2]] = np.nan                                     # no keys at all: costs nothing, goes direct
+    direct = _lib.direct_motifs_host(logodds, lens, thr)
+    expect = homogeneous.copy()
+    expect[short[::4]] = False
+    expect[short[1]] = False
+    assert np.array_equal(direct, expect) and direct.sum() >= 32
+
+    seq = synth.genome(39, 0, 60_000, gc=0.41, n_runs=False, lowercase=False)
+    codes = np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), seq).astype(np.uint8)
+    with np.errstate(invalid="ignore"):
+        pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    cand, info = _lib.direct_lookup_host(logodds, lens, thr, codes)
+    assert info["motifs"] == int(direct.sum()) and info["max_len"] == int(lens[direct].max())
+    assert cand[:, ~direct].sum() == 0
+    on_direct = direct[mot]
+    assert cand[pos[on_direct], mot[on_direct], strand[on_direct]].all()
+    filt, plan, _ = _lib.hits_filter_host(logodds, lens, thr, 4, codes, with_plan=True)
+    assert sum(b[3] for b in plan) == 200 - int(direct.sum())
+    assert filt[:, direct].sum() == 0
+    assert filt[pos[~on_direct], mot[~on_direct], strand[~on_direct]].all()
+    # the short motifs left on the tables close the length-sorted table order: the last block is sized for them
+    left_short = int((~direct & (lens <= 14)).sum())
+    assert left_short >= 10 and plan[-1][0] + plan[-1][1] <= 4
+
+
+def test_hits_table_capacity_covers_any_per_threshold_plan():
+    """The device tables are sized at upload for 32-motif blocks of the whole length-sorted library; a
+    per-threshold plan may start block i at a SHORTER motif, whose table can be the larger one (24 columns:
+    6 x 32 KB; 25 columns: 5 x 32 + 2 x 8 KB).  The sizing takes the running maximum over all shorter lengths."""
+    words = {}
+    for L in range(1, 33):
+        a, b = _lib.hits_group_plan(L)
+        words[L] = a * 8192 + b * 2048
+    assert words[24] > words[25]                               # the non-monotone step the envelope exists for
+    assert all(words[L] <= words[L + 1] for L in range(1, 16)) # monotone over the lengths the direct path can remove
+
+
 # ---- bench.py contract (CPU side) ---------------------------------------------------------------------
 def test_bench_reference_arm_prints_one_json_line_with_all_host_cores():
     """`bench.py --impl reference`: ONE JSON line on stdout with the contract's keys; the CPU arm takes its
