@@ -171,7 +171,9 @@ class MultiGpuScanner:
         self.last_ms = None
 
     def _make(self, i, logodds, cap):
-        self.workers[i] = _DeviceWorker(self.devices[i], logodds, self.lens, self.shards[i], cap)
+        # (a genome shorter than n_devices x 128 bases leaves the last shards empty: no worker for them)
+        if self.shards[i].scanned > 0:
+            self.workers[i] = _DeviceWorker(self.devices[i], logodds, self.lens, self.shards[i], cap)
 
     def _run(self, fn):
         import threading
@@ -206,6 +208,9 @@ class MultiGpuScanner:
 
         def work(i):
             w = self.workers[i]
+            if w is None:   # empty shard
+                parts[i] = np.zeros(0, dtype=_lib.HIT_DTYPE)
+                return
             sh = w.shard
             _lib.bind_thread_near(self.devices[i])
             parts[i] = w.ctx.scan_hits_host_shard(genome[sh.start: sh.scan_end], w.enc, w.lib, thresholds, w.hits,

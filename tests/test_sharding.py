@@ -220,3 +220,14 @@ def test_threads_drive_every_visible_gpu(ctx):
     got = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=list(range(ndev)))
     want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_scanner_with_more_devices_than_the_genome_has_128_base_blocks(ctx):
+    """A 200-base genome planned for three workers (contexts on the same GPU when the box has one): the
+    third shard is empty and gets no worker; the hits equal the oracle's."""
+    genome, logodds, lens, thr = _workload(n=200, M=9)
+    thr = np.full(lens.size, -5.0, dtype=np.float32)
+    got = sharding.scan_genome_multi_gpu(genome, logodds, lens, thr, devices=[0, 0, 0], cap=1 << 14)
+    want = sharding.merge_shard_hits([_oracle_hits(genome, logodds, lens, thr)])
+    assert want.size > 20 and np.array_equal(got, want)
