@@ -1269,6 +1269,7 @@ constexpr int kDirectMaxLen = 14;            // longest motif the path may take 
 constexpr int kDirectPrefixBases = 10;       // bitmap: first 10 bases
 constexpr size_t kDirectMaxEntries = (size_t)3 << 20;   // 3 Mi keys -> 8 Mi slots = 64 MB of hash
 constexpr size_t kDirectMotifMaxEntries = kDirectMaxEntries / 32;   // keys of ONE motif (both strands); more: it stays on the tables
+constexpr size_t kDirectSeedBudget = kDirectMaxEntries;             // unexpanded W-mers kept from the count pass (8 B each)
 constexpr double kDirectMaxDensity = 0.5;    // bitmap bits set: beyond this the screen stops screening (A/B on B200: 0.35 -> 0.5 gains 0.65 ms)
 
 // Keys of one (motif, strand) field.  L <= 12: every L-mer whose oracle score reaches the threshold —
@@ -1277,11 +1278,15 @@ constexpr double kDirectMaxDensity = 0.5;    // bitmap bits set: beyond this the
 // L-mer becomes 4^(12-L) keys.  L = 13 or 14: the 12-mers at columns off .. off+11 that can still reach the
 // threshold when every column outside the window scores its best (a superset of the hits: the verify pass
 // rejects the rest); the key is then taken `off` bases after the window start.
-// With entries == nullptr only the keys are counted (*count).  Returns false when more than `cap` keys.
-static bool enumerate_direct_field(const double *mat, int L, int off, float t, uint32_t value, std::vector<uint2> *entries,
-                                   size_t cap, size_t *count)
+// *count = keys of the field (4^(12-W) per enumerated W-mer, W = min(L, 12)).  `seeds` (may be nullptr)
+// receives the enumerated W-mers UNEXPANDED as {W-mer, value}, as long as they number at most `seed_cap`
+// (*seeds_complete tells whether all of them were recorded); the 12-mer keys are made from them when the
+// hash is filled (insert_direct_seeds).  Returns false when the field has more than `cap` keys.
+static bool enumerate_direct_field(const double *mat, int L, int off, float t, uint32_t value, std::vector<uint2> *seeds,
+                                   size_t seed_cap, bool *seeds_complete, size_t cap, size_t *count)
 {
     *count = 0;
+    if (seeds_complete) *seeds_complete = true;
     if (std::isnan(t)) return true;
     const int W = std::min(L, kDirectKeyBases);   // window columns off .. off+W-1
     double colmax[TFBS_MAX_MOTIF_LEN], best = 0.0, outside = 0.0;
@@ -1321,8 +1326,10 @@ static bool enumerate_direct_field(const double *mat, int L, int off, float t, u
                 for (int i = 0; i < W; i++) key |= (uint32_t)code[i] << (2 * i);
                 *count += n_suffix;
                 if (*count > cap) return false;
-                if (entries)
-                    for (uint32_t u = 0; u < n_suffix; u++) entries->push_back(make_uint2(key | (u << (2 * W)), value));
+                if (seeds) {
+                    if (seeds->size() < seed_cap) seeds->push_back(make_uint2(key, value));
+                    else if (seeds_complete) *seeds_complete = false;
+                }
             }
             code[j]++;
         } else {
@@ -1331,6 +1338,34 @@ static bool enumerate_direct_field(const double *mat, int L, int off, float t, u
         }
     }
     return true;
+}
+
+// Expand seeds (W-mers of one field) to their 4^(12-W) twelve-mer keys and enter them into the bitmap (first
+// 10 bases) and the open-addressing hash ({key, value}, linear probing, .y == 0 = empty).  Safe to call from
+// several threads at once on different seeds: a slot is claimed by a 64-bit compare-and-swap, a bitmap bit
+// set by an atomic OR.  (The position of equal keys in a probe chain may differ from run to run; a look-up
+// walks the chain to its first empty slot and reports every match, so results do not.)
+static void insert_direct_seeds(const uint2 *seeds, size_t n, int W, uint32_t *bitmap, uint2 *hash, uint32_t bits)
+{
+    static_assert(sizeof(uint2) == 8, "hash slots are claimed as 64-bit words");
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(hash);
+    const uint32_t mask = (uint32_t)(((size_t)1 << bits) - 1);
+    const uint32_t pmask = (1u << (2 * kDirectPrefixBases)) - 1u;
+    const uint32_t n_suffix = 1u << (2 * (kDirectKeyBases - W));
+    for (size_t k = 0; k < n; k++)
+        for (uint32_t u = 0; u < n_suffix; u++) {
+            const uint32_t key = seeds[k].x | (u << (2 * W));
+            const uint32_t k10 = key & pmask;
+            const uint32_t bit = 1u << (k10 & 31u);
+            if (!(__atomic_load_n(&bitmap[k10 >> 5], __ATOMIC_RELAXED) & bit)) __atomic_fetch_or(&bitmap[k10 >> 5], bit, __ATOMIC_RELAXED);
+            const unsigned long long rec = ((unsigned long long)seeds[k].y << 32) | key;   // uint2 {x = key, y = value}
+            for (uint32_t i = (key * 0x9E3779B1u) >> (32 - bits);; i = (i + 1u) & mask) {
+                unsigned long long expected = 0ull;
+                if (__atomic_load_n(&slots[i], __ATOMIC_RELAXED) == 0ull &&
+                    __atomic_compare_exchange_n(&slots[i], &expected, rec, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+                    break;
+            }
+        }
 }
 
 // Decide which motifs take the direct path for this threshold vector and build their bitmap + hash.
@@ -1358,47 +1393,67 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
     const int forced = env_int("TFBS_PLAN_THREADS");
     if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
     constexpr size_t kTooMany = SIZE_MAX;
-    std::vector<uint8_t> best_off((size_t)M * 2, 0);   // window offset chosen for every field (count pass)
-    std::vector<size_t> keys((size_t)M, kTooMany);     // keys of both strands of a motif (count pass)
-    std::vector<int32_t> taken;                        // motifs of the set being tried
-    std::vector<std::vector<uint2>> part(T);
-    // both passes run on the host's cores: count first (cheap: no suffix expansion), build only what fits
-    auto pass = [&](bool build) {
-        std::atomic<int> next{build ? 0 : M - n_max};
-        const int end = build ? (int)taken.size() : M;
+    // Count pass, on the host's cores: keys of every candidate field (for the motifs longer than the key, of
+    // the 12-column window that passes the fewest 12-mers).  The enumerated W-mers are kept as unexpanded
+    // seeds while they are few (a field of at most kDirectMotifMaxEntries seeds, kDirectSeedBudget in all),
+    // so that a plan that fits is filled from them without a second enumeration.
+    struct Field {
+        uint8_t off = 0;          // window offset inside the motif
+        bool recorded = false;    // seeds[thread][begin, begin + n) hold every W-mer of the field
+        uint32_t thread = 0;
+        size_t begin = 0, n = 0;
+    };
+    std::vector<Field> field((size_t)M * 2);
+    std::vector<size_t> keys((size_t)M, kTooMany);     // keys of both strands of a motif
+    std::vector<std::vector<uint2>> seeds(T);
+    std::atomic<size_t> seeds_total{0};
+    {
+        std::atomic<int> next{M - n_max};
         auto worker = [&](unsigned t) {
-            for (int i = next.fetch_add(1); i < end; i = next.fetch_add(1)) {
-                const int m = build ? taken[(size_t)i] : pw->order[i], L = pw->lens[m];
+            std::vector<uint2> cur, best;
+            for (int i = next.fetch_add(1); i < M; i = next.fetch_add(1)) {
+                const int m = pw->order[i], L = pw->lens[m];
                 size_t km = 0;
                 for (int s2 = 0; s2 < 2 && km != kTooMany; s2++) {
                     const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4;
-                    if (!build) {
-                        // motifs longer than the key: the 12-column window that passes the fewest 12-mers
-                        size_t best_c = kTooMany;
-                        for (int off = 0; off + std::min(L, kDirectKeyBases) <= L; off++) {
-                            size_t c2 = 0;
-                            if (enumerate_direct_field(mat, L, off, thr[m], 0u, nullptr, kDirectMaxEntries, &c2) && c2 < best_c) {
-                                best_c = c2;
-                                best_off[(size_t)m * 2 + s2] = (uint8_t)off;
-                            }
-                        }
-                        km = best_c == kTooMany ? kTooMany : km + best_c;
-                    } else {
-                        const int off = best_off[(size_t)m * 2 + s2];
+                    Field &F = field[(size_t)m * 2 + s2];
+                    size_t best_c = kTooMany;
+                    bool best_complete = false;
+                    for (int off = 0; off + std::min(L, kDirectKeyBases) <= L; off++) {
                         const uint32_t value = ((((uint32_t)m << 1) | (uint32_t)s2) << kDirectOffBits | (uint32_t)off) + 1u;
-                        size_t c = 0;
-                        enumerate_direct_field(mat, L, off, thr[m], value, &part[t], kDirectMaxEntries, &c);
+                        size_t c2 = 0;
+                        bool complete = false;
+                        cur.clear();
+                        if (enumerate_direct_field(mat, L, off, thr[m], value, &cur, kDirectMotifMaxEntries, &complete, kDirectMaxEntries, &c2) &&
+                            c2 < best_c) {
+                            best_c = c2;
+                            best_complete = complete;
+                            F.off = (uint8_t)off;
+                            best.swap(cur);
+                        }
+                    }
+                    km = best_c == kTooMany ? kTooMany : km + best_c;
+                    if (best_c != kTooMany && best_complete) {
+                        if (seeds_total.fetch_add(best.size()) + best.size() <= kDirectSeedBudget) {
+                            F.recorded = true;
+                            F.thread = t;
+                            F.begin = seeds[t].size();
+                            F.n = best.size();
+                            seeds[t].insert(seeds[t].end(), best.begin(), best.end());
+                        } else {
+                            seeds_total.fetch_sub(best.size());
+                        }
                     }
                 }
-                if (!build) keys[(size_t)m] = km;
+                keys[(size_t)m] = km;
             }
         };
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < T; t++) pool.emplace_back(worker, t);
         worker(0);
         for (auto &th : pool) th.join();
-    };
-    pass(false);
+    }
+    std::vector<int32_t> taken;   // motifs of the set being tried
     // One attempt: the motifs of at most Ld columns — all of them, or (per_motif) those with few enough keys.
     auto attempt = [&](int Ld, bool per_motif) -> int {
         int n = 0;
@@ -1417,35 +1472,51 @@ static int plan_direct(const tfbs_pwms *pw, const float *thr, std::vector<uint32
         }
         if (per_motif && (int)taken.size() == n) return 0;   // nothing left out: the whole set was tried already
         if ((int)taken.size() < 32 || total > kDirectMaxEntries) return 0;
-        for (auto &v : part) v.clear();
-        pass(true);
-        std::vector<uint2> entries;
-        entries.reserve(total);
-        for (auto &v : part) entries.insert(entries.end(), v.begin(), v.end());
+        // fill the bitmap and the hash from the seeds, field by field on the host's cores (lock-free: a slot
+        // is claimed with one compare-and-swap, a bitmap bit set with an atomic OR); a field whose seeds
+        // were not kept is enumerated again
+        uint32_t bits = 10;
+        while (((size_t)1 << bits) < 2 * total + 16) bits++;
+        hash.assign((size_t)1 << bits, make_uint2(0u, 0u));
         bitmap.assign(kDirectBitmapWords, 0u);
-        const uint32_t pmask = (1u << (2 * kDirectPrefixBases)) - 1u;
-        for (const uint2 &e : entries) bitmap[(e.x & pmask) >> 5] |= 1u << (e.x & 31u);
+        {
+            std::atomic<size_t> next{0};
+            auto worker = [&]() {
+                std::vector<uint2> again;
+                for (size_t k = next.fetch_add(1); k < 2 * taken.size(); k = next.fetch_add(1)) {
+                    const int m = taken[k >> 1], s2 = (int)(k & 1), L = pw->lens[m];
+                    const Field &F = field[(size_t)m * 2 + s2];
+                    const uint2 *src = F.recorded ? seeds[F.thread].data() + F.begin : nullptr;
+                    size_t n_src = F.n;
+                    if (!F.recorded) {
+                        const double *mat = pw->exact_host.data() + ((size_t)(m * 2 + s2) * TFBS_MAX_MOTIF_LEN) * 4;
+                        const uint32_t value = ((((uint32_t)m << 1) | (uint32_t)s2) << kDirectOffBits | (uint32_t)F.off) + 1u;
+                        size_t c = 0;
+                        again.clear();
+                        enumerate_direct_field(mat, L, F.off, thr[m], value, &again, SIZE_MAX, nullptr, kDirectMaxEntries, &c);
+                        src = again.data();
+                        n_src = again.size();
+                    }
+                    insert_direct_seeds(src, n_src, std::min(L, kDirectKeyBases), bitmap.data(), hash.data(), bits);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < T; t++) pool.emplace_back(worker);
+            worker();
+            for (auto &th : pool) th.join();
+        }
         size_t bits_set = 0;
         for (uint32_t w : bitmap) bits_set += (size_t)__builtin_popcount(w);
         double max_density = kDirectMaxDensity;
         if (const char *env = getenv("TFBS_DIRECT_DENSITY")) max_density = atof(env);   // A/B measurements
         if ((double)bits_set > max_density * (double)(1u << (2 * kDirectPrefixBases))) return 0;
-        uint32_t bits = 10;
-        while (((size_t)1 << bits) < 2 * entries.size() + 16) bits++;
-        hash.assign((size_t)1 << bits, make_uint2(0u, 0u));
-        const uint32_t mask = (uint32_t)(((size_t)1 << bits) - 1);
-        for (const uint2 &e : entries) {
-            uint32_t i = (e.x * 0x9E3779B1u) >> (32 - bits);
-            while (hash[i].y != 0u) i = (i + 1u) & mask;
-            hash[i] = e;
-        }
         *hash_shift = 32 - bits;
         *direct_len = 0;
         for (int m : taken) {
             is_direct[(size_t)m] = 1;
             *direct_len = std::max(*direct_len, (int)pw->lens[m]);
         }
-        *n_entries = (int64_t)entries.size();
+        *n_entries = (int64_t)total;
         return (int)taken.size();
     };
     for (bool per_motif : {false, true})
