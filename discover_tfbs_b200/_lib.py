@@ -78,6 +78,7 @@ _PROTOTYPES = {
     "tfbs_pwms_hits_blocks": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.POINTER(_i32)]),
     "tfbs_debug_direct_lookup": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "tfbs_debug_direct_motifs": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "tfbs_debug_hits_plan_checksum": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tfbs_debug_hits_filter": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
 }
 
@@ -182,6 +183,21 @@ def direct_lookup_host(logodds, lens, thr, codes):
     info = np.zeros(4, dtype=np.int64)
     _check(load().tfbs_debug_direct_lookup(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), _ptr(cd), int(cd.size), _ptr(out), _ptr(info)))
     return out, {"motifs": int(info[0]), "max_len": int(info[1]), "keys": int(info[2]), "bitmap_bits": int(info[3])}
+
+
+def hits_plan_checksum_host(logodds, lens, thr):
+    """The complete plan a hits scan makes for a threshold vector, built on the host by the scan's own code
+    (test hook, no GPU): ({blocks, words, tables, descriptors, direct_motifs, direct_keys}, [(A, B, form, motifs)])."""
+    lo = np.ascontiguousarray(logodds, dtype=np.float64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    th = np.ascontiguousarray(thr, dtype=np.float32)
+    M, Lmax = int(lo.shape[0]), int(lo.shape[1])
+    out = np.zeros(6, dtype=np.uint64)
+    plan = np.zeros((M, 4), dtype=np.int32)
+    _check(load().tfbs_debug_hits_plan_checksum(_ptr(lo), _ptr(ln), M, Lmax, _ptr(th), _ptr(out), _ptr(plan)))
+    keys = ("blocks", "words", "tables", "descriptors", "direct_motifs", "direct_keys")
+    info = {k: int(v) for k, v in zip(keys, out)}
+    return info, [tuple(int(v) for v in row) for row in plan[: info["blocks"]]]
 
 
 def direct_motifs_host(logodds, lens, thr) -> np.ndarray:

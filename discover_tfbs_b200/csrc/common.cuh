@@ -139,6 +139,7 @@ struct tfbs_shapes {
 
 int tfbs_scratch_reserve(tfbs_scratch &s, size_t bytes);
 void tfbs_hits_group_plan(int L, int *A_out, int *B_out);
+void tfbs_hits_order_and_capacity(tfbs_pwms *p, const int32_t *lens);
 void tfbs_dense_quantise(const double *F, const double *R, int L, int *K_out, int *G_out, int *e_out,
                          int32_t *neg_thr, std::vector<int2> &lut);
 // Exact scoring matrices of motif m: F = log-odds as given, R = reverse complement (columns reversed,

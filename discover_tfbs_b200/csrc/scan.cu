@@ -267,6 +267,34 @@ void tfbs_dense_quantise(const double *F, const double *R, int L, int *K_out, in
     *neg_thr = has_inf ? (int32_t)(-Rq) : INT32_MIN;
 }
 
+// Hits mode, library-level host state: motifs sorted by descending length, and the capacity of the device
+// arrays.  The cut into blocks (32 motifs with 16-bit filter fields or 64 with 8-bit fields) depends on the
+// thresholds and is made with the filter tables (plan_hits_tables in scan_hits.cu); the arrays are sized for
+// the largest plan, 32 motifs per block throughout.  A per-threshold plan leaves some short motifs to the
+// direct path, so block i may start at a motif SHORTER than lens_desc[32 i]; the table of a shorter motif
+// can be the larger one — 24 columns take 6 x 32 KB, 25 columns 5 x 32 + 2 x 8 KB — hence the running
+// maximum over all lengths up to it.
+void tfbs_hits_order_and_capacity(tfbs_pwms *p, const int32_t *lens)
+{
+    const int M = p->M;
+    p->order.resize(M);
+    for (int m = 0; m < M; m++) p->order[m] = m;
+    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    p->lens_desc.resize(M);
+    for (int i = 0; i < M; i++) p->lens_desc[i] = lens[p->order[i]];
+    p->n_blocks = 0;
+    p->n_blocks_max = (M + 31) / 32;
+    int64_t words = 0, words_upto[TFBS_MAX_MOTIF_LEN + 1] = {0};
+    for (int L = 1; L <= TFBS_MAX_MOTIF_LEN; L++) {
+        int A = 0, B = 1;
+        tfbs_hits_group_plan(L, &A, &B);
+        words_upto[L] = std::max(words_upto[L - 1], (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32);
+    }
+    for (int i = 0; i < M; i += 32) words += words_upto[p->lens_desc[i]];
+    p->hits_lut_bytes = (size_t)words_upto[p->lens_desc[0]] * 4;
+    p->hq_lut_words = words;
+}
+
 extern "C" {
 
 int tfbs_debug_dense_tables(const double *logodds, int32_t L, int32_t *K, int32_t *G, int32_t *scale_exp,
@@ -359,30 +387,9 @@ int tfbs_pwm_upload(tfbs_ctx *ctx, const double *logodds, const int32_t *lens, i
     p->Gmax = Gmax;
     p->lut_entries = (int64_t)lut.size();
 
-    // hits mode: motifs sorted by descending length.  The cut into blocks (32 motifs with 16-bit filter
-    // fields or 64 with 8-bit fields) depends on the thresholds and is made with the filter tables
-    // (tfbs_build_hits_tables in scan_hits.cu); here the device arrays are sized for the largest plan,
-    // 32 motifs per block throughout.
-    p->order.resize(M);
-    for (int m = 0; m < M; m++) p->order[m] = m;
-    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-    p->lens_desc.resize(M);
-    for (int i = 0; i < M; i++) p->lens_desc[i] = lens[p->order[i]];
-    p->n_blocks = 0;
-    p->n_blocks_max = (M + 31) / 32;
-    // (A per-threshold plan leaves some short motifs to the direct path, so block i may start at a motif
-    // SHORTER than lens_desc[32 i]; the table of a shorter motif can be the larger one — 24 columns take
-    // 6 x 32 KB, 25 columns 5 x 32 + 2 x 8 KB — hence the running maximum over all lengths up to it.)
-    int64_t words = 0, words_upto[TFBS_MAX_MOTIF_LEN + 1] = {0};
-    for (int L = 1; L <= TFBS_MAX_MOTIF_LEN; L++) {
-        int A = 0, B = 1;
-        tfbs_hits_group_plan(L, &A, &B);
-        words_upto[L] = std::max(words_upto[L - 1], (int64_t)A * 256 * 32 + (int64_t)B * 64 * 32);
-    }
-    for (int i = 0; i < M; i += 32) words += words_upto[p->lens_desc[i]];
-    p->hits_lut_bytes = (size_t)words_upto[p->lens_desc[0]] * 4;
+    // hits mode: length-sorted motif order and the capacity of the per-threshold device arrays
+    tfbs_hits_order_and_capacity(p, lens);
     p->exact_host = exact;
-    p->hq_lut_words = words;
 
     cudaError_t e = cudaMalloc(&p->exact, exact.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&p->exact2, exact2.size() * sizeof(double));

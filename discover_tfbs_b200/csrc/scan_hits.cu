@@ -1053,15 +1053,18 @@ static void cut_blocks(const int32_t *lens_desc, int M, Accept accept, Emit emit
 // and kinit (32 words) are overwritten.  Everything rounds in the direction that keeps {candidates} a
 // superset of {hits}.  Returns the expected number of candidates per window start (all fields of the
 // block, uniform i.i.d. bases) for a narrow or sticky block, 0 for a wide one (not needed by the model).
-static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *motifs, int count, int A, int B,
-                         int mode, uint32_t *lut, uint32_t *kinit)
+//
+// fill_block_lanes does the work for the motif slots on lanes [lane0, lane1) only — a lane's table words and
+// its initial value belong to that lane alone, so disjoint lane ranges of one block can be filled by
+// different host threads — and expects `lut` zeroed and `kinit` poisoned by the caller; field_expected
+// (may be nullptr) receives the expected candidates of every field, [slot][strand].
+static void fill_block_lanes(const tfbs_pwms *pw, const float *thr, const int32_t *motifs, int count, int A, int B,
+                             int mode, uint32_t *lut, uint32_t *kinit, int lane0, int lane1, double *field_expected)
 {
     const int G = A + B;
     const bool narrow = mode != kWide;
     const int FB = narrow ? 8 : 16;                   // field width
     const int fmax = (1 << (FB - 1)) - 1;             // 0x7F / 0x7FFF: largest value with the flag bit clear
-    std::fill(lut, lut + (size_t)A * 8192 + (size_t)B * 2048, 0u);
-    for (int lane = 0; lane < 32; lane++) kinit[lane] = narrow ? kPoisonNarrow : kPoison;
     // group g: first column, width, table offset (words) inside the block table
     int gcol[2 * kMaxG], gk[2 * kMaxG], goff[2 * kMaxG];
     for (int g = 0; g < G; g++) {
@@ -1070,10 +1073,10 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
         goff[g] = g < A ? g * 256 * 32 : A * 256 * 32 + (g - A) * 64 * 32;
     }
     std::vector<double> ent((size_t)G * 256);  // double k-mer partial sums of one (motif, strand)
-    double expected = 0.0;
     for (int l = 0; l < count; l++) {
         const int m = motifs[l];
         const int lane = l & 31, half = l >> 5;
+        if (lane < lane0 || lane >= lane1) continue;
         const int L = pw->lens[m];
         const float t = thr[m];
         for (int s = 0; s < 2; s++) {
@@ -1187,13 +1190,14 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
 
             // Steps and entry cap.  No carry out of a field needs
             //   (fmax - Dq - slack) + Gm * capq <= 2 * fmax + 1   with   Dq >= dq_max.
+            double expected = 0.0;   // of this field
             if (mode == kWide) {
                 const int dq_max = 0x7FFF / G - 3;  // block-wide bound; an entry above the budget kills alone
                 quantise(dq_max, dq_max + 2, true);
             } else if (mode == kSticky) {
                 // sticky fields may wrap (their flag is kept by the OR): entries <= 127, and `slack` steps
                 // of the field absorb the carries a wrapping neighbour sends in
-                expected += quantise(125 - slack, 127, true);  // slack <= 8: >= 117 steps at any G
+                expected = quantise(125 - slack, 127, true);  // slack <= 8: >= 117 steps at any G
             } else {
                 // Plain 8-bit fields must not wrap.  Either every entry above the budget kills alone
                 // (capq = dq_max + 2, which leaves only (128 - 2 Gm) / (Gm - 1) steps), or the steps are
@@ -1215,11 +1219,45 @@ static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *m
                         }
                     }
                 }
-                expected += quantise(best_dq, best_cap, true);
+                expected = quantise(best_dq, best_cap, true);
             }
+            if (field_expected) field_expected[l * 2 + s] = expected;
         }
     }
-    return narrow ? expected : 0.0;
+}
+
+// Expected candidates per window start of a block from its fields' values, summed in slot / strand order
+// (the order is fixed so that the cost model decides the same whichever threads filled the lanes).
+static double sum_field_expected(const double *field_expected, int count)
+{
+    double expected = 0.0;
+    for (int i = 0; i < 2 * count; i++) expected += field_expected[i];
+    return expected;
+}
+
+static double fill_block(const tfbs_pwms *pw, const float *thr, const int32_t *motifs, int count, int A, int B,
+                         int mode, uint32_t *lut, uint32_t *kinit)
+{
+    std::fill(lut, lut + (size_t)A * 8192 + (size_t)B * 2048, 0u);
+    for (int lane = 0; lane < 32; lane++) kinit[lane] = mode != kWide ? kPoisonNarrow : kPoison;
+    double field_expected[2 * TFBS_BLOCK_SLOTS] = {0.0};
+    fill_block_lanes(pw, thr, motifs, count, A, B, mode, lut, kinit, 0, 32, field_expected);
+    return mode != kWide ? sum_field_expected(field_expected, count) : 0.0;
+}
+
+// The cost model's choice for a block of G groups that would replace two wide blocks of G and G2 groups,
+// given the candidates per window start its sticky and its plain narrow tables are expected to pass.  The
+// sticky filter (>= 117 steps) also estimates the candidates of the wide form: measured, it passes about
+// 1.5x as many.
+static int cheapest_form(int G, int G2, double c_sticky, double c_narrow)
+{
+    const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
+    const double cost_wide = (double)(G + G2) + kCandidateCost[kWide] * c_sticky / 1.5;
+    const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
+    const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
+    if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) return kNarrow;
+    if (cost_sticky <= cost_wide) return kSticky;
+    return kWide;
 }
 
 // Form of the block made of motifs order[first, first + count) (count > 32; `order` = the motifs on the table
@@ -1245,23 +1283,13 @@ static int choose_form(const tfbs_pwms *pw, const float *thr, const int32_t *ord
     // groups of the second of the two wide blocks a narrow block replaces
     int A2 = 0, B2 = 1;
     tfbs_hits_group_plan(lens_desc[first + 32], &A2, &B2);
-    const bool can_stick = G >= TFBS_STICKY_MIN_GROUPS;
-    // the sticky filter (>= 117 steps) also estimates the candidates of the wide form: measured,
-    // it passes about 1.5x as many
+    // the sticky filter (>= 117 steps) also estimates the candidates of the wide form
     const double c_sticky = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
     const double c_narrow = fill_block(pw, thr, motifs, count, A, B, kNarrow, lut, kinit);
-    const double cost_wide = (double)(G + A2 + B2) + kCandidateCost[kWide] * c_sticky / 1.5;
-    const double cost_narrow = (double)G + kCandidateCost[kNarrow] * c_narrow;
-    const double cost_sticky = can_stick ? kStickyLoad * G + kCandidateCost[kSticky] * c_sticky : 1e300;
-    if (cost_narrow <= cost_wide && cost_narrow <= cost_sticky) {  // tables are in place
-        *expected = c_narrow;
-        return kNarrow;
-    }
-    if (cost_sticky <= cost_wide) {
-        *expected = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
-        return kSticky;
-    }
-    return kWide;
+    const int form = cheapest_form(G, A2 + B2, c_sticky, c_narrow);
+    if (form == kNarrow) *expected = c_narrow;  // tables are in place
+    if (form == kSticky) *expected = fill_block(pw, thr, motifs, count, A, B, kSticky, lut, kinit);
+    return form;
 }
 
 // ---- direct path planning (host) ------------------------------------------------------------------------
@@ -1541,27 +1569,34 @@ static void table_order(const tfbs_pwms *pw, const std::vector<uint8_t> &is_dire
     }
 }
 
-// Plan the blocks and quantise their tables for a threshold vector; cached per threshold vector.
-int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
+// Everything a hits scan needs for one threshold vector, planned on the host (no CUDA): which motifs take
+// the direct path (bitmap + hash), how the others are cut into blocks, each block's form and filter table.
+struct HitsPlan {
+    int n_direct = 0, direct_len = 0;
+    int64_t direct_entries = 0;
+    uint32_t direct_shift = 0;
+    std::vector<uint32_t> direct_bitmap;
+    std::vector<uint2> direct_hash;
+    int nb = 0;
+    int64_t words = 0;                   // table words of all blocks
+    std::vector<uint32_t> qlut, kinit;   // [words], [nb][32]
+    std::vector<int32_t> blk_A, blk_B, blk_narrow, blk_count, blk_lut_off, blk_AB, blk_motif;  // [nb] x6, [n_blocks_max][64]
+};
+
+// Plan the blocks and quantise their tables for a threshold vector.  Reads only the host fields of `pw`
+// (lens, exact_host, order, lens_desc, hq_lut_words, n_blocks_max).
+static int plan_hits_tables(const tfbs_pwms *pw, const float *thr, HitsPlan &H)
 {
     const int Mall = pw->M;
-    if (pw->hq_valid && pw->hq_thr.size() == (size_t)Mall && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * Mall) == 0)
-        return TFBS_OK;
-    pw->hq_valid = false;   // the device tables are overwritten from here on
     // short motifs may bypass the table filter altogether (direct path); the blocks below are cut from the
     // remaining M motifs
-    std::vector<uint32_t> d_bitmap;
-    std::vector<uint2> d_hash;
-    uint32_t d_shift = 0;
-    int d_len = 0;
-    int64_t d_entries = 0;
     std::vector<uint8_t> is_direct;
-    const int n_direct = plan_direct(pw, thr, d_bitmap, d_hash, &d_shift, &d_len, &d_entries, is_direct);
-    const int M = Mall - n_direct;
+    H.n_direct = plan_direct(pw, thr, H.direct_bitmap, H.direct_hash, &H.direct_shift, &H.direct_len, &H.direct_entries, is_direct);
+    const int M = Mall - H.n_direct;
     std::vector<int32_t> t_order, t_lens;   // the motifs left on the table filter, longest first
     table_order(pw, is_direct, t_order, t_lens);
-    std::vector<uint32_t> qlut((size_t)pw->hq_lut_words, 0u);
-    std::vector<uint32_t> kinit((size_t)pw->n_blocks_max * 32, kPoison);
+    H.qlut.assign((size_t)pw->hq_lut_words, 0u);
+    H.kinit.assign((size_t)pw->n_blocks_max * 32, kPoison);
     int64_t words = 0;   // table words of the blocks emitted so far
     int nb = 0;
     const int32_t *order = t_order.data();
@@ -1571,7 +1606,9 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     // one block after the other took 0.2 - 0.3 s per new threshold vector, ten times the scan.)
     struct Spec {
         int form = -1, A = 0, B = 0, count = 0;
-        std::vector<uint32_t> lut, kinit;
+        std::vector<uint32_t> lut, kinit;     // tables of the chosen form (narrow or sticky)
+        std::vector<uint32_t> lut2, kinit2;   // the sticky candidate while both are being filled
+        double fe[2][2 * TFBS_BLOCK_SLOTS];   // expected candidates of every field: [narrow, sticky][slot][strand]
     };
     std::vector<Spec> spec((size_t)(M + 31) / 32);
     std::vector<int> starts;
@@ -1584,25 +1621,61 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
     {
         cpu_set_t set;
         unsigned cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? (unsigned)CPU_COUNT(&set) : std::thread::hardware_concurrency();
-        unsigned T = std::max(1u, std::min<unsigned>(std::min(cores, 32u), (unsigned)starts.size()));
+        const bool forced_form = env_int("TFBS_HITS_NARROW") >= 0 || env_int("TFBS_HITS_STICKY") >= 0;
+        // work items: a whole start when the form is forced from the environment (choose_form), else one
+        // quarter of the lanes of one candidate form of one start — a lane's table words are its own, so
+        // the pieces of a block are filled independently and 16 or 32 cores stay busy with 10 - 20 starts
+        constexpr int kLaneChunks = 4, kLanesPerChunk = 32 / kLaneChunks;
+        const size_t n_items = forced_form ? starts.size() : starts.size() * 2 * kLaneChunks;
+        unsigned T = std::max<size_t>(1, std::min<size_t>(std::min(cores, 32u), n_items));
         const int forced = env_int("TFBS_PLAN_THREADS");  // 1 = plan in the calling thread
         if (forced >= 1) T = std::min<unsigned>(T, (unsigned)forced);
+        for (int i : starts) {
+            Spec &S = spec[(size_t)i / 32];
+            const size_t n_words = (size_t)S.A * 8192 + (size_t)S.B * 2048;
+            S.lut.assign(n_words, 0u);
+            S.kinit.assign(32, forced_form ? kPoison : kPoisonNarrow);
+            if (!forced_form) {
+                S.lut2.assign(n_words, 0u);
+                S.kinit2.assign(32, kPoisonNarrow);
+                std::fill(&S.fe[0][0], &S.fe[0][0] + 2 * 2 * TFBS_BLOCK_SLOTS, 0.0);
+            }
+        }
         std::atomic<size_t> next{0};
         auto worker = [&]() {
-            for (size_t k = next.fetch_add(1); k < starts.size(); k = next.fetch_add(1)) {
-                Spec &S = spec[(size_t)starts[k] / 32];
-                S.lut.assign((size_t)S.A * 8192 + (size_t)S.B * 2048, 0u);
-                S.kinit.assign(32, kPoison);
-                double expected;
-                S.form = choose_form(pw, thr, order, t_lens.data(), starts[k], S.count, S.A, S.B, S.lut.data(), S.kinit.data(), &expected);
+            for (size_t k = next.fetch_add(1); k < n_items; k = next.fetch_add(1)) {
+                if (forced_form) {
+                    Spec &S = spec[(size_t)starts[k] / 32];
+                    double expected;
+                    S.form = choose_form(pw, thr, order, t_lens.data(), starts[k], S.count, S.A, S.B, S.lut.data(), S.kinit.data(), &expected);
+                    continue;
+                }
+                const int first = starts[k / (2 * kLaneChunks)];
+                const int sticky = (int)(k / kLaneChunks) & 1, chunk = (int)(k % kLaneChunks);
+                Spec &S = spec[(size_t)first / 32];
+                fill_block_lanes(pw, thr, order + first, S.count, S.A, S.B, sticky ? kSticky : kNarrow,
+                                 sticky ? S.lut2.data() : S.lut.data(), sticky ? S.kinit2.data() : S.kinit.data(),
+                                 chunk * kLanesPerChunk, (chunk + 1) * kLanesPerChunk, S.fe[sticky]);
             }
         };
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < T; t++) pool.emplace_back(worker);
         worker();
         for (auto &th : pool) th.join();
+        if (!forced_form)
+            for (int i : starts) {
+                Spec &S = spec[(size_t)i / 32];
+                int A2 = 0, B2 = 1;   // groups of the second of the two wide blocks a narrow block replaces
+                tfbs_hits_group_plan(t_lens[(size_t)i + 32], &A2, &B2);
+                S.form = cheapest_form(S.A + S.B, A2 + B2, sum_field_expected(S.fe[1], S.count), sum_field_expected(S.fe[0], S.count));
+                if (S.form == kSticky) {
+                    S.lut.swap(S.lut2);
+                    S.kinit.swap(S.kinit2);
+                }
+                std::vector<uint32_t>().swap(S.lut2);
+            }
     }
-    // a narrow / sticky block's tables were built by choose_form above, a wide one is built by emit below
+    // a narrow / sticky block's tables were built above, a wide one is built by emit below
     bool fits = true;   // the device arrays were sized at upload for any plan (scan.cu); checked all the same
     auto accept = [&](int first, int count, int A, int B) -> int {
         const Spec &S = spec[(size_t)first / 32];
@@ -1610,44 +1683,59 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         fits = fits && nb < pw->n_blocks_max && words + (int64_t)S.A * 8192 + (int64_t)S.B * 2048 <= pw->hq_lut_words;
         if (!fits) return (int)kWide;
         if (S.form != kWide) {
-            std::copy(S.lut.begin(), S.lut.end(), qlut.begin() + words);
-            std::copy(S.kinit.begin(), S.kinit.end(), kinit.begin() + (size_t)nb * 32);
+            std::copy(S.lut.begin(), S.lut.end(), H.qlut.begin() + words);
+            std::copy(S.kinit.begin(), S.kinit.end(), H.kinit.begin() + (size_t)nb * 32);
         }
         return S.form;
     };
-    pw->blk_A.clear();
-    pw->blk_B.clear();
-    pw->blk_narrow.clear();
-    pw->blk_count.clear();
-    pw->blk_lut_off.clear();
-    pw->blk_motif.assign((size_t)pw->n_blocks_max * TFBS_BLOCK_SLOTS, -1);
-    std::vector<int32_t> blk_AB;
+    H.blk_motif.assign((size_t)pw->n_blocks_max * TFBS_BLOCK_SLOTS, -1);
     cut_blocks(t_lens.data(), M, accept, [&](const tfbs_hits_block &K) {
         fits = fits && nb < pw->n_blocks_max && words + (int64_t)K.A * 8192 + (int64_t)K.B * 2048 <= pw->hq_lut_words;
         if (!fits) return;
         if (K.narrow == kWide)
-            fill_block(pw, thr, order + K.first, K.count, K.A, K.B, kWide, qlut.data() + words, kinit.data() + (size_t)nb * 32);
-        for (int l = 0; l < K.count; l++) pw->blk_motif[(size_t)nb * TFBS_BLOCK_SLOTS + l] = order[K.first + l];
-        pw->blk_A.push_back(K.A);
-        pw->blk_B.push_back(K.B);
-        pw->blk_narrow.push_back(K.narrow);
-        pw->blk_count.push_back(K.count);
-        pw->blk_lut_off.push_back((int32_t)words);
-        blk_AB.push_back((K.narrow << 16) | (K.A << 8) | K.B);
+            fill_block(pw, thr, order + K.first, K.count, K.A, K.B, kWide, H.qlut.data() + words, H.kinit.data() + (size_t)nb * 32);
+        for (int l = 0; l < K.count; l++) H.blk_motif[(size_t)nb * TFBS_BLOCK_SLOTS + l] = order[K.first + l];
+        H.blk_A.push_back(K.A);
+        H.blk_B.push_back(K.B);
+        H.blk_narrow.push_back(K.narrow);
+        H.blk_count.push_back(K.count);
+        H.blk_lut_off.push_back((int32_t)words);
+        H.blk_AB.push_back((K.narrow << 16) | (K.A << 8) | K.B);
         words += (int64_t)K.A * 8192 + (int64_t)K.B * 2048;
         nb++;
     });
+    H.nb = nb;
+    H.words = words;
     if (!fits) {
-        pw->hq_valid = false;
         tfbs_set_error("tfbs_scan_hits: the block plan does not fit the tables sized at upload (%d blocks, %lld words)", nb, (long long)words);
         return TFBS_ERR_INVALID;
     }
+    return TFBS_OK;
+}
+
+// Plan (host) + upload of the filter tables of a threshold vector; cached per threshold vector.
+int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
+{
+    const int Mall = pw->M;
+    if (pw->hq_valid && pw->hq_thr.size() == (size_t)Mall && std::memcmp(pw->hq_thr.data(), thr, sizeof(float) * Mall) == 0)
+        return TFBS_OK;
+    pw->hq_valid = false;   // the device tables are overwritten from here on
+    HitsPlan H;
+    int rc = plan_hits_tables(pw, thr, H);
+    if (rc) return rc;
+    const int nb = H.nb;
+    pw->blk_A = H.blk_A;
+    pw->blk_B = H.blk_B;
+    pw->blk_narrow = H.blk_narrow;
+    pw->blk_count = H.blk_count;
+    pw->blk_lut_off = H.blk_lut_off;
+    pw->blk_motif = H.blk_motif;
     pw->n_blocks = nb;
     cudaError_t e = cudaSuccess;
     if (nb > 0) {  // (no table block at all when every motif took the direct path)
-        e = cudaMemcpy(pw->hq_lut_dev, qlut.data(), (size_t)words * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, kinit.data(), (size_t)nb * 32 * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(pw->blk_AB_dev, blk_AB.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(pw->hq_lut_dev, H.qlut.data(), (size_t)H.words * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->hq_kinit_dev, H.kinit.data(), (size_t)nb * 32 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->blk_AB_dev, H.blk_AB.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pw->blk_lut_off_dev, pw->blk_lut_off.data(), (size_t)nb * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pw->blk_motif_dev, pw->blk_motif.data(), (size_t)nb * TFBS_BLOCK_SLOTS * 4, cudaMemcpyHostToDevice);
     }
@@ -1655,10 +1743,11 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
         tfbs_set_error("tfbs_scan_hits: uploading filter tables failed: %s", cudaGetErrorString(e));
         return TFBS_ERR_CUDA;
     }
-    pw->n_direct = n_direct;
-    pw->direct_len = d_len;
-    pw->direct_entries = d_entries;
-    if (n_direct > 0) {
+    pw->n_direct = H.n_direct;
+    pw->direct_len = H.direct_len;
+    pw->direct_entries = H.direct_entries;
+    if (H.n_direct > 0) {
+        const std::vector<uint2> &d_hash = H.direct_hash;
         if (!pw->direct_bitmap_dev) e = cudaMalloc(&pw->direct_bitmap_dev, (size_t)kDirectBitmapWords * 4);
         if (e == cudaSuccess && pw->direct_hash_slots_dev < d_hash.size()) {
             if (pw->direct_hash_dev) cudaFree(pw->direct_hash_dev);
@@ -1667,14 +1756,14 @@ int tfbs_build_hits_tables(tfbs_pwms *pw, const float *thr)
             e = cudaMalloc(&pw->direct_hash_dev, d_hash.size() * sizeof(uint2));
             if (e == cudaSuccess) pw->direct_hash_slots_dev = d_hash.size();
         }
-        if (e == cudaSuccess) e = cudaMemcpy(pw->direct_bitmap_dev, d_bitmap.data(), (size_t)kDirectBitmapWords * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pw->direct_bitmap_dev, H.direct_bitmap.data(), (size_t)kDirectBitmapWords * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pw->direct_hash_dev, d_hash.data(), d_hash.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             tfbs_set_error("tfbs_scan_hits: uploading the direct-path tables failed: %s", cudaGetErrorString(e));
             return e == cudaErrorMemoryAllocation ? TFBS_ERR_NOMEM : TFBS_ERR_CUDA;
         }
         pw->direct_hash_mask = (uint32_t)(d_hash.size() - 1);
-        pw->direct_hash_shift = d_shift;
+        pw->direct_hash_shift = H.direct_shift;
     }
     pw->hq_thr.assign(thr, thr + Mall);
     pw->hq_valid = true;
@@ -1993,11 +2082,7 @@ static int host_library(tfbs_pwms &pw, const double *logodds, const int32_t *len
         tfbs_fill_exact(logodds, Lmax, m, lens[m], &pw.exact_host[((size_t)m * 2 + 0) * TFBS_MAX_MOTIF_LEN * 4],
                         &pw.exact_host[((size_t)m * 2 + 1) * TFBS_MAX_MOTIF_LEN * 4]);
     }
-    pw.order.resize(M);
-    for (int m = 0; m < M; m++) pw.order[m] = m;
-    std::stable_sort(pw.order.begin(), pw.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-    pw.lens_desc.resize(M);
-    for (int i = 0; i < M; i++) pw.lens_desc[i] = lens[pw.order[i]];
+    tfbs_hits_order_and_capacity(&pw, lens);
     return TFBS_OK;
 }
 
@@ -2147,6 +2232,47 @@ extern "C" int tfbs_debug_direct_motifs(const double *logodds, const int32_t *le
     int64_t entries = 0;
     plan_direct(&pw, thr, bitmap, hash, &shift, &dlen, &entries, flags);
     std::copy(flags.begin(), flags.end(), is_direct);
+    return TFBS_OK;
+}
+
+// Test hook (host only, no CUDA): the COMPLETE plan a scan makes for a threshold vector (plan_hits_tables:
+// direct-path choice, speculative parallel block planning, the cut, every filter table) reduced to
+// checksums, so that the CPU suite can pin the plan across refactorings and thread counts:
+// out = {blocks, table words, FNV-1a of the filter tables + initial field values, FNV-1a of the block
+// descriptors (A, B, form, count, table offset, motif slots), motifs on the direct path, direct keys}.
+// plan (optional, room for M blocks): int32[blocks][4] = {A, B, form, motifs}.
+extern "C" int tfbs_debug_hits_plan_checksum(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                             const float *thr, uint64_t out[6], int32_t *plan)
+{
+    if (!logodds || !lens || !thr || !out || M < 1 || Lmax < 1 || Lmax > TFBS_MAX_MOTIF_LEN) return TFBS_ERR_INVALID;
+    tfbs_pwms pw;  // host fields only
+    if (host_library(pw, logodds, lens, M, Lmax)) return TFBS_ERR_INVALID;
+    HitsPlan H;
+    const int rc = plan_hits_tables(&pw, thr, H);
+    if (rc) return rc;
+    auto fnv = [](uint64_t h, const void *data, size_t bytes) {
+        const uint8_t *p = static_cast<const uint8_t *>(data);
+        for (size_t i = 0; i < bytes; i++) h = (h ^ p[i]) * 0x100000001B3ull;
+        return h;
+    };
+    uint64_t ht = 0xCBF29CE484222325ull, hb = 0xCBF29CE484222325ull;
+    ht = fnv(ht, H.qlut.data(), (size_t)H.words * 4);
+    ht = fnv(ht, H.kinit.data(), (size_t)H.nb * 32 * 4);
+    for (const std::vector<int32_t> *v : {&H.blk_A, &H.blk_B, &H.blk_narrow, &H.blk_count, &H.blk_lut_off, &H.blk_AB})
+        hb = fnv(hb, v->data(), v->size() * 4);
+    hb = fnv(hb, H.blk_motif.data(), (size_t)H.nb * TFBS_BLOCK_SLOTS * 4);
+    out[0] = (uint64_t)H.nb;
+    out[1] = (uint64_t)H.words;
+    out[2] = ht;
+    out[3] = hb;
+    out[4] = (uint64_t)H.n_direct;
+    out[5] = (uint64_t)H.direct_entries;
+    for (int b = 0; plan && b < H.nb; b++) {
+        plan[4 * b + 0] = H.blk_A[(size_t)b];
+        plan[4 * b + 1] = H.blk_B[(size_t)b];
+        plan[4 * b + 2] = H.blk_narrow[(size_t)b];
+        plan[4 * b + 3] = H.blk_count[(size_t)b];
+    }
     return TFBS_OK;
 }
 

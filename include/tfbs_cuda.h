@@ -316,6 +316,14 @@ int tfbs_debug_direct_lookup(const double *logodds, const int32_t *lens, int32_t
 int tfbs_debug_direct_motifs(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
                              const float *thr, uint8_t *is_direct);
 
+/* The COMPLETE plan a hits scan makes for a threshold vector (direct-path choice, block cut, block forms,
+ * every filter table), built on the host by the code the scan itself runs and reduced to checksums:
+ * out = {blocks, table words, FNV-1a of the filter tables + initial field values, FNV-1a of the block
+ * descriptors, motifs on the direct path, direct-path keys}; plan (optional, room for M blocks) =
+ * int32[blocks][4] {A, B, form, motifs}.  Pins the plan across refactorings and host thread counts. */
+int tfbs_debug_hits_plan_checksum(const double *logodds, const int32_t *lens, int32_t M, int32_t Lmax,
+                                  const float *thr, uint64_t out[6], int32_t *plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,8 +92,13 @@ def one_case(rng, case):
     assert cand[:, ~direct].sum() == 0
     # the table side of the real plan (form 4) must cover every hit of the motifs it keeps; form 3 (every
     # motif on the tables) must cover all of them
+    info_plan, real_plan = _lib.hits_plan_checksum_host(logodds, lens, thr)   # the scan's own (parallel) planner
+    assert info_plan["direct_motifs"] == info["motifs"] and info_plan["direct_keys"] == info["keys"]
     for form in (3, 4):
-        filt = _lib.hits_filter_host(logodds, lens, thr, form, codes)
+        filt, plan, _ = _lib.hits_filter_host(logodds, lens, thr, form, codes, with_plan=True)
+        if form == 4:
+            assert plan == real_plan, f"case {case}: parallel and sequential planners disagree"
+
         keep = np.ones(cnt, dtype=bool) if form == 3 else ~direct[mot]
         lost = int((filt[pos[keep], mot[keep], strand[keep]] == 0).sum())
         if lost:

@@ -761,6 +761,39 @@ def test_direct_path_is_chosen_per_motif(monkeypatch):
     assert left_short >= 10 and plan[-1][0] + plan[-1][1] <= 4
 
 
+def test_hits_plan_is_the_same_on_any_number_of_host_threads(monkeypatch):
+    """The complete plan of a threshold vector (tfbs_debug_hits_plan_checksum runs the scan's own
+    plan_hits_tables: direct-path choice, speculative block planning split by lane ranges over the host's
+    cores, the cut, every filter table) must not depend on how many threads built it, and its blocks must be
+    the ones the sequential route (choose_form, block after block: tfbs_debug_hits_filter form 4) cuts."""
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY", "TFBS_PLAN_THREADS"):
+        monkeypatch.delenv(v, raising=False)
+    rng = np.random.default_rng(77)
+    codes = np.zeros(40, dtype=np.uint8)
+    seen_forms = set()
+    for case in range(6):
+        M = (33, 64, 200, 300, 130, 97)[case]
+        logodds, lens = synth.pwm_library(100 + case, M, lmin=(6, 1, 6, 10, 25, 4)[case], lmax=(30, 14, 30, 32, 32, 20)[case],
+                                          alpha=(0.3, 0.3, 0.1, 1.0, 0.3, 0.1)[case])
+        if case == 3:
+            logodds = np.where(rng.random(logodds.shape) < 0.02, -np.inf, logodds)
+        fin = np.where(np.isinf(logodds), -20.0, logodds)
+        thr = synth.thresholds_for_rate(fin, lens, rate=(1e-4, 1e-4, 1e-3, 1e-4, 3e-3, 1e-2)[case], gc=0.5, seed=case, sample=10_000)
+        if case in (2, 5):
+            thr[3::11], thr[5::11], thr[7::11] = -np.inf, np.inf, np.nan
+        monkeypatch.delenv("TFBS_PLAN_THREADS", raising=False)
+        info, plan = _lib.hits_plan_checksum_host(logodds, lens, thr)
+        for threads in ("1", "3"):
+            monkeypatch.setenv("TFBS_PLAN_THREADS", threads)
+            assert _lib.hits_plan_checksum_host(logodds, lens, thr) == (info, plan), (case, threads)
+        _, seq_plan, _ = _lib.hits_filter_host(logodds, lens, thr, 4, codes, with_plan=True)
+        assert plan == seq_plan, case
+        assert sum(b[3] for b in plan) + info["direct_motifs"] == M
+        assert info["direct_motifs"] == int(_lib.direct_motifs_host(logodds, lens, thr).sum())
+        seen_forms |= {b[2] for b in plan}
+    assert seen_forms == {0, 1, 2}       # wide, narrow and sticky blocks all occurred
+
+
 def test_hits_table_capacity_covers_any_per_threshold_plan():
     """The device tables are sized at upload for 32-motif blocks of the whole length-sorted library; a
     per-threshold plan may start block i at a SHORTER motif, whose table can be the larger one (24 columns:
