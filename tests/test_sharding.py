@@ -78,6 +78,12 @@ def test_ordered_concatenation_of_sorted_shards_equals_global_sort():
     buf = np.empty(want.size + 5, dtype=_lib.HIT_DTYPE)
     got = sharding.concat_sorted_shards(big, 50, out=buf, threads=4)
     assert got.base is not None and np.array_equal(got, want)
+    # motif boundaries by vectorised binary search on the strided field (no copy of the column): every
+    # motif present, some absent, all absent, one row
+    for col in (big[0], big[0][big[0]["motif"] % 3 == 0], big[0][:1], big[0][:0]):
+        if col.size:
+            assert np.array_equal(sharding._motif_bounds(col["motif"], 50), np.searchsorted(col["motif"], np.arange(51)))
+    assert np.array_equal(sharding.concat_sorted_shards([big[0][:0], big[1]], 50), big[1])
     assert np.array_equal(sharding.concat_sorted_shards(big, 50, threads=1), want)
     with pytest.raises(ValueError):
         sharding.concat_sorted_shards(big, 50, out=buf[:10])
