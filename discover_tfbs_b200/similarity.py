@@ -26,28 +26,35 @@ for _i, _b in enumerate(b"ACGT"):
 _ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def _murmur3_rows(keys: np.ndarray, seed: int = 39) -> np.ndarray:
-    """MurmurHash3_x86_32 of every row of a uint8 matrix [N, k] (vectorised)."""
-    n, k = keys.shape
+# ASCII bytes of 4 consecutive bases as one little-endian uint32 (the 4-byte block MurmurHash3 consumes),
+# indexed by their 2-bit codes with the FIRST base in the two most significant bits (k-mer code order)
+_BLOCK4 = np.zeros(256, dtype=np.uint32)
+for _x in range(256):
+    _BLOCK4[_x] = sum(int(_ASCII[(_x >> (2 * (3 - _j))) & 3]) << (8 * _j) for _j in range(4))
+
+
+def _murmur3_kmers(codes: np.ndarray, k: int, seed: int = 39) -> np.ndarray:
+    """MurmurHash3_x86_32 of the ASCII spelling of every k-mer given as a 2-bit code (first base most
+    significant), vectorised; equals mmh3.hash(kmer_string, seed) as an unsigned 32-bit value
+    (reference: utils.py:1259-1269).  The 4-byte blocks come from a 256-entry table, the k-mer strings are
+    never materialised."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint32).reshape(-1)
     c1, c2 = np.uint32(0xCC9E2D51), np.uint32(0x1B873593)
-    h = np.full(n, seed, dtype=np.uint32)
+    h = np.full(codes.size, seed, dtype=np.uint32)
+
+    def rotl(x, r):
+        return (x << np.uint32(r)) | (x >> np.uint32(32 - r))
+
     with np.errstate(over="ignore"):
-        def rotl(x, r):
-            return (x << np.uint32(r)) | (x >> np.uint32(32 - r))
-        for i in range(0, k - k % 4, 4):
-            blk = keys[:, i:i + 4].astype(np.uint32)
-            kk = blk[:, 0] | (blk[:, 1] << np.uint32(8)) | (blk[:, 2] << np.uint32(16)) | (blk[:, 3] << np.uint32(24))
+        for i in range(0, k - k % 4, 4):                       # bases i .. i+3 of the k-mer
+            kk = _BLOCK4[(codes >> np.uint32(2 * (k - 4 - i))) & np.uint32(255)]
             kk = rotl(kk * c1, 15) * c2
             h = rotl(h ^ kk, 13) * np.uint32(5) + np.uint32(0xE6546B64)
         t = k % 4
-        if t:
-            tail = keys[:, k - t:].astype(np.uint32)
-            kk = np.zeros(n, dtype=np.uint32)
-            if t >= 3:
-                kk ^= tail[:, 2] << np.uint32(16)
-            if t >= 2:
-                kk ^= tail[:, 1] << np.uint32(8)
-            kk ^= tail[:, 0]
+        if t:                                                   # tail: bases k-t .. k-1, low bytes first
+            kk = np.zeros(codes.size, dtype=np.uint32)
+            for j in range(t):
+                kk |= _ASCII[(codes >> np.uint32(2 * (t - 1 - j))) & np.uint32(3)].astype(np.uint32) << np.uint32(8 * j)
             h ^= rotl(kk * c1, 15) * c2
         h ^= np.uint32(k)
         h ^= h >> np.uint32(16)
@@ -59,7 +66,7 @@ def _murmur3_rows(keys: np.ndarray, seed: int = 39) -> np.ndarray:
 
 
 def _csr_unique(rows: np.ndarray):
-    """Per-row sorted unique values + counts of a 2-D integer array -> (values, counts, offsets)."""
+    """Per-row sorted unique values + counts of a 2-D integer array -> (values, counts, per-row sizes)."""
     srt = np.sort(rows, axis=1)
     first = np.ones(srt.shape, dtype=bool)
     first[:, 1:] = srt[:, 1:] != srt[:, :-1]
@@ -67,14 +74,26 @@ def _csr_unique(rows: np.ndarray):
     values = srt.reshape(-1)[flat_first]
     starts = np.flatnonzero(flat_first)
     counts = np.diff(np.append(starts, flat_first.size))
-    per_row = first.sum(axis=1)
-    off = np.zeros(rows.shape[0] + 1, dtype=np.int64)
-    np.cumsum(per_row, out=off[1:])
-    return values, counts, off
+    return values, counts, first.sum(axis=1)
 
 
 def acgt_only(seqs) -> bool:
     return all(not s.strip("ACGT") for s in seqs)
+
+
+def _scatter_rows(dst_off: np.ndarray, idx: np.ndarray, sizes: np.ndarray, *pairs):
+    """Copy the CSR rows of one length group (row r of the group = sequence idx[r], `sizes[r]` entries, rows
+    laid end to end in every `src`) to their places in the whole-set arrays: pairs = (dst, src), ..."""
+    if idx.size and int(idx[-1]) - int(idx[0]) + 1 == idx.size:       # a run of consecutive sequences: one block
+        lo = int(dst_off[idx[0]])
+        for dst, src in pairs:
+            dst[lo: lo + src.size] = src
+        return
+    start = np.zeros(sizes.size, dtype=np.int64)
+    np.cumsum(sizes[:-1], out=start[1:])
+    where = np.repeat(dst_off[idx] - start, sizes) + np.arange(int(sizes.sum()), dtype=np.int64)
+    for dst, src in pairs:
+        dst[where] = src
 
 
 def prepare(seqs, k: int) -> dict:
@@ -82,8 +101,10 @@ def prepare(seqs, k: int) -> dict:
     CSR layout tfbs_similarity_sums expects (sequence order preserved)."""
     S = len(seqs)
     lens = np.array([len(s) for s in seqs], dtype=np.int64)
-    out_words, out_counts, out_hash = [None] * S, [None] * S, [None] * S
     nk = np.maximum(lens - k + 1, 0).astype(np.int32)
+    groups = []
+    wsize = np.zeros(S, dtype=np.int64)
+    hsize = np.zeros(S, dtype=np.int64)
     for n in np.unique(lens):
         idx = np.flatnonzero(lens == n)
         m = int(n) - k + 1
@@ -96,24 +117,22 @@ def prepare(seqs, k: int) -> dict:
         for j in range(k):
             kmer |= codes[:, j:j + m] << np.uint32(2 * (k - 1 - j))
             rc |= (np.uint32(3) - codes[:, k - 1 - j: k - 1 - j + m]) << np.uint32(2 * (k - 1 - j))
-        w, c, woff = _csr_unique(kmer)
-        canon = np.minimum(kmer, rc).reshape(-1)
-        keys = np.empty((canon.size, k), dtype=np.uint8)
-        for j in range(k):
-            keys[:, j] = _ASCII[(canon >> np.uint32(2 * (k - 1 - j))) & np.uint32(3)]
-        hv, _, hoff = _csr_unique(_murmur3_rows(keys).reshape(idx.size, m))
-        for r, i in enumerate(idx):
-            out_words[i] = w[woff[r]:woff[r + 1]]
-            out_counts[i] = c[woff[r]:woff[r + 1]]
-            out_hash[i] = hv[hoff[r]:hoff[r + 1]]
-    woff = np.zeros(S + 1, dtype=np.int32)
-    hoff = np.zeros(S + 1, dtype=np.int32)
-    np.cumsum([a.size for a in out_words], out=woff[1:])
-    np.cumsum([a.size for a in out_hash], out=hoff[1:])
-    return {"words": np.concatenate(out_words).astype(np.uint32) if S else np.zeros(0, np.uint32),
-            "counts": np.concatenate(out_counts).astype(np.uint16) if S else np.zeros(0, np.uint16),
-            "woff": woff, "nk": nk,
-            "hash": np.concatenate(out_hash).astype(np.uint32) if S else np.zeros(0, np.uint32), "hoff": hoff}
+        w, c, wn = _csr_unique(kmer)
+        hv, _, hn = _csr_unique(_murmur3_kmers(np.minimum(kmer, rc), k).reshape(idx.size, m))
+        wsize[idx], hsize[idx] = wn, hn
+        groups.append((idx, w, c, wn, hv, hn))
+    woff = np.zeros(S + 1, dtype=np.int64)
+    hoff = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum(wsize, out=woff[1:])
+    np.cumsum(hsize, out=hoff[1:])
+    words = np.zeros(int(woff[-1]), dtype=np.uint32)
+    counts = np.zeros(int(woff[-1]), dtype=np.uint16)
+    hashes = np.zeros(int(hoff[-1]), dtype=np.uint32)
+    for idx, w, c, wn, hv, hn in groups:
+        _scatter_rows(woff, idx, wn, (words, w), (counts, c))
+        _scatter_rows(hoff, idx, hn, (hashes, hv))
+    return {"words": words, "counts": counts, "woff": woff.astype(np.int32), "nk": nk,
+            "hash": hashes, "hoff": hoff.astype(np.int32)}
 
 
 def similarity_columns_gpu(ctx, seqs, true_seqs):

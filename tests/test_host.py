@@ -158,6 +158,36 @@ def test_similarity_vs_reference_golden(golden):
         assert abs(got[0] - pas) < 1e-12 and abs(got[1] - pps) < 1e-12
 
 
+def test_similarity_host_preparation_equals_the_scalar_restatement():
+    """The vectorised host preparation the all-pairs kernel is fed with (k-mer multisets and canonical
+    MurmurHash3 sets in CSR layout, discover_tfbs_b200/similarity.py:prepare) against the scalar restatement
+    pinned to the reference's outputs above: mixed lengths (rows are scattered back into sequence order),
+    every k mod 4 (block and tail paths of the hash), duplicated k-mers."""
+    from collections import Counter
+
+    from discover_tfbs_b200 import similarity as product
+    from oracle import similarity_oracle as oracle
+
+    rng = np.random.default_rng(8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for k, lo, hi, n in ((3, 5, 9, 30), (4, 20, 20, 16), (5, 18, 40, 40), (6, 12, 13, 25), (7, 30, 31, 20), (8, 200, 204, 12),
+                         (9, 9, 33, 20), (13, 13, 14, 6)):
+        seqs = [bytes(acgt[rng.integers(0, 4 if i % 3 else 2, size=int(rng.integers(lo, hi + 1)))]).decode() for i in range(n)]
+        p = product.prepare(seqs, k)
+        assert p["woff"].dtype == np.int32 and p["hoff"].dtype == np.int32 and p["counts"].dtype == np.uint16
+        assert np.array_equal(p["nk"], [len(s) - k + 1 for s in seqs])
+        for i, sq in enumerate(seqs):
+            want_hash = np.array(sorted({oracle._canonical_hash(sq[j:j + k]) for j in range(len(sq) - k + 1)}), dtype=np.uint32)
+            assert np.array_equal(p["hash"][p["hoff"][i]: p["hoff"][i + 1]], want_hash), (k, i)
+            wc = Counter(sq[j:j + k] for j in range(len(sq) - k + 1))
+            code = {w: sum("ACGT".index(ch) << (2 * (k - 1 - j)) for j, ch in enumerate(w)) for w in wc}
+            order = sorted(wc, key=code.get)
+            assert np.array_equal(p["words"][p["woff"][i]: p["woff"][i + 1]], [code[w] for w in order]), (k, i)
+            assert np.array_equal(p["counts"][p["woff"][i]: p["woff"][i + 1]], [wc[w] for w in order]), (k, i)
+    with pytest.raises(ValueError):
+        product.prepare(["ACGT"], 6)
+
+
 def test_parse_fasta_and_locations(tmp_path):
     p = tmp_path / "x.fasta"
     p.write_text(">chr1:5-17(-) extra\nACGT\nTT GG\n>b\n\nAC\n")
