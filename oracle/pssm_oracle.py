@@ -1,10 +1,17 @@
 """CPU oracle for the PWM path — Biopython PSSM semantics.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the arithmetic restated here lives in Biopython (Bio/motifs/matrix.py,
+PARITY STATUS: the arithmetic restated here lives in Biopython (Bio/motifs/matrix.py,
 Bio/motifs/_pwm.c), which the reference never calls, which is not installed
-here and whose version the reference does not pin.  The restatement follows SURVEY.md
-Appendix A.1; it is cross-checked three ways in tests/test_oracle.py (C loop, NumPy
-gather-sum in float64, and the identity rev(seq) == fwd(revcomp(seq))[::-1]).
+here and whose version the reference does not pin — there is no run of Biopython behind this file.
+The restatement follows SURVEY.md Appendix A.1; it is cross-checked three ways in
+tests/test_oracle.py (C loop, NumPy gather-sum in float64, and the identity
+rev(seq) == fwd(revcomp(seq))[::-1]) and PINNED TO THE PUBLISHED KNOWN-ANSWER EXAMPLE of the
+Biopython Tutorial (Bio.motifs chapter): counts -> normalize -> log_odds -> calculate (22 float32
+scores to the 8 printed decimals) -> search -> max / min / mean / std
+(tests/golden/biopython_tutorial.json, which states how the vectors were obtained offline;
+tests/test_oracle.py::test_pwm_oracle_reproduces_the_biopython_tutorial).  One published example is not
+a run of the library: semantics the example does not exercise (-inf entries, lower case, N handling)
+rest on the restatement alone.
 """
 import math
 

@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def biopython_tutorial():
+    """Published known-answer vectors of the Bio.motifs example (tests/golden/biopython_tutorial.json)."""
+    with open(os.path.join(ROOT, "tests", "golden", "biopython_tutorial.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
 def ctx():
     """One libtfbs_cuda context on cuda:0.  No skip-on-missing: a GPU test without the CUDA
     library or device must fail loudly."""

@@ -993,6 +993,30 @@ def test_hits_library_of_short_motifs_only_runs_without_a_table_block(ctx, monke
     lib.close()
 
 
+def test_pssm_calculate_and_search_reproduce_the_biopython_tutorial(ctx, biopython_tutorial):
+    """The CUDA path against the PUBLISHED outputs of Biopython itself (tests/golden/biopython_tutorial.json):
+    PSSM.calculate (dense mode) gives the tutorial's 22 scores within SCORE_ATOL — the oracle itself matches
+    all 8 printed decimals, tests/test_oracle.py — and PSSM.search (hits mode, re-scored in the oracle's
+    arithmetic) the tutorial's hits: both strands, negative reverse positions, order, scores to 3 decimals."""
+    from discover_tfbs_b200 import pssm
+
+    t = biopython_tutorial
+    b = t["example_background"]
+    counts = np.array(t["counts_ACGT_by_column"], dtype=np.float64)
+    m = pssm.PSSM(pssm.log_odds(pssm.normalize(counts, b["pseudocounts"]), b["background"]), ctx)
+    scores = m.calculate(b["test_seq"])
+    want = np.array([float(v) for v in b["calculate_float32_8dec"]])
+    assert scores.dtype == np.float32 and scores.shape == want.shape and np.abs(scores - want).max() <= SCORE_ATOL
+    hits = [[int(p), "%5.3f" % s] for p, s in m.search(b["test_seq"], threshold=b["search_threshold"])]
+    assert hits == b["search_position_score_3dec"]
+    fwd_only = [[int(p), "%5.3f" % s] for p, s in m.search(b["test_seq"], threshold=b["search_threshold"], both=False)]
+    assert fwd_only == [h for h in b["search_position_score_3dec"] if h[0] >= 0]
+    # hits mode re-scores in the oracle's arithmetic: with a threshold below every score it returns all 22
+    # windows, and their float32 scores print exactly as the tutorial's calculate() output
+    every = list(m.search(b["test_seq"], threshold=-1e30, both=False))
+    assert [p for p, _ in every] == list(range(22)) and ["%.8f" % s for _, s in every] == b["calculate_float32_8dec"]
+
+
 @pytest.mark.parametrize("chunks", [0, 3])
 def test_hits_direct_path_is_chosen_per_motif(ctx, chunks, monkeypatch):
     """Heterogeneous thresholds: most of the library at a sparse rate, every 5th short motif at a dense one,

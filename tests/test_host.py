@@ -188,6 +188,28 @@ def test_similarity_host_preparation_equals_the_scalar_restatement():
         product.prepare(["ACGT"], 6)
 
 
+def test_pssm_host_functions_reproduce_the_biopython_tutorial(biopython_tutorial):
+    """The product's normalize / log_odds / max / min (host side of pssm.PSSM) against the published
+    Bio.motifs example (tests/golden/biopython_tutorial.json); calculate / search are the GPU test
+    tests/test_gpu_parity.py::test_pssm_calculate_and_search_reproduce_the_biopython_tutorial."""
+    from discover_tfbs_b200 import pssm
+
+    t = biopython_tutorial
+    counts = np.array(t["counts_ACGT_by_column"], dtype=np.float64)
+    u, b = t["example_uniform"], t["example_background"]
+    pwm = pssm.normalize(counts, u["pseudocounts"])
+    assert np.array_equal(np.round(pwm.T, 2), np.array(u["pwm_2dec_rows_ACGT"]))
+    assert np.array_equal(np.round(pssm.log_odds(pwm).T, 2), np.array(u["pssm_2dec_rows_ACGT"]))
+    pwm = pssm.normalize(counts, b["pseudocounts"])
+    assert np.array_equal(np.round(pwm.T, 2), np.array(b["pwm_2dec_rows_ACGT"]))
+    lo = pssm.log_odds(pwm, b["background"])
+    assert np.array_equal(np.round(lo.T, 2), np.array(b["pssm_2dec_rows_ACGT"]))
+    m = pssm.PSSM(lo)
+    assert "%4.2f" % m.max == b["max_2dec"] and "%4.2f" % m.min == b["min_2dec"]
+    rc = m.reverse_complement().matrix
+    assert np.array_equal(rc, lo[::-1, ::-1])
+
+
 def test_parse_fasta_and_locations(tmp_path):
     p = tmp_path / "x.fasta"
     p.write_text(">chr1:5-17(-) extra\nACGT\nTT GG\n>b\n\nAC\n")

@@ -133,3 +133,43 @@ def test_openmp_forms_equal_the_plain_loops():
     for m in (0, 5):
         mat = lo[m, : lens[m]]
         assert np.array_equal(po.calculate(seq, mat), po.calculate(seq, mat, threads=0), equal_nan=True)
+
+
+def _tutorial_counts(t):
+    counts = np.zeros((5, 4))
+    for inst in t["instances"]:
+        for j, ch in enumerate(inst):
+            counts[j, "ACGT".index(ch)] += 1
+    assert counts.tolist() == t["counts_ACGT_by_column"]
+    return counts
+
+
+def test_pwm_oracle_reproduces_the_biopython_tutorial(biopython_tutorial):
+    """Known-answer test against the PUBLISHED outputs of the dependency the PWM path replaces (Biopython
+    Tutorial, Bio.motifs chapter; provenance in tests/golden/biopython_tutorial.json): counts -> normalize
+    (scalar and per-letter pseudocounts) -> log_odds (uniform and explicit background) -> calculate (all 22
+    float32 scores to the 8 printed decimals) -> search (both strands, negative reverse positions, order)
+    -> max / min / mean / std."""
+    t = biopython_tutorial
+    counts = _tutorial_counts(t)
+    u = t["example_uniform"]
+    pwm = po.normalize(counts, u["pseudocounts"])
+    assert np.array_equal(np.round(pwm.T, 2), np.array(u["pwm_2dec_rows_ACGT"]))
+    assert np.array_equal(np.round(po.log_odds(pwm).T, 2), np.array(u["pssm_2dec_rows_ACGT"]))
+    b = t["example_background"]
+    pwm = po.normalize(counts, b["pseudocounts"])
+    assert np.array_equal(np.round(pwm.T, 2), np.array(b["pwm_2dec_rows_ACGT"]))
+    pssm = po.log_odds(pwm, b["background"])
+    assert np.array_equal(np.round(pssm.T, 2), np.array(b["pssm_2dec_rows_ACGT"]))
+    seq = np.frombuffer(b["test_seq"].encode(), dtype=np.uint8)
+    scores = po.calculate(seq, pssm)
+    assert scores.dtype == np.float32 and ["%.8f" % v for v in scores] == b["calculate_float32_8dec"]
+    assert np.array_equal(po.calculate_numpy(seq, pssm), scores)
+    hits = [[int(p), "%5.3f" % s] for p, s in po.search(seq, pssm, b["search_threshold"])]
+    assert hits == b["search_position_score_3dec"]
+    assert "%4.2f" % pssm.max(axis=1).sum() == b["max_2dec"] and "%4.2f" % pssm.min(axis=1).sum() == b["min_2dec"]
+    # PositionSpecificScoringMatrix.mean / .std: p = background * 2^logodds per letter and column
+    bg = np.array([b["background"][ch] for ch in "ACGT"])
+    p = bg[None, :] * np.exp2(pssm)
+    sx, sxx = (p * pssm).sum(axis=1), (p * pssm * pssm).sum(axis=1)
+    assert "%0.2f" % sx.sum() == b["mean_2dec"] and "%0.2f" % np.sqrt((sxx - sx * sx).sum()) == b["std_2dec"]
