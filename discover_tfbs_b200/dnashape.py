@@ -201,8 +201,11 @@ def to_reference_float64(values: np.ndarray) -> np.ndarray:
     two decimals and Python parsed them back (float("%.2f" % v)).  Exact: a float32 times 100 is
     exactly representable in float64, so rint() performs the same round-half-even on the exact
     binary value that printf does, and c / 100 is the correctly rounded double of the decimal."""
-    v = np.asarray(values, dtype=np.float64)
-    return np.rint(v * 100.0) / 100.0
+    v = np.array(values, dtype=np.float64)   # one fresh float64 copy, then in place (no further temporaries)
+    np.multiply(v, 100.0, out=v)
+    np.rint(v, out=v)
+    np.divide(v, 100.0, out=v)
+    return v
 
 
 def format_tokens(track: np.ndarray, n_tokens: int) -> list:

@@ -309,11 +309,13 @@ def build_feature_table(infasta: str, truefasta: str, genome_wide_shape_data=Non
 
     for name, values in cols.items():
         tf_data[name] = values
+    blocks = [tf_data]
     for shape, rows in shape_rows.items():
         # json_normalize in the reference only creates the keys that exist in some row
-        keep = [w for w in range(rows.shape[1]) if not np.isnan(rows[:, w]).all()] if len(locs) else []
-        block = pd.DataFrame({f"{shape}_{w + 1:02d}": rows[:, w] for w in keep}, index=tf_data.index)
-        tf_data = tf_data.join(block)
+        keep = np.flatnonzero(~np.isnan(rows).all(axis=0)) if len(locs) else np.zeros(0, dtype=np.int64)
+        blocks.append(pd.DataFrame(rows[:, keep], columns=[f"{shape}_{w + 1:02d}" for w in keep], index=tf_data.index))
+    if len(blocks) > 1:
+        tf_data = pd.concat(blocks, axis=1)   # one concatenation instead of a join per shape
     print(strftime("%x %X | Finished building feature table"))
     return tf_data
 
