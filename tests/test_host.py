@@ -846,6 +846,45 @@ def test_hits_plan_is_the_same_on_any_number_of_host_threads(monkeypatch):
     assert seen_forms == {0, 1, 2}       # wide, narrow and sticky blocks all occurred
 
 
+@pytest.mark.parametrize("rate", [1e-4, 1e-3])
+def test_bench_library_plan_never_loses_a_hit_on_the_host(rate, monkeypatch):
+    """The bench workload's library (800 PWMs, L 6-30, seed 39) at the thresholds of the GPU rate sweeps: the plan a scan makes
+    (direct path for the short motifs at 1e-4, 8-bit narrow blocks for most of the rest) replayed on the host
+    over 30 kb — direct keys == oracle hits for the motifs of <= 12 columns, table candidates (form 4) cover
+    every oracle hit of the motifs left on the tables, and the parallel planner's blocks are the ones the
+    sequential route cuts."""
+    from oracle import pssm_oracle as po
+
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY", "TFBS_PLAN_THREADS"):
+        monkeypatch.delenv(v, raising=False)
+    logodds, lens = synth.pwm_library(39, 800, 6, 30)
+    # thresholds of that library as the rate sweeps on the GPU used them (profiles/hits_rate_quick.py); computing
+    # them here (synth.thresholds_for_rate, 100 000 samples x 800 motifs) would take half a minute
+    thr = np.load(os.path.join(ROOT, "profiles", "hits_rate_thresholds.npz"))[f"{rate:g}"]
+    assert thr.shape == (800,) and thr.dtype == np.float32
+    seq = synth.genome(39, 0, 30_000, gc=0.41, n_runs=False, lowercase=False)
+    codes = np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), seq).astype(np.uint8)
+    pos, mot, strand, score, cnt = po.search_library(seq, logodds, lens, thr, threads=0)
+    info, plan = _lib.hits_plan_checksum_host(logodds, lens, thr)
+    direct = _lib.direct_motifs_host(logodds, lens, thr)
+    filt, seq_plan, _ = _lib.hits_filter_host(logodds, lens, thr, 4, codes, with_plan=True)
+    assert plan == seq_plan and sum(b[3] for b in plan) + int(direct.sum()) == 800
+    assert any(b[2] == 1 for b in plan)                               # narrow blocks in the plan
+    if rate == 1e-4:
+        assert direct.sum() == int((lens <= 14).sum()) == info["direct_motifs"] and info["direct_keys"] > 10**6
+    on_direct = direct[mot]
+    assert filt[pos[~on_direct], mot[~on_direct], strand[~on_direct]].all() and filt[:, direct].sum() == 0
+    cand, _ = _lib.direct_lookup_host(logodds, lens, thr, codes)
+    want = np.zeros_like(cand)
+    want[pos, mot, strand] = 1
+    inside = np.arange(seq.size)[:, None] + lens[None, :] <= seq.size
+    exact = direct & (lens <= 12)
+    assert np.array_equal(cand[:, exact][inside[:, exact]], want[:, exact][inside[:, exact]])
+    longer = direct & (lens > 12)
+    assert np.all(cand[:, longer][inside[:, longer]] >= want[:, longer][inside[:, longer]])
+    assert cnt > 2000
+
+
 def test_hits_table_capacity_covers_any_per_threshold_plan():
     """The device tables are sized at upload for 32-motif blocks of the whole length-sorted library; a
     per-threshold plan may start block i at a SHORTER motif, whose table can be the larger one (24 columns:
