@@ -7,7 +7,7 @@ window's score, +-inf, NaN) and sequences with homopolymer runs.  For every case
   * a subset of the table filter's candidates for every motif the plan keeps on the tables (form 4) and
     for every motif when all stay on the tables (form 3).
 
-Usage: python profiles/fuzz_hits_host.py [--cases 200] [--seed 1]   (oracle = test infrastructure)."""
+Usage: python tests/fuzz_hits_host.py [--cases 200] [--seed 1]   (oracle = test infrastructure)."""
 import argparse
 import os
 import sys
