@@ -885,6 +885,22 @@ def test_bench_library_plan_never_loses_a_hit_on_the_host(rate, monkeypatch):
     assert cnt > 2000
 
 
+def test_host_fuzz_campaign_cases(monkeypatch):
+    """A few cases of tests/fuzz_hits_host.py (random libraries with -inf entries, thresholds set exactly on
+    window scores, +-inf / NaN / loose thresholds, homopolymer runs): the plan a scan makes never loses an
+    oracle hit.  The full campaign (hundreds of cases) is run by hand: python tests/fuzz_hits_host.py."""
+    import importlib.util
+
+    for v in ("TFBS_HITS_DIRECT", "TFBS_HITS_NARROW", "TFBS_HITS_STICKY", "TFBS_PLAN_THREADS"):
+        monkeypatch.delenv(v, raising=False)
+    spec = importlib.util.spec_from_file_location("fuzz_hits_host", os.path.join(ROOT, "tests", "fuzz_hits_host.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(2026)
+    hits = sum(fuzz.one_case(rng, case)[0] for case in range(6))
+    assert hits > 10_000
+
+
 def test_hits_table_capacity_covers_any_per_threshold_plan():
     """The device tables are sized at upload for 32-motif blocks of the whole length-sorted library; a
     per-threshold plan may start block i at a SHORTER motif, whose table can be the larger one (24 columns:
