@@ -28,7 +28,6 @@ namespace {
 constexpr int kScanThreads = 1024;                   // one persistent CTA per SM
 constexpr int kPosPerThread = 4;
 constexpr int kTile = kScanThreads * kPosPerThread;  // 4096 window starts per sub-tile
-constexpr int kMaxGroups = (TFBS_MAX_MOTIF_LEN + 2) / 3;  // 11
 
 struct ScanParams {
     const uint32_t *packed;
