@@ -5,6 +5,8 @@
 #include <random>
 extern "C" int tfbs_debug_hits_plan_checksum(const double*, const int32_t*, int32_t, int32_t, const float*, uint64_t*, int32_t*);
 extern "C" int tfbs_debug_hits_filter(const double*, const int32_t*, int32_t, int32_t, const float*, int32_t, const uint8_t*, int64_t, uint8_t*, int32_t*, double*, int32_t*);
+extern "C" int tfbs_debug_dense_tables(const double*, int32_t, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int64_t);
+extern "C" int tfbs_debug_swar4(uint32_t, uint32_t*, uint32_t*);
 extern "C" int tfbs_debug_direct_lookup(const double*, const int32_t*, int32_t, int32_t, const float*, const uint8_t*, int64_t, uint8_t*, int64_t*);
 int main(){
   std::mt19937 rng(7);
@@ -22,6 +24,17 @@ int main(){
     std::vector<uint8_t> cand((size_t)n*M*2); std::vector<double> exp(M); int32_t nb=0; int64_t info[4];
     int rc2=0; for(int form=0; form<=4; form++) rc2|=tfbs_debug_hits_filter(lo.data(),lens.data(),M,Lmax,thr.data(),form,codes.data(),n,cand.data(),plan.data(),exp.data(),&nb);
     int rc3=tfbs_debug_direct_lookup(lo.data(),lens.data(),M,Lmax,thr.data(),codes.data(),n,cand.data(),info);
+    // dense-scan fixed-point tables of every motif (tfbs_dense_quantise, run at library upload)
+    int rc4 = 0;
+    std::vector<int32_t> ent((size_t)11 * 256 * 2);
+    for (int m = 0; m < M; m += (M > 100 ? 7 : 1)) {
+      std::vector<double> one((size_t)lens[m] * 4);
+      for (int j = 0; j < lens[m]; j++) for (int b = 0; b < 4; b++) one[(size_t)j * 4 + b] = lo[((size_t)m * Lmax + j) * 4 + b];
+      int32_t K, G, e, neg;
+      rc4 |= tfbs_debug_dense_tables(one.data(), lens[m], &K, &G, &e, &neg, ent.data(), (int64_t)ent.size());
+    }
+    uint32_t c8, v4; rc4 |= tfbs_debug_swar4(0x4E544341u ^ (uint32_t)rng(), &c8, &v4);
+    rc2 |= rc4;
     printf("case %d M %d L %d-%d: rc %d %d %d blocks %llu direct %llu keys %llu\n",cs,M,lmin,lmax,rc,rc2,rc3,(unsigned long long)out[0],(unsigned long long)out[4],(unsigned long long)out[5]);
   }
   return 0; }
